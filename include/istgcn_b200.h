@@ -1,0 +1,169 @@
+/* istgcn_b200 -- C ABI of the B200-native IST-GCN hot path (libistgcn_b200.so).
+ *
+ * Every entry point is `extern "C"`, takes plain device pointers + sizes + a CUDA stream and
+ * returns 0 on success (a cudaError_t value, or a negative ISTGCN_E_* code for bad arguments;
+ * istgcn_last_error() holds the text).  Nothing is allocated or freed inside: the caller owns
+ * every buffer.  All activations are fp32, channels-last: a tensor the reference holds as
+ * (N*M, C, T, V) (net/st_gcnold.py:80) lives here as rows[(n*T + t)*V + v][C].
+ *
+ * The reference is pure Python/PyTorch, so there is no FFI to mirror; each function below
+ * names the reference lines whose PyTorch ops it replaces.  The Python binding that the
+ * reference-side drop-in (ist-gcn_b200/net/*.py) uses is ist-gcn_b200/istgcn/_lib.py (ctypes);
+ * INTEGRATION.md shows the stub.
+ *
+ * Sparse adjacency ("SpA" arguments).  A_eff = A*imp (+ A2*imp2 + A3*imp3) has a static
+ * non-zero pattern.  The caller passes the values of the nnz entries in
+ * canonical order (sorted by k, v, w) in `vals[nnz]` and four index arrays built once:
+ *   dst_ptr[K*V+1], dst_src[nnz], dst_id[nnz]   entries grouped by destination (k, w):
+ *                                               source joint v and canonical id
+ *   src_ptr[V+1],   src_kw[nnz],  src_id[nnz]   entries grouped by source v: k*V+w and id
+ */
+#ifndef ISTGCN_B200_H
+#define ISTGCN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* istgcn_stream_t; /* cudaStream_t */
+
+#define ISTGCN_E_SHAPE (-1)   /* unsupported shape / channel count            */
+#define ISTGCN_E_ARG   (-2)   /* null pointer, bad flag                       */
+#define ISTGCN_E_ARCH  (-3)   /* device is not sm_100                         */
+
+/* math mode of the tensor-core GEMMs */
+#define ISTGCN_MATH_TF32   0  /* one TF32 pass (fast mode, <=2e-2 budget)     */
+#define ISTGCN_MATH_3XTF32 1  /* error-compensated split, fp32-grade (<=1e-4) */
+
+const char* istgcn_last_error(void);
+int istgcn_version(void);
+/* 0 when the current device can run the library (compute capability 10.x) */
+int istgcn_check_device(void);
+
+/* ---- data_bn: nn.BatchNorm1d(V*C) on (N*M, V*C, T) + the two permutes ------------------
+ * reference: net/st_gcnold.py:74-80.  x is the model input (N, C, T, V, M) contiguous.
+ * stats: per channel ch = v*C + c over (N, M, T), written as double sum[VC], sumsq[VC]
+ * (must be zeroed by the caller).  apply: y rows[((n*M+m)*T + t)*V + v][C].               */
+int istgcn_data_bn_stats(const float* x, double* sum, double* sumsq,
+                         int N, int C, int T, int V, int M, istgcn_stream_t s);
+int istgcn_data_bn_apply(const float* x, const float* scale, const float* shift, float* y,
+                         int N, int C, int T, int V, int M, istgcn_stream_t s);
+/* backward of the affine parameters only (the network input needs no gradient):
+ * dgamma[ch] = sum g*xhat, dbeta[ch] = sum g, with g rows[...][C] channels-last.           */
+int istgcn_data_bn_bwd(const float* x, const float* g, const float* mean, const float* rstd,
+                       double* dgamma, double* dbeta, int N, int C, int T, int V, int M,
+                       istgcn_stream_t s);
+
+/* ---- BatchNorm bookkeeping (nn.BatchNorm2d train/eval; st_gcnold.py:165,174) -----------
+ * From double sum/sumsq over `count` elements: mean, biased var -> scale = gamma*rstd,
+ * shift = beta - mean*scale; running stats updated with momentum (unbiased var) when
+ * running_mean != NULL.                                                                    */
+int istgcn_bn_finalize(const double* sum, const double* sumsq, double count,
+                       const float* gamma, const float* beta, float* running_mean,
+                       float* running_var, float momentum, float eps, float* scale,
+                       float* shift, float* mean, float* rstd, int C, istgcn_stream_t s);
+/* eval mode: scale/shift from the running statistics */
+int istgcn_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                          const float* running_var, float eps, float* scale, float* shift,
+                          int C, istgcn_stream_t s);
+/* backward coefficients: with sg = sum g, sgx = sum g*xhat (double) over `count` elements,
+ * dx = p*g + q*x + r per channel; also dgamma = sgx, dbeta = sg.                           */
+int istgcn_bn_bwd_coeffs(const double* sg, const double* sgx, double count, const float* gamma,
+                         const float* mean, const float* rstd, float* p, float* q, float* r,
+                         float* dgamma, float* dbeta, int C, istgcn_stream_t s);
+
+/* ---- fused graph convolution ------------------------------------------------------------
+ * reference: net/utils/tgcn.py:76-89 (conv1x1 to K*Cout, einsum 'nkctv,kvw->nctw') and
+ * net/utils/inceptionv2_gcn.py:64-89 (three einsums with A, A2, A3 == one with A_eff).
+ *   z[(f,w)][c] = sum_k sum_ci Wc[k*Cin+ci][c] * (sum_v A_eff[k][v][w] x[(f,v)][ci])
+ *                 + biasterm[w][c]
+ * Wc[K*Cin][Cout] is the conv weight regrouped (Wc[k*Cin+ci][c] = weight[k*Cout+c][ci]);
+ * biasterm[V][Cout] = sum_k bias[k*Cout+c] * colsum(A_eff[k])[w].  `frames` = N*M*T.
+ * stat_sum/stat_sumsq (double[Cout], caller-zeroed, may be NULL) receive the BatchNorm
+ * statistics of z.
+ * Temporal stride: with t_out > 0, output frame f = n*t_out + to reads input frame
+ * n*t_in + to*t_stride (and gin / add_in of the backward use the same mapping).  With K = 1
+ * and an identity adjacency this is the strided 1x1 convolution of the residual branch
+ * (net/st_gcnold.py:186-193); t_out = 0 means "same frames".                               */
+int istgcn_gcn_fwd(const float* x, const float* Wc, const float* biasterm, const float* vals,
+                   const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
+                   float* z, double* stat_sum, double* stat_sumsq,
+                   int frames, int V, int K, int Cin, int Cout,
+                   int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
+/* input gradient + adjacency gradient.  dz is formed on the fly from the BatchNorm-backward
+ * coefficients: dz = p[c]*g[r][c] + q[c]*z[r][c] + r0[c] (pass q = NULL to use g as dz).
+ *   gin[(f,v)][ci] = sum_k sum_w A_eff[k][v][w] (dz Wc_k^T)[(f,w)][ci]  (+ add_in if not NULL)
+ *   dvals[id] += sum_{f,ci} x[(f,v)][ci] * (dz Wc_k^T)[(f,w)][ci]       (caller-zeroed)     */
+int istgcn_gcn_bwd_x(const float* g, const float* z, const float* p, const float* q,
+                     const float* r0, const float* x, const float* Wc, const float* vals,
+                     const int* src_ptr, const int* src_kw, const int* src_id, int nnz,
+                     const float* add_in, float* gin, float* dvals,
+                     int frames, int V, int K, int Cin, int Cout,
+                     int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
+/* weight gradient: dWc[K*Cin][Cout] += X'^T dz, dbiasterm[V][Cout] += sum_f dz (both
+ * caller-zeroed fp32).                                                                     */
+int istgcn_gcn_bwd_w(const float* g, const float* z, const float* p, const float* q,
+                     const float* r0, const float* x, const float* vals,
+                     const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
+                     float* dWc, float* dbiasterm,
+                     int frames, int V, int K, int Cin, int Cout,
+                     int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
+
+/* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
+ *   a  = relu(z*scale1 + shift1)                       (tcn_start: BN + ReLU)
+ *   h1 = a Wd + bd                                     (conv_1x1_start, C -> b)
+ *   h2[to] = sum_tap Weff[tap] h1[to*stride + tap - 7] + beff   (tcn_1/2/3 merged: 15 taps,
+ *            Weff = imp0*W3x1 (+6) + imp1*W9x1 (+3) + imp2*W15x1, zero padding on h1)
+ *   u  = h2 Wu + bu                                    (conv_1x1_end, b -> C)
+ * Wd[C][bp], Weff[15][bp(in)][bp(out)], Wu[bp][C]; bp = b rounded up to a multiple of 8
+ * (padding columns/rows zero).  h1[(n,t,v)][bp] and h2[(n,to,v)][bp] are saved for backward.
+ * stats of u optional.                                                                     */
+int istgcn_tcn_fwd(const float* z, const float* scale1, const float* shift1, const float* Wd,
+                   const float* bd, const float* Weff, const float* beff, const float* Wu,
+                   const float* bu, float* h1, float* h2, float* u, double* stat_sum,
+                   double* stat_sumsq, int NM, int T, int V, int C, int bp, int stride,
+                   int math, istgcn_stream_t s);
+/* backward.  du = p2*gy + q2*u + r2 where gy = go * keep(dropout); writes g1 = d(loss)/d(bn1
+ * output) masked by the ReLU, accumulates sum g1 and sum g1*zhat (double[C], caller-zeroed)
+ * and all weight gradients (caller-zeroed fp32).  dh2_ws[(n,to,v)][bp] and dh1_ws[(n,t,v)][bp]
+ * are caller-provided scratch (fully overwritten).                                         */
+int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float* q2,
+                   const float* r2, const float* z, const float* scale1, const float* shift1,
+                   const float* mean1, const float* rstd1, const float* h1, const float* h2,
+                   const float* Wd, const float* Weff, const float* Wu,
+                   float* dh2_ws, float* dh1_ws, float* g1, double* sg1, double* sg1x, float* dWd, float* dbd, float* dWeff,
+                   float* dbeff, float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
+                   int stride, float drop_p, uint64_t drop_seed, int math, istgcn_stream_t s);
+
+/* ---- block tail: BN2 -> dropout -> + residual -> ReLU (st_gcn_mstcn_1x1.py:262-266) -----
+ * out = relu((u*scale2 + shift2)*keep/(1-p) + res) where res = NULL (0), the block input
+ * (identity) or rres*scale_r + shift_r (strided conv + BN).  Rows = NM*T*V, C channels.     */
+int istgcn_block_tail_fwd(const float* u, const float* scale2, const float* shift2,
+                          const float* res, const float* scale_r, const float* shift_r,
+                          float* out, long long rows, int C, float drop_p, uint64_t drop_seed,
+                          istgcn_stream_t s);
+/* backward reduction pass: go = gout * (out > 0) written to `go` (may alias gout); BN2 sums
+ * sum gy, sum gy*uhat with gy = go*keep/(1-p); if rres != NULL also sum go, sum go*rhat.    */
+int istgcn_block_tail_bwd(const float* gout, const float* out, const float* u,
+                          const float* mean2, const float* rstd2, const float* rres,
+                          const float* mean_r, const float* rstd_r, float* go, double* sg2,
+                          double* sg2x, double* sgr, double* sgrx, long long rows, int C,
+                          float drop_p, uint64_t drop_seed, istgcn_stream_t s);
+
+/* keep-mask of the counter-based dropout the two functions above use (element index =
+ * row*C + c); exported so that parity tests can inject the same mask into the oracle.      */
+int istgcn_dropout_mask(unsigned char* mask, long long n, float p, uint64_t seed,
+                        istgcn_stream_t s);
+
+/* ---- head: global average pool over (T, V), mean over M, 1x1 conv (st_gcnold.py:89-94) --*/
+int istgcn_pool_fwd(const float* x, float* pooled, int N, int M, int TV, int C,
+                    istgcn_stream_t s);
+int istgcn_pool_bwd(const float* gpooled, float* gx, int N, int M, int TV, int C,
+                    istgcn_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISTGCN_B200_H */

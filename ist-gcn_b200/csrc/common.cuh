@@ -1,0 +1,171 @@
+// Shared device helpers for the istgcn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/istgcn_b200.h"
+
+#define ISTGCN_API extern "C" __attribute__((visibility("default")))
+
+namespace istgcn {
+
+void set_error(const char* fmt, ...);
+int finish_launch(const char* what);   // cudaGetLastError -> error text, returns code
+
+#define ISTGCN_REQUIRE(cond, code, ...)            \
+    do {                                           \
+        if (!(cond)) {                             \
+            ::istgcn::set_error(__VA_ARGS__);      \
+            return (code);                         \
+        }                                          \
+    } while (0)
+
+constexpr int kThreads = 256;     // every tiled kernel runs 8 warps
+constexpr int kWarps = 8;
+constexpr int kMaxNnz = 1024;     // non-zeros of A_eff (197 NTU-sym, 152 OpenPose-sym)
+constexpr int kMaxKV = 4 * 32;    // K*V upper bound for the CSR pointer arrays
+constexpr int kTileRows = 128;    // rows of a frame tile (floor(128 / V) frames)
+
+__host__ __device__ inline int frames_per_tile(int V) { return kTileRows / V; }
+
+int num_sms();
+
+// ---------------------------------------------------------------- tensor-core primitives
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+
+// D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate (legacy mma.sync path;
+// used for the skinny GEMMs whose N or M is the 8..16-wide bottleneck).
+__device__ __forceinline__ void mma_m16n8k8(float (&d)[4], const uint32_t (&a)[4],
+                                            const uint32_t (&b)[2]) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, "
+        "{%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// Split x into a TF32 head and a TF32 tail (x ~= hi + lo to ~21 mantissa bits).
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+
+// Warp-level tile product on shared-memory operands.
+//   acc[mt][nt] (16x8 each) += A[16*MT x kdim] * B[kdim x 8*NT]
+//   A element (m, k): A_T ? A[k*lda + m] : A[m*lda + k]      (A points at the warp's row 0)
+//   B element (k, n): B_T ? B[n*ldb + k] : B[k*ldb + n]      (B points at the warp's column 0)
+// Bank-conflict-free fragment loads: row-indexed-by-g operands (A, B_T) need ld % 8 == 4,
+// row-indexed-by-t operands (A_T, B) need ld % 16 == 8.
+// PRECISE = 3xTF32 error compensation (small cross terms first).
+template <int MT, int NT, bool A_T, bool B_T, bool PRECISE>
+__device__ __forceinline__ void warp_mma(float (&acc)[MT][NT][4], const float* __restrict__ A,
+                                         int lda, const float* __restrict__ B, int ldb,
+                                         int kdim, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    for (int k0 = 0; k0 < kdim; k0 += 8) {
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = mt * 16 + g + 8 * (i & 1);
+                const int k = k0 + t + 4 * (i >> 1);
+                const float v = A_T ? A[k * lda + m] : A[m * lda + k];
+                if (PRECISE) split_tf32(v, ah[mt][i], al[mt][i]);
+                else ah[mt][i] = to_tf32(v);
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            uint32_t bh[2], bl[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int k = k0 + t + 4 * i;
+                const int n = nt * 8 + g;
+                const float v = B_T ? B[n * ldb + k] : B[k * ldb + n];
+                if (PRECISE) split_tf32(v, bh[i], bl[i]);
+                else bh[i] = to_tf32(v);
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                if (PRECISE) {
+                    mma_m16n8k8(acc[mt][nt], al[mt], bh);
+                    mma_m16n8k8(acc[mt][nt], ah[mt], bl);
+                }
+                mma_m16n8k8(acc[mt][nt], ah[mt], bh);
+            }
+        }
+    }
+}
+
+// one 16x8x8 step on already-loaded fp32 fragment values
+template <bool PRECISE>
+__device__ __forceinline__ void mma_step(float (&acc)[4], const float (&a)[4], const float (&b)[2]) {
+    uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (PRECISE) split_tf32(a[i], ah[i], al[i]);
+        else ah[i] = to_tf32(a[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        if (PRECISE) split_tf32(b[i], bh[i], bl[i]);
+        else bh[i] = to_tf32(b[i]);
+    }
+    if (PRECISE) {
+        mma_m16n8k8(acc, al, bh);
+        mma_m16n8k8(acc, ah, bl);
+    }
+    mma_m16n8k8(acc, ah, bh);
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void zero_acc(float (&acc)[MT][NT][4]) {
+#pragma unroll
+    for (int a = 0; a < MT; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+}
+
+// ---------------------------------------------------------------- reductions / misc
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// sum over the 8 "g" lanes that share the same (lane & 3): xor 4, 8, 16
+__device__ __forceinline__ float group_sum_g(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
+// Counter-based dropout keep decision: one 64-bit mix per element, identical in the forward
+// and backward kernels (nn.Dropout's Philox stream cannot be reproduced from a custom kernel;
+// parity tests read the mask back through istgcn_dropout_mask).
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p) {
+    uint64_t x = seed + idx * 0x9E3779B97F4A7C15ull;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    const float u = (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);   // 24 bits -> [0, 1)
+    return u >= p;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) {
+    return *reinterpret_cast<const float4*>(p);
+}
+__device__ __forceinline__ void st4(float* p, const float4& v) {
+    *reinterpret_cast<float4*>(p) = v;
+}
+
+}  // namespace istgcn

@@ -1,0 +1,789 @@
+// Inception TCN with 1x1 bottlenecks (reference: net/st_gcn_mstcn_1x1.py:186-266):
+//     a  = relu(BN1(z))                  tcn_start
+//     h1 = a Wd + bd                     conv_1x1_start   C -> b = int(sqrt(C)) in {8, 11, 16}
+//     h2 = sum_i imp[i] * tcn_i(h1)      3x1 / 9x1 / 15x1 temporal convs, stride s  == ONE 15-tap
+//                                        conv with Weff = imp0*W3 (+6) + imp1*W9 (+3) + imp2*W15
+//     u  = h2 Wu + bu                    conv_1x1_end     b -> C   (BN2 statistics in the epilogue)
+// The block is ~13 FLOP/byte, i.e. HBM-bound: forward reads z once and writes u once; the
+// b-channel intermediates h1/h2 (1/8..1/16 of an activation) are the only extra traffic and are
+// kept for the backward pass.  The skinny GEMMs (N or M = b padded to bp in {8, 16}) run on the
+// legacy mma.sync TF32 path - tcgen05 tiles (M=128, N>=16 from shared-memory descriptors) buy
+// nothing at K=bp<=16 / N=bp<=16.
+//
+//   tcn_down    z -> h1                         rows x C x bp GEMM, BN1+ReLU applied on load
+//   tcn_up      h1 -> h2 -> u                   15-tap implicit GEMM from a smem halo tile, then
+//                                               rows x bp x C GEMM, BN2 sums
+//   tcn_bwd_up  go,u -> du -> dh2, dWu, dbu, dbeff
+//   tcn_bwd_t   dh2,h1 -> dh1, dWeff, dbd
+//   tcn_bwd_dn  dh1,z -> g1 (ReLU-masked), BN1-backward sums, dWd
+#include "common.cuh"
+
+namespace istgcn {
+
+constexpr int kTaps = 15, kHalf = 7;
+
+__host__ __device__ inline int ld_g(int bp) { return bp + 4; }                 // g-indexed rows
+__host__ __device__ inline int ld_t(int bp) { return bp == 8 ? 8 : 24; }       // t-indexed rows
+
+// ----------------------------------------------------------------------------------- down
+struct TcnDownParams {
+    const float *z, *scale1, *shift1, *Wd, *bd;
+    float* h1;
+    long long rows;
+    int C, bp;
+};
+
+template <int NT, bool PRECISE>
+__global__ void __launch_bounds__(kThreads) tcn_down_kernel(TcnDownParams p) {
+    constexpr int BP = NT * 8;
+    constexpr int LDW = BP == 8 ? 8 : 24;
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;                       // [128][36]
+    float* Ws = As + kTileRows * 36;        // [C][LDW]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int C = p.C;
+    for (int i = tid; i < C * BP; i += kThreads) Ws[(i / BP) * LDW + (i % BP)] = p.Wd[i];
+    const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long row0 = tile * kTileRows;
+        const int valid = (int)min((long long)kTileRows, p.rows - row0);
+        float acc[1][NT][4];
+        zero_acc<1, NT>(acc);
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            __syncthreads();
+            for (int i = tid; i < kTileRows * 8; i += kThreads) {
+                const int r = i >> 3, c4 = (i & 7) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < valid) {
+                    const float4 zv = ld4(p.z + (row0 + r) * C + c0 + c4);
+                    const float4 sc = ld4(p.scale1 + c0 + c4), sh = ld4(p.shift1 + c0 + c4);
+                    v.x = fmaxf(zv.x * sc.x + sh.x, 0.f);
+                    v.y = fmaxf(zv.y * sc.y + sh.y, 0.f);
+                    v.z = fmaxf(zv.z * sc.z + sh.z, 0.f);
+                    v.w = fmaxf(zv.w * sc.w + sh.w, 0.f);
+                }
+                st4(As + r * 36 + c4, v);
+            }
+            __syncthreads();
+            warp_mma<1, NT, false, false, PRECISE>(acc, As + warp * 16 * 36, 36, Ws + c0 * LDW, LDW,
+                                                   32, lane);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = warp * 16 + g + 8 * h;
+                const int c = nt * 8 + 2 * t;
+                if (r < valid)
+                    *reinterpret_cast<float2*>(p.h1 + (row0 + r) * BP + c) =
+                        make_float2(acc[0][nt][2 * h] + p.bd[c], acc[0][nt][2 * h + 1] + p.bd[c + 1]);
+            }
+    }
+}
+
+// ----------------------------------------------------------------------------------- up
+struct TcnUpParams {
+    const float *h1, *Weff, *beff, *Wu, *bu;
+    float *h2, *u;
+    double *stat_sum, *stat_sumsq;
+    int NM, T, Tout, V, C, bp, stride, TT, tiles_per_sample;
+};
+
+constexpr int kUpRows = 256;   // output rows (frames*V) of one temporal tile
+
+template <int NT, bool PRECISE>
+__global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
+    constexpr int BP = NT * 8;
+    constexpr int LDH = BP + 4;                 // halo / h2 tiles (g-indexed)
+    constexpr int LDW = BP == 8 ? 8 : 24;       // Weff[(tap, ci)][co]  (t-indexed)
+    extern __shared__ __align__(16) float smem[];
+    const int V = p.V, C = p.C, s = p.stride, TT = p.TT;
+    const int TI = (TT - 1) * s + kTaps;        // input frames of the halo tile
+    const int LDU = C + 8;
+    float* hs = smem;                           // [TI*V][LDH]
+    float* h2s = hs + TI * V * LDH;             // [256][LDH]
+    float* Wts = h2s + kUpRows * LDH;           // [15*BP][LDW]
+    float* Wus = Wts + kTaps * BP * LDW;        // [BP][LDU]
+    float* s_sum = Wus + BP * LDU;              // [C]
+    float* s_sq = s_sum + C;                    // [C]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < kTaps * BP * BP; i += kThreads) Wts[(i / BP) * LDW + (i % BP)] = p.Weff[i];
+    for (int i = tid; i < BP * C; i += kThreads) Wus[(i / C) * LDU + (i % C)] = p.Wu[i];
+    for (int i = tid; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
+
+    const int total = p.NM * p.tiles_per_sample;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_sample;
+        const int to0 = (tile - n * p.tiles_per_sample) * TT;
+        const int nto = min(TT, p.Tout - to0);
+        const int valid = nto * V;
+        const int ti0 = to0 * s - kHalf;        // first input frame of the halo (may be < 0)
+        __syncthreads();                        // previous tile finished with hs / h2s
+        // halo tile: TI frames x V joints x BP channels, zero outside [0, T)
+        for (int i = tid; i < TI * V * (BP / 4); i += kThreads) {
+            const int r = i / (BP / 4), c4 = (i % (BP / 4)) * 4;
+            const int ti = ti0 + r / V;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ti >= 0 && ti < p.T)
+                v = ld4(p.h1 + (((size_t)n * p.T + ti) * V + (r % V)) * BP + c4);
+            st4(hs + r * LDH + c4, v);
+        }
+        __syncthreads();
+        // ---- temporal 15-tap conv: h2[(to,v)][co] = sum_tap sum_ci hs[(to*s+tap, v)][ci] Weff
+        for (int mt = warp; mt * 16 < valid; mt += kWarps) {
+            int base[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int r = mt * 16 + g + 8 * h;
+                if (r >= valid) r = 0;
+                const int to_l = r / V, v = r - to_l * V;
+                base[h] = ((to_l * s) * V + v) * LDH;
+            }
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+            for (int tap = 0; tap < kTaps; ++tap) {
+#pragma unroll
+                for (int kk = 0; kk < NT; ++kk) {
+                    float a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        a[i] = hs[base[i & 1] + tap * V * LDH + kk * 8 + t + 4 * (i >> 1)];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        float b[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            b[i] = Wts[(tap * BP + kk * 8 + t + 4 * i) * LDW + nt * 8 + g];
+                        mma_step<PRECISE>(acc[nt], a, b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = mt * 16 + g + 8 * h;
+                    const int c = nt * 8 + 2 * t;
+                    const float v0 = acc[nt][2 * h] + p.beff[c], v1 = acc[nt][2 * h + 1] + p.beff[c + 1];
+                    const bool ok = r < valid;
+                    *reinterpret_cast<float2*>(h2s + r * LDH + c) = ok ? make_float2(v0, v1)
+                                                                      : make_float2(0.f, 0.f);
+                    if (ok)
+                        *reinterpret_cast<float2*>(
+                            p.h2 + (((size_t)n * p.Tout + to0) * V + r) * BP + c) = make_float2(v0, v1);
+                }
+        }
+        __syncthreads();
+        // ---- up projection u = h2 Wu + bu, BN2 statistics
+        for (int mt = warp; mt * 16 < valid; mt += kWarps) {
+            float a[NT][4];
+#pragma unroll
+            for (int kk = 0; kk < NT; ++kk)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    a[kk][i] = h2s[(mt * 16 + g + 8 * (i & 1)) * LDH + kk * 8 + t + 4 * (i >> 1)];
+            for (int nt = 0; nt < C / 8; ++nt) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kk = 0; kk < NT; ++kk) {
+                    float b[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) b[i] = Wus[(kk * 8 + t + 4 * i) * LDU + nt * 8 + g];
+                    mma_step<PRECISE>(acc, a[kk], b);
+                }
+                const int c = nt * 8 + 2 * t;
+                const float b0 = p.bu[c], b1 = p.bu[c + 1];
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = mt * 16 + g + 8 * h;
+                    if (r < valid) {
+                        const float v0 = acc[2 * h] + b0, v1 = acc[2 * h + 1] + b1;
+                        *reinterpret_cast<float2*>(
+                            p.u + (((size_t)n * p.Tout + to0) * V + r) * C + c) = make_float2(v0, v1);
+                        s0 += v0; s1 += v1; q0 += v0 * v0; q1 += v1 * v1;
+                    }
+                }
+                if (p.stat_sum) {
+                    s0 = group_sum_g(s0); s1 = group_sum_g(s1);
+                    q0 = group_sum_g(q0); q1 = group_sum_g(q1);
+                    if (g == 0) {
+                        atomicAdd(&s_sum[c], s0); atomicAdd(&s_sum[c + 1], s1);
+                        atomicAdd(&s_sq[c], q0); atomicAdd(&s_sq[c + 1], q1);
+                    }
+                }
+            }
+        }
+    }
+    if (p.stat_sum) {
+        __syncthreads();
+        for (int c = tid; c < C; c += kThreads) {
+            atomicAdd(&p.stat_sum[c], (double)s_sum[c]);
+            atomicAdd(&p.stat_sumsq[c], (double)s_sq[c]);
+        }
+    }
+}
+
+// --------------------------------------------------------------------------- backward: up
+struct TcnBwdUpParams {
+    const float *go, *u, *p2, *q2, *r2, *h2, *Wu;
+    float *dh2, *dWu, *dbu, *dbeff;
+    long long rows;
+    int C, bp;
+    float drop_p, keep_scale;
+    uint64_t seed;
+};
+
+template <int NT, bool PRECISE>
+__global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) {
+    constexpr int BP = NT * 8;
+    constexpr int LDT = BP == 8 ? 8 : 24;       // h2s as A^T (t-indexed rows)
+    constexpr int MAXCH = 8;                    // C <= 256 -> at most 8 column chunks of 32
+    extern __shared__ __align__(16) float smem[];
+    const int C = p.C, LDWU = C + 4;
+    float* DUs = smem;                          // [128][36]
+    float* h2s = DUs + kTileRows * 36;          // [128][LDT] (+8 pad)
+    float* Wus = h2s + kTileRows * LDT + 8;     // [BP][LDWU]   B^T: n = j, k = c
+    float* s_dbu = Wus + BP * LDWU;             // [C]
+    float* s_dbe = s_dbu + C;                   // [BP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < BP * C; i += kThreads) Wus[(i / C) * LDWU + (i % C)] = p.Wu[i];
+    for (int i = tid; i < C + BP; i += kThreads) s_dbu[i] = 0.f;
+    float acc_w[MAXCH][4];                      // dWu[j][c]: m = j (16, rows >= bp ignored)
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc_w[ch][i] = 0.f;
+    const int wn = warp & 3, wk = warp >> 2;    // n-tile of the chunk, K-half (64 rows)
+
+    const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long row0 = tile * kTileRows;
+        const int valid = (int)min((long long)kTileRows, p.rows - row0);
+        __syncthreads();
+        for (int i = tid; i < kTileRows * (BP / 4); i += kThreads) {
+            const int r = i / (BP / 4), c4 = (i % (BP / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < valid) v = ld4(p.h2 + (row0 + r) * BP + c4);
+            st4(h2s + r * LDT + c4, v);
+        }
+        float acc_h[1][NT][4];
+        zero_acc<1, NT>(acc_h);
+#pragma unroll
+        for (int ch = 0; ch < MAXCH; ++ch) {
+            const int c0 = ch * 32;
+            if (c0 < C) {
+                __syncthreads();
+                for (int i = tid; i < kTileRows * 8; i += kThreads) {
+                    const int r = i >> 3, c4 = (i & 7) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < valid) {
+                        const long long off = (row0 + r) * C + c0 + c4;
+                        const float4 gv = ld4(p.go + off), uv = ld4(p.u + off);
+                        const float4 pv = ld4(p.p2 + c0 + c4), qv = ld4(p.q2 + c0 + c4),
+                                     rv = ld4(p.r2 + c0 + c4);
+                        float gy[4] = {gv.x, gv.y, gv.z, gv.w};
+                        if (p.drop_p > 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                gy[j] = dropout_keep(p.seed, (uint64_t)(off + j), p.drop_p)
+                                            ? gy[j] * p.keep_scale : 0.f;
+                        }
+                        v.x = pv.x * gy[0] + qv.x * uv.x + rv.x;
+                        v.y = pv.y * gy[1] + qv.y * uv.y + rv.y;
+                        v.z = pv.z * gy[2] + qv.z * uv.z + rv.z;
+                        v.w = pv.w * gy[3] + qv.w * uv.w + rv.w;
+                    }
+                    st4(DUs + r * 36 + c4, v);
+                }
+                __syncthreads();
+                // dh2[rows][j] += DU[rows][c0..] * Wu[j][c0..]^T
+                warp_mma<1, NT, false, true, PRECISE>(acc_h, DUs + warp * 16 * 36, 36, Wus + c0, LDWU,
+                                                      32, lane);
+                // dWu[j][c0 + wn*8 ..] += h2^T (K = 64 rows of this warp's half) * DU
+                {
+                    float accw[1][1][4] = {{{acc_w[ch][0], acc_w[ch][1], acc_w[ch][2], acc_w[ch][3]}}};
+                    warp_mma<1, 1, true, false, PRECISE>(accw, h2s + wk * 64 * LDT, LDT,
+                                                         DUs + wk * 64 * 36 + wn * 8, 36, 64, lane);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc_w[ch][i] = accw[0][0][i];
+                }
+                // dbu[c] += column sums of DU
+                {
+                    const int c = tid & 31, r0 = (tid >> 5) * 16;
+                    float sacc = 0.f;
+#pragma unroll 4
+                    for (int r = 0; r < 16; ++r) sacc += DUs[(r0 + r) * 36 + c];
+                    atomicAdd(&s_dbu[c0 + c], sacc);
+                }
+            }
+        }
+        // dh2 tile -> global, dbeff = column sums of dh2
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int c = nt * 8 + 2 * t;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = warp * 16 + g + 8 * h;
+                if (r < valid) {
+                    *reinterpret_cast<float2*>(p.dh2 + (row0 + r) * BP + c) =
+                        make_float2(acc_h[0][nt][2 * h], acc_h[0][nt][2 * h + 1]);
+                    s0 += acc_h[0][nt][2 * h];
+                    s1 += acc_h[0][nt][2 * h + 1];
+                }
+            }
+            s0 = group_sum_g(s0); s1 = group_sum_g(s1);
+            if (g == 0) { atomicAdd(&s_dbe[c], s0); atomicAdd(&s_dbe[c + 1], s1); }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch) {
+        if (ch * 32 < C) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = g + 8 * (i >> 1);
+                const int c = ch * 32 + wn * 8 + 2 * t + (i & 1);
+                if (j < BP) atomicAdd(&p.dWu[(size_t)j * C + c], acc_w[ch][i]);
+            }
+        }
+    }
+    for (int c = tid; c < C; c += kThreads) atomicAdd(&p.dbu[c], s_dbu[c]);
+    for (int c = tid; c < BP; c += kThreads) atomicAdd(&p.dbeff[c], s_dbe[c]);
+}
+
+// ----------------------------------------------------------------------- backward: temporal
+struct TcnBwdTParams {
+    const float *dh2, *h1, *Weff;
+    float *dh1, *dWeff, *dbd;
+    int NM, T, Tout, V, bp, stride, TT, tiles_per_sample;
+};
+
+// Tile = TT input frames of one sample.  dh1[(ti,v)][ci] = sum_tap sum_co Weff[tap][ci][co] *
+// dh2[(to,v)][co] with to*s + tap - 7 = ti;  dWeff[tap][ci][co] += h1[(ti,v)][ci] * dh2[(to,v)][co].
+template <int NT, bool PRECISE>
+__global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
+    constexpr int BP = NT * 8;
+    constexpr int LDH = BP + 4;                 // dh2 halo (g-indexed gathers)
+    constexpr int LDT = BP == 8 ? 8 : 24;       // h1 tile as A^T
+    constexpr int LDWT = BP + 4;                // Weff[tap][ci][co] as B^T (n = ci, k = co)
+    extern __shared__ __align__(16) float smem[];
+    const int V = p.V, s = p.stride, TT = p.TT;
+    const int TO = (TT - 1 + 2 * kHalf) / s + 2;   // output frames that can touch the tile
+    float* ds = smem;                           // [TO*V][LDH]   dh2 halo
+    float* h1s = ds + TO * V * LDH;             // [256][LDT] (+8)
+    float* Wts = h1s + kUpRows * LDT + 8;       // [15*BP][LDWT]
+    float* s_dbd = Wts + kTaps * BP * LDWT;     // [BP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < kTaps * BP * BP; i += kThreads) Wts[(i / BP) * LDWT + (i % BP)] = p.Weff[i];
+    for (int i = tid; i < BP; i += kThreads) s_dbd[i] = 0.f;
+    float acc_w[2][NT][4];                      // this warp's taps: warp and warp + 8
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc_w[a][b][c] = 0.f;
+
+    const int total = p.NM * p.tiles_per_sample;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int n = tile / p.tiles_per_sample;
+        const int ti0 = (tile - n * p.tiles_per_sample) * TT;
+        const int nti = min(TT, p.T - ti0);
+        const int valid = nti * V;
+        // first output frame that can contribute: to*s + 14 - 7 >= ti0  ->  to >= (ti0 - 7)/s
+        int to_lo = ti0 - kHalf;
+        to_lo = to_lo <= 0 ? 0 : (to_lo + s - 1) / s;
+        __syncthreads();
+        for (int i = tid; i < TO * V * (BP / 4); i += kThreads) {
+            const int r = i / (BP / 4), c4 = (i % (BP / 4)) * 4;
+            const int to = to_lo + r / V;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (to < p.Tout) v = ld4(p.dh2 + (((size_t)n * p.Tout + to) * V + (r % V)) * BP + c4);
+            st4(ds + r * LDH + c4, v);
+        }
+        for (int i = tid; i < kUpRows * (BP / 4); i += kThreads) {
+            const int r = i / (BP / 4), c4 = (i % (BP / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < valid) v = ld4(p.h1 + (((size_t)n * p.T + ti0) * V + r) * BP + c4);
+            st4(h1s + r * LDT + c4, v);
+        }
+        __syncthreads();
+        // gather offset of dh2 row feeding input row r at tap: -1 if none
+        auto src_off = [&](int r, int tap) -> int {
+            if (r >= valid) return -1;
+            const int ti_l = r / V, v = r - ti_l * V;
+            const int num = ti0 + ti_l + kHalf - tap;
+            if (num < 0) return -1;
+            const int to = num / s;
+            if (to * s != num || to >= p.Tout) return -1;
+            return ((to - to_lo) * V + v) * LDH;
+        };
+        // ---- dh1
+        for (int mt = warp; mt * 16 < valid; mt += kWarps) {
+            float acc[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+            for (int tap = 0; tap < kTaps; ++tap) {
+                const int o0 = src_off(mt * 16 + g, tap), o1 = src_off(mt * 16 + g + 8, tap);
+#pragma unroll
+                for (int kk = 0; kk < NT; ++kk) {       // k = co
+                    float a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int o = (i & 1) ? o1 : o0;
+                        a[i] = o < 0 ? 0.f : ds[o + kk * 8 + t + 4 * (i >> 1)];
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {   // n = ci
+                        float b[2];
+#pragma unroll
+                        for (int i = 0; i < 2; ++i)
+                            b[i] = Wts[(tap * BP + nt * 8 + g) * LDWT + kk * 8 + t + 4 * i];
+                        mma_step<PRECISE>(acc[nt], a, b);
+                    }
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int c = nt * 8 + 2 * t;
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = mt * 16 + g + 8 * h;
+                    if (r < valid) {
+                        *reinterpret_cast<float2*>(
+                            p.dh1 + (((size_t)n * p.T + ti0) * V + r) * BP + c) =
+                            make_float2(acc[nt][2 * h], acc[nt][2 * h + 1]);
+                        s0 += acc[nt][2 * h];
+                        s1 += acc[nt][2 * h + 1];
+                    }
+                }
+                s0 = group_sum_g(s0); s1 = group_sum_g(s1);
+                if (g == 0) { atomicAdd(&s_dbd[c], s0); atomicAdd(&s_dbd[c + 1], s1); }
+            }
+        }
+        // ---- dWeff[tap][ci][co]: m = ci (A^T from h1s), n = co, k = rows of the tile
+#pragma unroll
+        for (int sel = 0; sel < 2; ++sel) {
+            const int tap = warp + sel * kWarps;
+            if (tap < kTaps) {
+                for (int k0 = 0; k0 < valid; k0 += 8) {
+                    float a[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        a[i] = h1s[(k0 + t + 4 * (i >> 1)) * LDT + g + 8 * (i & 1)];
+                    const int o0 = src_off(k0 + t, tap), o1 = src_off(k0 + t + 4, tap);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) {
+                        float b[2];
+                        b[0] = o0 < 0 ? 0.f : ds[o0 + nt * 8 + g];
+                        b[1] = o1 < 0 ? 0.f : ds[o1 + nt * 8 + g];
+                        mma_step<PRECISE>(acc_w[sel][nt], a, b);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int sel = 0; sel < 2; ++sel) {
+        const int tap = warp + sel * kWarps;
+        if (tap < kTaps) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int ci = g + 8 * (i >> 1), co = nt * 8 + 2 * t + (i & 1);
+                    if (ci < BP) atomicAdd(&p.dWeff[(tap * BP + ci) * BP + co], acc_w[sel][nt][i]);
+                }
+        }
+    }
+    for (int c = tid; c < BP; c += kThreads) atomicAdd(&p.dbd[c], s_dbd[c]);
+}
+
+// --------------------------------------------------------------------------- backward: down
+struct TcnBwdDownParams {
+    const float *dh1, *z, *scale1, *shift1, *mean1, *rstd1, *Wd;
+    float *g1, *dWd;
+    double *sg1, *sg1x;
+    long long rows;
+    int C, bp;
+};
+
+template <int NT, bool PRECISE>
+__global__ void __launch_bounds__(kThreads) tcn_bwd_down_kernel(TcnBwdDownParams p) {
+    constexpr int BP = NT * 8;
+    constexpr int LDD = BP + 4;                 // dh1s as A (g-indexed), Wds as B^T (g-indexed)
+    constexpr int LDA = 40;                     // a-tile as A^T (t-indexed)
+    constexpr int MAXCH = 8;
+    extern __shared__ __align__(16) float smem[];
+    const int C = p.C;
+    float* Zs = smem;                           // [128][36]   raw z chunk
+    float* As = Zs + kTileRows * 36;            // [128][40]   relu(bn1(z)) chunk
+    float* dhs = As + kTileRows * LDA;          // [128][LDD]
+    float* Wds = dhs + kTileRows * LDD;         // [C][LDD]
+    float* s_g = Wds + C * LDD;                 // [C]
+    float* s_gx = s_g + C;                      // [C]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+
+    for (int i = tid; i < C * BP; i += kThreads) Wds[(i / BP) * LDD + (i % BP)] = p.Wd[i];
+    for (int i = tid; i < 2 * C; i += kThreads) s_g[i] = 0.f;
+    float acc_w[MAXCH][NT][4];                  // dWd[c][j]: m = c (this warp's m-tile), n = j
+#pragma unroll
+    for (int a = 0; a < MAXCH; ++a)
+#pragma unroll
+        for (int b = 0; b < NT; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc_w[a][b][c] = 0.f;
+    const int wm = warp & 1, wk = warp >> 1;    // m-tile (16 channels) of the chunk, K-quarter
+
+    const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long row0 = tile * kTileRows;
+        const int valid = (int)min((long long)kTileRows, p.rows - row0);
+        __syncthreads();
+        for (int i = tid; i < kTileRows * (BP / 4); i += kThreads) {
+            const int r = i / (BP / 4), c4 = (i % (BP / 4)) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < valid) v = ld4(p.dh1 + (row0 + r) * BP + c4);
+            st4(dhs + r * LDD + c4, v);
+        }
+#pragma unroll
+        for (int ch = 0; ch < MAXCH; ++ch) {
+            const int c0 = ch * 32;
+            if (c0 < C) {
+                __syncthreads();
+                for (int i = tid; i < kTileRows * 8; i += kThreads) {
+                    const int r = i >> 3, c4 = (i & 7) * 4;
+                    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), av = zv;
+                    if (r < valid) {
+                        zv = ld4(p.z + (row0 + r) * C + c0 + c4);
+                        const float4 sc = ld4(p.scale1 + c0 + c4), sh = ld4(p.shift1 + c0 + c4);
+                        av.x = fmaxf(zv.x * sc.x + sh.x, 0.f);
+                        av.y = fmaxf(zv.y * sc.y + sh.y, 0.f);
+                        av.z = fmaxf(zv.z * sc.z + sh.z, 0.f);
+                        av.w = fmaxf(zv.w * sc.w + sh.w, 0.f);
+                    }
+                    st4(Zs + r * 36 + c4, zv);
+                    st4(As + r * LDA + c4, av);
+                }
+                __syncthreads();
+                // da[rows][c0..c0+32) = dh1[rows][j] * Wd[c][j]^T  (K = bp)
+                float acc[1][4][4];
+                zero_acc<1, 4>(acc);
+                warp_mma<1, 4, false, true, PRECISE>(acc, dhs + warp * 16 * LDD, LDD, Wds + c0 * LDD,
+                                                     LDD, BP, lane);
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const int cl = nt * 8 + 2 * t;
+                    const float mu0 = p.mean1[c0 + cl], mu1 = p.mean1[c0 + cl + 1];
+                    const float rs0 = p.rstd1[c0 + cl], rs1 = p.rstd1[c0 + cl + 1];
+                    float s0 = 0.f, s1 = 0.f, x0 = 0.f, x1 = 0.f;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int r = warp * 16 + g + 8 * h;
+                        if (r < valid) {
+                            const float a0 = As[r * LDA + cl], a1 = As[r * LDA + cl + 1];
+                            const float g0 = a0 > 0.f ? acc[0][nt][2 * h] : 0.f;
+                            const float g1v = a1 > 0.f ? acc[0][nt][2 * h + 1] : 0.f;
+                            *reinterpret_cast<float2*>(p.g1 + (row0 + r) * C + c0 + cl) =
+                                make_float2(g0, g1v);
+                            s0 += g0; s1 += g1v;
+                            x0 += g0 * (Zs[r * 36 + cl] - mu0) * rs0;
+                            x1 += g1v * (Zs[r * 36 + cl + 1] - mu1) * rs1;
+                        }
+                    }
+                    s0 = group_sum_g(s0); s1 = group_sum_g(s1);
+                    x0 = group_sum_g(x0); x1 = group_sum_g(x1);
+                    if (g == 0) {
+                        atomicAdd(&s_g[c0 + cl], s0); atomicAdd(&s_g[c0 + cl + 1], s1);
+                        atomicAdd(&s_gx[c0 + cl], x0); atomicAdd(&s_gx[c0 + cl + 1], x1);
+                    }
+                }
+                // dWd[c0 + wm*16 ..][j] += a^T (K = 32 rows of this warp's quarter) * dh1
+                {
+                    float accw[1][NT][4];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) accw[0][nt][i] = acc_w[ch][nt][i];
+                    // B (k = row, n = j) read from dhs with k as the row index: ld = LDD is
+                    // g-friendly, not t-friendly -> a few 2-way conflicts on a tiny operand.
+                    warp_mma<1, NT, true, false, PRECISE>(accw, As + wk * 32 * LDA + wm * 16, LDA,
+                                                          dhs + wk * 32 * LDD, LDD, 32, lane);
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc_w[ch][nt][i] = accw[0][nt][i];
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ch = 0; ch < MAXCH; ++ch) {
+        if (ch * 32 < C) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c = ch * 32 + wm * 16 + g + 8 * (i >> 1);
+                    const int j = nt * 8 + 2 * t + (i & 1);
+                    atomicAdd(&p.dWd[(size_t)c * BP + j], acc_w[ch][nt][i]);
+                }
+        }
+    }
+    for (int c = tid; c < C; c += kThreads) {
+        atomicAdd(&p.sg1[c], (double)s_g[c]);
+        atomicAdd(&p.sg1x[c], (double)s_gx[c]);
+    }
+}
+
+static int grid_for(long long tiles, int per_sm) {
+    long long n = (long long)num_sms() * per_sm;
+    if (n > tiles) n = tiles;
+    return (int)(n < 1 ? 1 : n);
+}
+
+template <typename K>
+static void set_smem(K kern, size_t bytes) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+static int check_tcn(const char* who, int NM, int T, int V, int C, int bp, int stride) {
+    ISTGCN_REQUIRE(NM >= 0 && T >= 1 && V >= 1 && V <= 32, ISTGCN_E_SHAPE, "%s: bad NM/T/V (%d,%d,%d)", who, NM, T, V);
+    ISTGCN_REQUIRE(C % 32 == 0 && C >= 32 && C <= 256, ISTGCN_E_SHAPE, "%s: C=%d unsupported (32..256, multiple of 32)", who, C);
+    ISTGCN_REQUIRE(bp == 8 || bp == 16, ISTGCN_E_SHAPE, "%s: padded bottleneck bp=%d must be 8 or 16", who, bp);
+    ISTGCN_REQUIRE(stride == 1 || stride == 2, ISTGCN_E_SHAPE, "%s: stride=%d unsupported", who, stride);
+    return 0;
+}
+
+}  // namespace istgcn
+
+using namespace istgcn;
+
+ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* scale1, const float* shift1,
+                              const float* Wd, const float* bd, const float* Weff, const float* beff,
+                              const float* Wu, const float* bu, float* h1, float* h2, float* u,
+                              double* stat_sum, double* stat_sumsq, int NM, int T, int V, int C,
+                              int bp, int stride, int math, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(z && scale1 && shift1 && Wd && bd && Weff && beff && Wu && bu && h1 && h2 && u,
+                   ISTGCN_E_ARG, "tcn_fwd: null pointer");
+    if (int e = check_tcn("tcn_fwd", NM, T, V, C, bp, stride)) return e;
+    if (NM == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const bool pc = math == ISTGCN_MATH_3XTF32;
+    const int Tout = (T - 1) / stride + 1;
+    {
+        TcnDownParams p{z, scale1, shift1, Wd, bd, h1, (long long)NM * T * V, C, bp};
+        const size_t smem = sizeof(float) * (kTileRows * 36 + C * ld_t(bp));
+        const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 4);
+#define LAUNCH_DOWN(NT, PC)                                          \
+    set_smem(tcn_down_kernel<NT, PC>, smem);                         \
+    tcn_down_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
+        if (bp == 8) { if (pc) { LAUNCH_DOWN(1, true); } else { LAUNCH_DOWN(1, false); } }
+        else { if (pc) { LAUNCH_DOWN(2, true); } else { LAUNCH_DOWN(2, false); } }
+#undef LAUNCH_DOWN
+        if (int e = finish_launch("tcn_down")) return e;
+    }
+    {
+        TcnUpParams p{h1, Weff, beff, Wu, bu, h2, u, stat_sum, stat_sumsq,
+                      NM, T, Tout, V, C, bp, stride, 0, 0};
+        p.TT = kUpRows / V;
+        if (p.TT > Tout) p.TT = Tout;
+        p.tiles_per_sample = (Tout + p.TT - 1) / p.TT;
+        const int TI = (p.TT - 1) * stride + kTaps;
+        const size_t smem = sizeof(float) * ((size_t)TI * V * ld_g(bp) + kUpRows * ld_g(bp) +
+                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 2 * C);
+        const int grid = grid_for((long long)NM * p.tiles_per_sample, 2);
+#define LAUNCH_UP(NT, PC)                                            \
+    set_smem(tcn_up_kernel<NT, PC>, smem);                           \
+    tcn_up_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
+        if (bp == 8) { if (pc) { LAUNCH_UP(1, true); } else { LAUNCH_UP(1, false); } }
+        else { if (pc) { LAUNCH_UP(2, true); } else { LAUNCH_UP(2, false); } }
+#undef LAUNCH_UP
+        if (int e = finish_launch("tcn_up")) return e;
+    }
+    return 0;
+}
+
+ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float* q2,
+                              const float* r2, const float* z, const float* scale1,
+                              const float* shift1, const float* mean1, const float* rstd1,
+                              const float* h1, const float* h2, const float* Wd, const float* Weff,
+                              const float* Wu, float* dh2_ws, float* dh1_ws, float* g1, double* sg1,
+                              double* sg1x, float* dWd, float* dbd, float* dWeff, float* dbeff,
+                              float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
+                              int stride, float drop_p, uint64_t drop_seed, int math,
+                              istgcn_stream_t s) {
+    ISTGCN_REQUIRE(go && u && p2 && q2 && r2 && z && scale1 && shift1 && mean1 && rstd1 && h1 && h2 &&
+                       Wd && Weff && Wu && dh2_ws && dh1_ws && g1 && sg1 && sg1x && dWd && dbd &&
+                       dWeff && dbeff && dWu && dbu,
+                   ISTGCN_E_ARG, "tcn_bwd: null pointer");
+    if (int e = check_tcn("tcn_bwd", NM, T, V, C, bp, stride)) return e;
+    ISTGCN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, ISTGCN_E_ARG, "tcn_bwd: dropout p=%f", drop_p);
+    if (NM == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    const bool pc = math == ISTGCN_MATH_3XTF32;
+    const int Tout = (T - 1) / stride + 1;
+    {
+        TcnBwdUpParams p{go, u, p2, q2, r2, h2, Wu, dh2_ws, dWu, dbu, dbeff,
+                         (long long)NM * Tout * V, C, bp, drop_p, 1.f / (1.f - drop_p), drop_seed};
+        const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * ld_t(bp) + 8 + bp * (C + 4) + C + bp);
+        const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 3);
+#define LAUNCH_BU(NT, PC)                                            \
+    set_smem(tcn_bwd_up_kernel<NT, PC>, smem);                       \
+    tcn_bwd_up_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
+        if (bp == 8) { if (pc) { LAUNCH_BU(1, true); } else { LAUNCH_BU(1, false); } }
+        else { if (pc) { LAUNCH_BU(2, true); } else { LAUNCH_BU(2, false); } }
+#undef LAUNCH_BU
+        if (int e = finish_launch("tcn_bwd_up")) return e;
+    }
+    {
+        TcnBwdTParams p{dh2_ws, h1, Weff, dh1_ws, dWeff, dbd, NM, T, Tout, V, bp, stride, 0, 0};
+        p.TT = kUpRows / V;
+        if (p.TT > T) p.TT = T;
+        p.tiles_per_sample = (T + p.TT - 1) / p.TT;
+        const int TO = (p.TT - 1 + 2 * kHalf) / stride + 2;
+        const size_t smem = sizeof(float) * ((size_t)TO * V * ld_g(bp) + kUpRows * ld_t(bp) + 8 +
+                                             kTaps * bp * ld_g(bp) + bp);
+        const int grid = grid_for((long long)NM * p.tiles_per_sample, 2);
+#define LAUNCH_BT(NT, PC)                                            \
+    set_smem(tcn_bwd_t_kernel<NT, PC>, smem);                        \
+    tcn_bwd_t_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
+        if (bp == 8) { if (pc) { LAUNCH_BT(1, true); } else { LAUNCH_BT(1, false); } }
+        else { if (pc) { LAUNCH_BT(2, true); } else { LAUNCH_BT(2, false); } }
+#undef LAUNCH_BT
+        if (int e = finish_launch("tcn_bwd_t")) return e;
+    }
+    {
+        TcnBwdDownParams p{dh1_ws, z, scale1, shift1, mean1, rstd1, Wd, g1, dWd, sg1, sg1x,
+                           (long long)NM * T * V, C, bp};
+        const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * 40 + kTileRows * ld_g(bp) +
+                                             C * ld_g(bp) + 2 * C);
+        const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 3);
+#define LAUNCH_BD(NT, PC)                                            \
+    set_smem(tcn_bwd_down_kernel<NT, PC>, smem);                     \
+    tcn_bwd_down_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
+        if (bp == 8) { if (pc) { LAUNCH_BD(1, true); } else { LAUNCH_BD(1, false); } }
+        else { if (pc) { LAUNCH_BD(2, true); } else { LAUNCH_BD(2, false); } }
+#undef LAUNCH_BD
+        if (int e = finish_launch("tcn_bwd_down")) return e;
+    }
+    return 0;
+}

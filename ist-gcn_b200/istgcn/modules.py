@@ -1,0 +1,205 @@
+"""nn.Module shells shared by the drop-in ``net.*`` models.
+
+The classes here own *no* parameters of their own naming: every ``net/<file>.py`` declares its
+sub-modules itself, in the reference's registration order, so ``state_dict()`` has the
+reference's keys, order and shapes.  What lives here is the part that is
+identical for every variant: turning the reference-layout parameters into the operands of the
+fused kernels (tiny differentiable torch ops) and driving ``ops.STBlock``.
+"""
+import itertools
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .sparse import SparsePattern
+
+_TAPS = 15
+_seed_counter = itertools.count(1)
+
+
+def padded_bottleneck(b):
+    """Bottleneck width b = int(sqrt(C)) in {8, 11, 16} -> kernel width bp in {8, 16}."""
+    if b <= 8:
+        return 8
+    if b <= 16:
+        return 16
+    raise NotImplementedError('bottleneck width %d > 16 is not supported by the TCN kernels' % b)
+
+
+def to_channels_last(x):
+    """(N, C, T, V) -> (N, T, V, C) contiguous."""
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def to_channels_first(x):
+    """(N, T, V, C) -> (N, C, T, V) contiguous."""
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+def graph_conv_operands(weight, bias, adjs, pattern):
+    """Reference-layout conv weight (K*Cout, Cin, 1, 1) + bias and the adjacency stacks
+    [A*imp (, A2*imp2, A3*imp3)] -> (vals[nnz], Wc[K*Cin, Cout], biasterm[V, Cout]).
+
+    Three einsums with A, A2, A3 are one with their sum (inceptionv2_gcn.py:69-88); the conv
+    bias passes through the aggregation as bias[k, c] * colsum(A_eff[k])[w]."""
+    a_eff = adjs[0]
+    for extra in adjs[1:]:
+        a_eff = a_eff + extra
+    K = a_eff.shape[0]
+    kc, cin = weight.shape[0], weight.shape[1]
+    cout = kc // K
+    vals = a_eff.reshape(-1).index_select(0, pattern.flat_idx)
+    wc = weight.view(K, cout, cin).permute(0, 2, 1).reshape(K * cin, cout)
+    if bias is None:
+        biasterm = a_eff.new_zeros(a_eff.shape[1], cout)
+    else:
+        biasterm = torch.einsum('kc,kw->wc', bias.view(K, cout), a_eff.sum(1))
+    return vals, wc, biasterm
+
+
+def bottleneck_tcn_operands(conv_start, tcn_1, tcn_2, tcn_3, conv_end, m_imp):
+    """conv_1x1_start / tcn_1,2,3 / conv_1x1_end (st_gcn_mstcn_1x1.py:190-224) ->
+    Wd[C, bp], bd[bp], Weff[15, bp, bp] (tap, in, out), beff[bp], Wu[bp, C], bu[C].
+
+    The three branches scaled by mstcn_importance and summed (:257-261) are ONE 15-tap
+    convolution: the 3- and 9-tap kernels are centred inside the 15-tap window."""
+    b, C = conv_start.weight.shape[0], conv_start.weight.shape[1]
+    bp = padded_bottleneck(b)
+    wd = F.pad(conv_start.weight.view(b, C).t(), (0, bp - b))
+    bd = F.pad(conv_start.bias, (0, bp - b))
+    weff, beff = 0, 0
+    for i, conv in enumerate((tcn_1, tcn_2, tcn_3)):
+        k = conv.weight.shape[2]
+        off = (_TAPS - k) // 2
+        w = conv.weight[:, :, :, 0].permute(2, 1, 0)            # (tap, in, out)
+        weff = weff + F.pad(w, (0, 0, 0, 0, off, off)) * m_imp[i]
+        beff = beff + conv.bias * m_imp[i]
+    weff = F.pad(weff, (0, bp - b, 0, bp - b))
+    beff = F.pad(beff, (0, bp - b))
+    wu = F.pad(conv_end.weight.view(C, b).t(), (0, 0, 0, bp - b))
+    return wd, bd, weff, beff, wu, conv_end.bias
+
+
+class FusedBlockMixin(object):
+    """Drives ops.STBlock for a block whose sub-modules follow the reference's names:
+    ``gcn`` (ConvTemporalGraphical or Inception2), ``tcn_start``, ``conv_1x1_start``, ``tcn_1``,
+    ``tcn_2``, ``tcn_3``, ``conv_1x1_end``, ``tcn_end``, ``residual``."""
+
+    def _init_fused(self, in_channels, out_channels, stride, dropout, residual):
+        self._io = (in_channels, out_channels, stride)
+        self._drop_p = float(dropout)
+        if not residual:
+            self._res_mode = 0
+        elif in_channels == out_channels and stride == 1:
+            self._res_mode = 1
+        else:
+            self._res_mode = 2
+        self._cfg = None
+
+    def _gcn_conv(self):
+        gcn = self.gcn
+        return gcn.branch.conv if hasattr(gcn, 'branch') else gcn.conv
+
+    def _block_cfg(self, pattern):
+        if self._cfg is None or self._cfg.pattern is not pattern:
+            bnr = ops.BNState(self.residual[1]) if self._res_mode == 2 else None
+            ident = SparsePattern.identity(pattern.V, pattern.flat_idx.device) \
+                if self._res_mode == 2 else None
+            b = self.conv_1x1_start.weight.shape[0]
+            self._cfg = ops.BlockCfg(pattern, ident, self._io[2], self._res_mode, self._drop_p,
+                                     ops.BNState(self.tcn_start[0]), ops.BNState(self.tcn_end[0]),
+                                     bnr, padded_bottleneck(b))
+        else:                                  # buffers may have been re-assigned by .to()/load
+            self._cfg.bn1 = ops.BNState(self.tcn_start[0])
+            self._cfg.bn2 = ops.BNState(self.tcn_end[0])
+            if self._res_mode == 2:
+                self._cfg.bnr = ops.BNState(self.residual[1])
+        return self._cfg
+
+    def forward_cl(self, x, adjs, m_imp, pattern):
+        """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
+        cfg = self._block_cfg(pattern)
+        cfg.training = self.training
+        cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
+        conv = self._gcn_conv()
+        vals, wc, biasterm = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
+        wd, bd, weff, beff, wu, bu = bottleneck_tcn_operands(
+            self.conv_1x1_start, self.tcn_1, self.tcn_2, self.tcn_3, self.conv_1x1_end, m_imp)
+        bn1, bn2 = self.tcn_start[0], self.tcn_end[0]
+        wr = btr = bnr_w = bnr_b = None
+        if self._res_mode == 2:
+            rconv, rbn = self.residual[0], self.residual[1]
+            cout, cin = rconv.weight.shape[0], rconv.weight.shape[1]
+            wr = rconv.weight.view(cout, cin).t()
+            btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout)
+            bnr_w, bnr_b = rbn.weight, rbn.bias
+        out = ops.STBlock.apply(x, vals, wc, biasterm, bn1.weight, bn1.bias, wd, bd, weff, beff, wu,
+                                bu, bn2.weight, bn2.bias, wr, btr, bnr_w, bnr_b, cfg)
+        if self.training:
+            for bn in (bn1, bn2) + ((self.residual[1],) if self._res_mode == 2 else ()):
+                bn.num_batches_tracked += 1
+        self.last_seed = cfg.seed
+        return out
+
+
+class FusedModelMixin(object):
+    """Model.forward / extract_feature shared by every variant (st_gcnold.py:71-120): data_bn
+    with the layout change, the block loop, global pooling, the ``fcn`` 1x1 conv."""
+
+    def _pattern(self):
+        dev = self.A.device
+        pat = getattr(self, '_pat', None)
+        key = (dev, self.A._version, self.A.data_ptr())
+        if pat is None or getattr(self, '_pat_key', None) != key:
+            mask = self.A != 0
+            for name in ('A2', 'A3'):
+                if hasattr(self, name):
+                    mask = mask | (getattr(self, name) != 0)
+            pat = SparsePattern(mask.cpu().numpy(), dev)
+            self._pat, self._pat_key = pat, key
+        return pat
+
+    def _require_cuda(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('istgcn_b200: this model only runs on a CUDA sm_100a device '
+                               '(got a CPU tensor); there is no CPU fallback')
+
+    def _trunk(self, x):
+        self._require_cuda(x)
+        N, C, T, V, M = x.size()
+        x = ops.DataBN.apply(x.float(), self.data_bn.weight, self.data_bn.bias,
+                             ops.BNState(self.data_bn), self.training)
+        if self.training:
+            self.data_bn.num_batches_tracked += 1
+        pattern = self._pattern()
+        n = len(self.st_gcn_networks)
+        imp1 = self.edge_importance
+        imp2 = getattr(self, 'edge_importance2', None)
+        imp3 = getattr(self, 'edge_importance3', None)
+        m_imp = getattr(self, 'mstcn_importance', None)
+        for i, blk in enumerate(self.st_gcn_networks):
+            adjs = [self.A * imp1[i]]
+            if imp2 is not None:
+                adjs.append(self.A2 * imp2[i])
+                adjs.append(self.A3 * imp3[i])
+            x = blk.forward_cl(x, adjs, m_imp[i] if m_imp is not None else None, pattern)
+        return x
+
+    def forward(self, x):
+        N, C, T, V, M = x.size()
+        y = self._trunk(x)
+        pooled = ops.Pool.apply(y, N, M)
+        w = self.fcn.weight
+        return F.linear(pooled, w.view(w.shape[0], w.shape[1]), self.fcn.bias)
+
+    def extract_feature(self, x):
+        N, C, T, V, M = x.size()
+        y = self._trunk(x)                                   # (N*M, t, v, c)
+        _, t, v, c = y.shape
+        feature = y.view(N, M, t, v, c).permute(0, 4, 2, 3, 1)
+        w = self.fcn.weight
+        out = F.linear(y, w.view(w.shape[0], w.shape[1]), self.fcn.bias)
+        output = out.view(N, M, t, v, -1).permute(0, 4, 2, 3, 1)
+        return output, feature

@@ -1,0 +1,271 @@
+"""torch.autograd Functions over the C ABI (include/istgcn_b200.h).
+
+Layout: activations are channels-last fp32 tensors of shape (N*M, T, V, C) -- the reference's
+(N*M, C, T, V) (net/st_gcnold.py:80) with C moved to the fastest axis -- so a 1x1 convolution is
+a row-major GEMM and a temporal tap is a shift of V rows.
+
+One Function per st_gcn block (``STBlock``): forward launches the fused graph convolution
+(+ strided 1x1 residual conv), the Inception-TCN kernels and the block tail, with the
+training-mode BatchNorm statistics accumulated in the producers' epilogues; backward launches
+the mirrored chain.  Parameter regrouping (A*importance, merged temporal taps, weight
+transposes) is done with tiny differentiable torch ops *outside* the Function, so autograd
+maps the kernel's gradients back onto the reference's parameter tensors.
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib, math_flag
+from ._lib import call, f64, i64, u64
+
+
+def _coeffs(n, C, device):
+    buf = torch.empty(n, C, device=device, dtype=torch.float32)
+    return [buf[i] for i in range(n)]
+
+
+class BNState(object):
+    """The mutable bits of an nn.BatchNorm module that the kernels touch."""
+    __slots__ = ('running_mean', 'running_var', 'momentum', 'eps')
+
+    def __init__(self, bn):
+        self.running_mean, self.running_var = bn.running_mean, bn.running_var
+        self.momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        self.eps = float(bn.eps)
+
+
+def _bn_forward_coeffs(training, sum_, sumsq, count, weight, bias, st, C, device):
+    """-> scale, shift, mean, rstd (mean/rstd None in eval mode)."""
+    if training:
+        scale, shift, mean, rstd = _coeffs(4, C, device)
+        call('bn_finalize', sum_, sumsq, f64(count), weight, bias, st.running_mean, st.running_var,
+             st.momentum, st.eps, scale, shift, mean, rstd, C)
+        return scale, shift, mean, rstd
+    scale, shift = _coeffs(2, C, device)
+    call('bn_eval_coeffs', weight, bias, st.running_mean, st.running_var, st.eps, scale, shift, C)
+    return scale, shift, None, None
+
+
+class DataBN(Function):
+    """data_bn + both permutes: (N, C, T, V, M) -> (N*M, T, V, C)   [st_gcnold.py:74-80]."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, st, training):
+        x = x.contiguous()
+        N, C, T, V, M = x.shape
+        dev = x.device
+        if training:
+            stats = torch.zeros(2, V * C, device=dev, dtype=torch.float64)
+            call('data_bn_stats', x, stats[0], stats[1], N, C, T, V, M)
+            scale, shift, mean, rstd = _bn_forward_coeffs(True, stats[0], stats[1], N * M * T, weight,
+                                                          bias, st, V * C, dev)
+        else:
+            scale, shift, mean, rstd = _bn_forward_coeffs(False, None, None, 0, weight, bias, st,
+                                                          V * C, dev)
+        y = torch.empty(N * M, T, V, C, device=dev, dtype=torch.float32)
+        call('data_bn_apply', x, scale, shift, y, N, C, T, V, M)
+        ctx.training = training
+        ctx.dims = (N, C, T, V, M)
+        if training:
+            ctx.save_for_backward(x, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if not ctx.training:
+            raise RuntimeError('istgcn: backward through eval-mode BatchNorm is not supported')
+        x, mean, rstd = ctx.saved_tensors
+        N, C, T, V, M = ctx.dims
+        d = torch.zeros(2, V * C, device=x.device, dtype=torch.float64)
+        call('data_bn_bwd', x, gy.contiguous(), mean, rstd, d[0], d[1], N, C, T, V, M)
+        d = d.float()
+        return None, d[0], d[1], None, None
+
+
+class BlockCfg(object):
+    """Static (non-tensor) description of one block, built once per module."""
+
+    def __init__(self, pattern, ident, stride, res_mode, drop_p, bn1, bn2, bnr, bp):
+        self.pattern, self.ident = pattern, ident
+        self.stride, self.res_mode, self.drop_p, self.bp = stride, res_mode, float(drop_p), bp
+        self.bn1, self.bn2, self.bnr = bn1, bn2, bnr
+        self.ones = None
+        self.training = True
+        self.seed = 0
+
+
+class STBlock(Function):
+    """One IST-GCN block: graph conv -> BN -> ReLU -> 1x1 -> {3,9,15}x1 -> 1x1 -> BN -> dropout
+    -> + residual -> ReLU  (net/st_gcn_mstcn_1x1.py:250-266 with tgcn.py:76-89 or
+    inceptionv2_gcn.py:64-89 as the graph conv)."""
+
+    @staticmethod
+    def forward(ctx, x, vals, Wc, biasterm, bn1_w, bn1_b, Wd, bd, Weff, beff, Wu, bu, bn2_w,
+                bn2_b, Wr, biasterm_r, bnr_w, bnr_b, cfg):
+        x = x.contiguous()
+        NM, T, V, Cin = x.shape
+        Cout = Wc.shape[1]
+        pat, s, bp = cfg.pattern, cfg.stride, cfg.bp
+        K = pat.K
+        Tout = (T - 1) // s + 1
+        R_in, R_out = NM * T * V, NM * Tout * V
+        dev = x.device
+        training = cfg.training
+        math = math_flag()
+        drop_p = cfg.drop_p if training else 0.0
+        vals, Wc, biasterm = vals.contiguous(), Wc.contiguous(), biasterm.contiguous()
+        Wd, bd, Weff, beff = Wd.contiguous(), bd.contiguous(), Weff.contiguous(), beff.contiguous()
+        Wu, bu = Wu.contiguous(), bu.contiguous()
+        stats = torch.zeros(6, Cout, device=dev, dtype=torch.float64) if training else [None] * 6
+
+        z = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
+        call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
+             stats[0], stats[1], NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        scale1, shift1, mean1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w,
+                                                          bn1_b, cfg.bn1, Cout, dev)
+        h1 = torch.empty(NM, T, V, bp, device=dev, dtype=torch.float32)
+        h2 = torch.empty(NM, Tout, V, bp, device=dev, dtype=torch.float32)
+        u = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
+        call('tcn_fwd', z, scale1, shift1, Wd, bd, Weff, beff, Wu, bu, h1, h2, u, stats[2], stats[3],
+             NM, T, V, Cout, bp, s, math)
+        scale2, shift2, mean2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w,
+                                                          bn2_b, cfg.bn2, Cout, dev)
+        rres = scale_r = shift_r = mean_r = rstd_r = None
+        res = None
+        if cfg.res_mode == 1:
+            res = x
+        elif cfg.res_mode == 2:
+            idn = cfg.ident
+            if cfg.ones is None or cfg.ones.device != dev:
+                cfg.ones = torch.ones(V, device=dev, dtype=torch.float32)
+            Wr, biasterm_r = Wr.contiguous(), biasterm_r.contiguous()
+            rres = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
+            call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
+                 rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+            scale_r, shift_r, mean_r, rstd_r = _bn_forward_coeffs(
+                training, stats[4], stats[5], R_out, bnr_w, bnr_b, cfg.bnr, Cout, dev)
+            res = rres
+        out = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
+        call('block_tail_fwd', u, scale2, shift2, res, scale_r, shift_r, out, i64(R_out), Cout,
+             float(drop_p), u64(cfg.seed))
+
+        ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
+        ctx.dims = (NM, T, Tout, V, Cin, Cout)
+        if training:
+            ctx.save_for_backward(x, vals, Wc, z, h1, h2, u, out, rres, scale1, shift1, mean1, rstd1,
+                                  mean2, rstd2, mean_r, rstd_r, Wd, Weff, Wu, Wr, bn1_w, bn2_w, bnr_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        if not ctx.training:
+            raise RuntimeError('istgcn: backward through eval-mode BatchNorm is not supported')
+        (x, vals, Wc, z, h1, h2, u, out, rres, scale1, shift1, mean1, rstd1, mean2, rstd2, mean_r,
+         rstd_r, Wd, Weff, Wu, Wr, bn1_w, bn2_w, bnr_w) = ctx.saved_tensors
+        cfg, math, drop_p, seed = ctx.cfg, ctx.math, ctx.drop_p, ctx.seed
+        NM, T, Tout, V, Cin, Cout = ctx.dims
+        pat, s, bp = cfg.pattern, cfg.stride, cfg.bp
+        K = pat.K
+        R_in, R_out = NM * T * V, NM * Tout * V
+        dev = x.device
+        gout = gout.contiguous()
+        sums = torch.zeros(6, Cout, device=dev, dtype=torch.float64)
+        go = torch.empty_like(gout)
+        call('block_tail_bwd', gout, out, u, mean2, rstd2, rres, mean_r, rstd_r, go, sums[0], sums[1],
+             sums[2] if rres is not None else None, sums[3] if rres is not None else None,
+             i64(R_out), Cout, float(drop_p), u64(seed))
+        p2, q2, r2, dg2, db2 = _coeffs(5, Cout, dev)
+        call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, mean2, rstd2, p2, q2, r2, dg2, db2,
+             Cout)
+        dWd, dbd = torch.zeros_like(Wd), torch.zeros(bp, device=dev)
+        dWeff, dbeff = torch.zeros_like(Weff), torch.zeros(bp, device=dev)
+        dWu, dbu = torch.zeros_like(Wu), torch.zeros(Cout, device=dev)
+        g1 = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
+        dh2 = torch.empty(R_out, bp, device=dev, dtype=torch.float32)
+        dh1 = torch.empty(R_in, bp, device=dev, dtype=torch.float32)
+        call('tcn_bwd', go, u, p2, q2, r2, z, scale1, shift1, mean1, rstd1, h1, h2, Wd, Weff, Wu, dh2,
+             dh1, g1, sums[4], sums[5], dWd, dbd, dWeff, dbeff, dWu, dbu, NM, T, V, Cout, bp, s,
+             float(drop_p), u64(seed), math)
+        p1, q1, r1, dg1, db1 = _coeffs(5, Cout, dev)
+        call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, mean1, rstd1, p1, q1, r1, dg1, db1,
+             Cout)
+        gin = torch.empty_like(x)
+        dvals = torch.zeros_like(vals)
+        call('gcn_bwd_x', g1, z, p1, q1, r1, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id, pat.nnz,
+             go if cfg.res_mode == 1 else None, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
+        call('gcn_bwd_w', g1, z, p1, q1, r1, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz,
+             dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        dWr = dbtr = dgr = dbr = None
+        if cfg.res_mode == 2:
+            idn = cfg.ident
+            pr, qr, rr, dgr, dbr = _coeffs(5, Cout, dev)
+            call('bn_bwd_coeffs', sums[2], sums[3], f64(R_out), bnr_w, mean_r, rstd_r, pr, qr, rr, dgr,
+                 dbr, Cout)
+            call('gcn_bwd_x', go, rres, pr, qr, rr, x, Wr, cfg.ones, idn.src_ptr, idn.src_kw,
+                 idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+            dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, Cout, device=dev)
+            call('gcn_bwd_w', go, rres, pr, qr, rr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id,
+                 V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+        return (gin, dvals, dWc, dbt, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr, dbtr,
+                dgr, dbr, None)
+
+
+class GraphConv(Function):
+    """The fused graph convolution on its own (no BatchNorm behind it): tgcn.py:76-89 /
+    inceptionv2_gcn.py:64-89.  x (NM, T, V, Cin) channels-last -> (NM, T, V, Cout)."""
+
+    @staticmethod
+    def forward(ctx, x, vals, Wc, biasterm, pattern):
+        x, vals, Wc, biasterm = x.contiguous(), vals.contiguous(), Wc.contiguous(), biasterm.contiguous()
+        NM, T, V, Cin = x.shape
+        Cout = Wc.shape[1]
+        z = torch.empty(NM, T, V, Cout, device=x.device, dtype=torch.float32)
+        math = math_flag()
+        call('gcn_fwd', x, Wc, biasterm, vals, pattern.dst_ptr, pattern.dst_src, pattern.dst_id,
+             pattern.nnz, z, None, None, NM * T, V, pattern.K, Cin, Cout, 0, 0, 1, math)
+        ctx.pattern, ctx.math = pattern, math
+        ctx.save_for_backward(x, vals, Wc)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, vals, Wc = ctx.saved_tensors
+        pat, math = ctx.pattern, ctx.math
+        NM, T, V, Cin = x.shape
+        Cout = Wc.shape[1]
+        gz = gz.contiguous()
+        gin, dvals = torch.empty_like(x), torch.zeros_like(vals)
+        call('gcn_bwd_x', gz, None, None, None, None, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id,
+             pat.nnz, None, gin, dvals, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
+        dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=x.device)
+        call('gcn_bwd_w', gz, None, None, None, None, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
+             pat.nnz, dWc, dbt, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
+        return gin, dvals, dWc, dbt, None
+
+
+class Pool(Function):
+    """F.avg_pool2d over (T, V) then mean over M (st_gcnold.py:89-90): (N*M, T, V, C) -> (N, C)."""
+
+    @staticmethod
+    def forward(ctx, x, N, M):
+        x = x.contiguous()
+        NM, T, V, C = x.shape
+        pooled = torch.empty(N, C, device=x.device, dtype=torch.float32)
+        call('pool_fwd', x, pooled, N, M, T * V, C)
+        ctx.dims = (N, M, T, V, C)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        N, M, T, V, C = ctx.dims
+        gx = torch.empty(N * M, T, V, C, device=g.device, dtype=torch.float32)
+        call('pool_bwd', g.contiguous(), gx, N, M, T * V, C)
+        return gx, None, None
+
+
+def dropout_mask(numel, p, seed, device):
+    """The keep-mask STBlock's counter-based dropout uses for a (rows, C) tensor of ``numel``
+    elements and ``seed`` -- exported for parity tests."""
+    mask = torch.empty(numel, device=device, dtype=torch.uint8)
+    call('dropout_mask', mask, _lib.i64(numel), float(p), u64(seed))
+    return mask

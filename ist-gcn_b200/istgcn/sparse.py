@@ -1,0 +1,45 @@
+"""Static non-zero lists of the partitioned adjacency (the "SpA" arguments of the C ABI).
+
+A_eff = A*imp (+ A2*imp2 + A3*imp3) keeps the fixed zero pattern of A U A2 U A3 because the
+importances multiply element-wise (net/st_gcnold.py:86, net/st_gcn_msgcn.py:116-117;
+SURVEY.md App. A: 197 of 2500 entries for NTU 'spatial_3_sym').  The lists are built once per
+model from the registered buffers and cached on the device."""
+import numpy as np
+import torch
+
+
+class SparsePattern(object):
+    """Index arrays for a (K, V, V) stack with non-zero pattern ``mask``.
+
+    canonical order: sorted by (k, v, w) -> ``flat_idx`` (index into A_eff.reshape(-1))
+    destination order (forward aggregation): grouped by (k, w): dst_ptr[K*V+1], dst_src, dst_id
+    source order (backward): grouped by v: src_ptr[V+1], src_kw (= k*V + w), src_id
+    """
+
+    def __init__(self, mask, device):
+        mask = np.asarray(mask, dtype=bool)
+        K, V, V2 = mask.shape
+        assert V == V2
+        k, v, w = np.nonzero(mask)                      # already sorted by (k, v, w)
+        nnz = k.size
+        self.K, self.V, self.nnz = K, V, int(nnz)
+        ids = np.arange(nnz)
+        order_d = np.lexsort((v, w, k))                 # by k, then w, then v
+        counts = np.bincount(k[order_d] * V + w[order_d], minlength=K * V)
+        dst_ptr = np.concatenate([[0], np.cumsum(counts)])
+        order_s = np.lexsort((w, k, v))                 # by v, then k, then w
+        counts_s = np.bincount(v[order_s], minlength=V)
+        src_ptr = np.concatenate([[0], np.cumsum(counts_s)])
+
+        def dev(a, dt=torch.int32):
+            return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
+        self.flat_idx = dev(k * V * V + v * V + w, torch.int64)
+        self.dst_ptr, self.dst_src, self.dst_id = dev(dst_ptr), dev(v[order_d]), dev(ids[order_d])
+        self.src_ptr = dev(src_ptr)
+        self.src_kw = dev(k[order_s] * V + w[order_s])
+        self.src_id = dev(ids[order_s])
+
+    @classmethod
+    def identity(cls, V, device):
+        """K = 1, A = I: turns the fused graph conv into a plain (strided) 1x1 convolution."""
+        return cls(np.eye(V, dtype=bool)[None], device)
