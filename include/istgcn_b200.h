@@ -48,8 +48,9 @@ int istgcn_check_device(void);
  * (must be zeroed by the caller).  apply: y rows[((n*M+m)*T + t)*V + v][C].               */
 int istgcn_data_bn_stats(const float* x, double* sum, double* sumsq,
                          int N, int C, int T, int V, int M, istgcn_stream_t s);
-int istgcn_data_bn_apply(const float* x, const float* scale, const float* shift, float* y,
-                         int N, int C, int T, int V, int M, istgcn_stream_t s);
+int istgcn_data_bn_apply(const float* x, const float* mean, const float* scale,
+                         const float* beta, float* y, int N, int C, int T, int V, int M,
+                         istgcn_stream_t s);
 /* backward of the affine parameters only (the network input needs no gradient):
  * dgamma[ch] = sum g*xhat, dbeta[ch] = sum g, with g rows[...][C] channels-last.           */
 int istgcn_data_bn_bwd(const float* x, const float* g, const float* mean, const float* rstd,
@@ -57,22 +58,23 @@ int istgcn_data_bn_bwd(const float* x, const float* g, const float* mean, const 
                        istgcn_stream_t s);
 
 /* ---- BatchNorm bookkeeping (nn.BatchNorm2d train/eval; st_gcnold.py:165,174) -----------
- * From double sum/sumsq over `count` elements: mean, biased var -> scale = gamma*rstd,
- * shift = beta - mean*scale; running stats updated with momentum (unbiased var) when
+ * Every kernel applies BatchNorm in the cancellation-free form y = (x - mean)*scale + beta and
+ * its backward as dx = p*((g - m1) - c*(x - mean)).
+ * finalize: from double sum/sumsq over `count` elements -> mean, rstd (biased variance),
+ * scale = gamma*rstd; running stats updated with momentum (unbiased variance) when
  * running_mean != NULL.                                                                    */
 int istgcn_bn_finalize(const double* sum, const double* sumsq, double count,
-                       const float* gamma, const float* beta, float* running_mean,
-                       float* running_var, float momentum, float eps, float* scale,
-                       float* shift, float* mean, float* rstd, int C, istgcn_stream_t s);
-/* eval mode: scale/shift from the running statistics */
-int istgcn_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
-                          const float* running_var, float eps, float* scale, float* shift,
+                       const float* gamma, float* running_mean, float* running_var,
+                       float momentum, float eps, float* scale, float* mean, float* rstd, int C,
+                       istgcn_stream_t s);
+/* eval mode: scale = gamma / sqrt(running_var + eps) (mean = running_mean is passed as is) */
+int istgcn_bn_eval_coeffs(const float* gamma, const float* running_var, float eps, float* scale,
                           int C, istgcn_stream_t s);
-/* backward coefficients: with sg = sum g, sgx = sum g*xhat (double) over `count` elements,
- * dx = p*g + q*x + r per channel; also dgamma = sgx, dbeta = sg.                           */
+/* backward coefficients: with sg = sum g, sgx = sum g*xhat (double) over `count` elements:
+ * p = gamma*rstd, m1 = sg/count, c = rstd*sgx/count; also dgamma = sgx, dbeta = sg.        */
 int istgcn_bn_bwd_coeffs(const double* sg, const double* sgx, double count, const float* gamma,
-                         const float* mean, const float* rstd, float* p, float* q, float* r,
-                         float* dgamma, float* dbeta, int C, istgcn_stream_t s);
+                         const float* rstd, float* p, float* m1, float* c, float* dgamma,
+                         float* dbeta, int C, istgcn_stream_t s);
 
 /* ---- fused graph convolution ------------------------------------------------------------
  * reference: net/utils/tgcn.py:76-89 (conv1x1 to K*Cout, einsum 'nkctv,kvw->nctw') and
@@ -93,26 +95,28 @@ int istgcn_gcn_fwd(const float* x, const float* Wc, const float* biasterm, const
                    int frames, int V, int K, int Cin, int Cout,
                    int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
 /* input gradient + adjacency gradient.  dz is formed on the fly from the BatchNorm-backward
- * coefficients: dz = p[c]*g[r][c] + q[c]*z[r][c] + r0[c] (pass q = NULL to use g as dz).
+ * coefficients: dz = bn_p*((g - bn_m1) - bn_c*(z - bn_mu)) per channel (bn_p = NULL: dz = g).
  *   gin[(f,v)][ci] = sum_k sum_w A_eff[k][v][w] (dz Wc_k^T)[(f,w)][ci]  (+ add_in if not NULL)
  *   dvals[id] += sum_{f,ci} x[(f,v)][ci] * (dz Wc_k^T)[(f,w)][ci]       (caller-zeroed)     */
-int istgcn_gcn_bwd_x(const float* g, const float* z, const float* p, const float* q,
-                     const float* r0, const float* x, const float* Wc, const float* vals,
+int istgcn_gcn_bwd_x(const float* g, const float* z, const float* bn_p, const float* bn_m1,
+                     const float* bn_c, const float* bn_mu,
+                     const float* x, const float* Wc, const float* vals,
                      const int* src_ptr, const int* src_kw, const int* src_id, int nnz,
                      const float* add_in, float* gin, float* dvals,
                      int frames, int V, int K, int Cin, int Cout,
                      int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
 /* weight gradient: dWc[K*Cin][Cout] += X'^T dz, dbiasterm[V][Cout] += sum_f dz (both
  * caller-zeroed fp32).                                                                     */
-int istgcn_gcn_bwd_w(const float* g, const float* z, const float* p, const float* q,
-                     const float* r0, const float* x, const float* vals,
+int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const float* bn_m1,
+                     const float* bn_c, const float* bn_mu,
+                     const float* x, const float* vals,
                      const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
                      float* dWc, float* dbiasterm,
                      int frames, int V, int K, int Cin, int Cout,
                      int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
 
 /* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
- *   a  = relu(z*scale1 + shift1)                       (tcn_start: BN + ReLU)
+ *   a  = relu((z - mean1)*scale1 + beta1)              (tcn_start: BN + ReLU)
  *   h1 = a Wd + bd                                     (conv_1x1_start, C -> b)
  *   h2[to] = sum_tap Weff[tap] h1[to*stride + tap - 7] + beff   (tcn_1/2/3 merged: 15 taps,
  *            Weff = imp0*W3x1 (+6) + imp1*W9x1 (+3) + imp2*W15x1, zero padding on h1)
@@ -120,30 +124,31 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* p, const float
  * Wd[C][bp], Weff[15][bp(in)][bp(out)], Wu[bp][C]; bp = b rounded up to a multiple of 8
  * (padding columns/rows zero).  h1[(n,t,v)][bp] and h2[(n,to,v)][bp] are saved for backward.
  * stats of u optional.                                                                     */
-int istgcn_tcn_fwd(const float* z, const float* scale1, const float* shift1, const float* Wd,
-                   const float* bd, const float* Weff, const float* beff, const float* Wu,
+int istgcn_tcn_fwd(const float* z, const float* mean1, const float* scale1, const float* beta1,
+                   const float* Wd, const float* bd, const float* Weff, const float* beff, const float* Wu,
                    const float* bu, float* h1, float* h2, float* u, double* stat_sum,
                    double* stat_sumsq, int NM, int T, int V, int C, int bp, int stride,
                    int math, istgcn_stream_t s);
-/* backward.  du = p2*gy + q2*u + r2 where gy = go * keep(dropout); writes g1 = d(loss)/d(bn1
+/* backward.  du = p2*((gy - m12) - c2*(u - mean2)), gy = go * keep(dropout); writes g1 = d(loss)/d(bn1
  * output) masked by the ReLU, accumulates sum g1 and sum g1*zhat (double[C], caller-zeroed)
  * and all weight gradients (caller-zeroed fp32).  dh2_ws[(n,to,v)][bp] and dh1_ws[(n,t,v)][bp]
  * are caller-provided scratch (fully overwritten).                                         */
-int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float* q2,
-                   const float* r2, const float* z, const float* scale1, const float* shift1,
-                   const float* mean1, const float* rstd1, const float* h1, const float* h2,
+int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float* m12,
+                   const float* c2, const float* mean2, const float* z, const float* scale1,
+                   const float* beta1, const float* mean1, const float* rstd1,
+                   const float* h1, const float* h2,
                    const float* Wd, const float* Weff, const float* Wu,
                    float* dh2_ws, float* dh1_ws, float* g1, double* sg1, double* sg1x, float* dWd, float* dbd, float* dWeff,
                    float* dbeff, float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
                    int stride, float drop_p, uint64_t drop_seed, int math, istgcn_stream_t s);
 
 /* ---- block tail: BN2 -> dropout -> + residual -> ReLU (st_gcn_mstcn_1x1.py:262-266) -----
- * out = relu((u*scale2 + shift2)*keep/(1-p) + res) where res = NULL (0), the block input
- * (identity) or rres*scale_r + shift_r (strided conv + BN).  Rows = NM*T*V, C channels.     */
-int istgcn_block_tail_fwd(const float* u, const float* scale2, const float* shift2,
-                          const float* res, const float* scale_r, const float* shift_r,
-                          float* out, long long rows, int C, float drop_p, uint64_t drop_seed,
-                          istgcn_stream_t s);
+ * out = relu(BN2(u)*keep/(1-p) + res) where res = NULL (0), the block input (identity,
+ * scale_r = NULL) or BNr(res) (strided conv + BN).  Rows = NM*T*V, C channels.             */
+int istgcn_block_tail_fwd(const float* u, const float* mean2, const float* scale2,
+                          const float* beta2, const float* res, const float* mean_r,
+                          const float* scale_r, const float* beta_r, float* out, long long rows,
+                          int C, float drop_p, uint64_t drop_seed, istgcn_stream_t s);
 /* backward reduction pass: go = gout * (out > 0) written to `go` (may alias gout); BN2 sums
  * sum gy, sum gy*uhat with gy = go*keep/(1-p); if rres != NULL also sum go, sum go*rhat.    */
 int istgcn_block_tail_bwd(const float* gout, const float* out, const float* u,

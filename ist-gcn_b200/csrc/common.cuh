@@ -63,9 +63,9 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // row-indexed-by-t operands (A_T, B) need ld % 16 == 8.
 // PRECISE = 3xTF32 error compensation (small cross terms first).
 template <int MT, int NT, bool A_T, bool B_T, bool PRECISE>
-__device__ __forceinline__ void warp_mma(float (&acc)[MT][NT][4], const float* __restrict__ A,
-                                         int lda, const float* __restrict__ B, int ldb,
-                                         int kdim, int lane) {
+__device__ __forceinline__ void warp_mma_raw(float (&acc)[MT][NT][4], const float* __restrict__ A,
+                                             int lda, const float* __restrict__ B, int ldb,
+                                             int kdim, int lane) {
     const int g = lane >> 2, t = lane & 3;
     for (int k0 = 0; k0 < kdim; k0 += 8) {
         uint32_t ah[MT][4], al[MT][4];
@@ -103,6 +103,37 @@ __device__ __forceinline__ void warp_mma(float (&acc)[MT][NT][4], const float* _
     }
 }
 
+// The tensor core adds products into the accumulator with truncation, so a long K loop drifts
+// (~K * 2^-24).  In PRECISE mode every 32-deep slice accumulates into a fresh fragment that is
+// then added to the running sum with ordinary round-to-nearest fp32 adds.
+template <int MT, int NT, bool A_T, bool B_T, bool PRECISE>
+__device__ __forceinline__ void warp_mma(float (&acc)[MT][NT][4], const float* __restrict__ A,
+                                         int lda, const float* __restrict__ B, int ldb,
+                                         int kdim, int lane) {
+    if (PRECISE) {
+        for (int k0 = 0; k0 < kdim; k0 += 32) {
+            float part[MT][NT][4];
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) part[a][b][c] = 0.f;
+            const int kk = kdim - k0 < 32 ? kdim - k0 : 32;
+            warp_mma_raw<MT, NT, A_T, B_T, true>(part, A_T ? A + k0 * lda : A + k0, lda,
+                                                 B_T ? B + k0 : B + k0 * ldb, ldb, kk, lane);
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int b = 0; b < NT; ++b)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][b][c] += part[a][b][c];
+        }
+    } else {
+        warp_mma_raw<MT, NT, A_T, B_T, false>(acc, A, lda, B, ldb, kdim, lane);
+    }
+}
+
 // one 16x8x8 step on already-loaded fp32 fragment values
 template <bool PRECISE>
 __device__ __forceinline__ void mma_step(float (&acc)[4], const float (&a)[4], const float (&b)[2]) {
@@ -118,10 +149,15 @@ __device__ __forceinline__ void mma_step(float (&acc)[4], const float (&a)[4], c
         else bh[i] = to_tf32(b[i]);
     }
     if (PRECISE) {
-        mma_m16n8k8(acc, al, bh);
-        mma_m16n8k8(acc, ah, bl);
+        float part[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_m16n8k8(part, al, bh);
+        mma_m16n8k8(part, ah, bl);
+        mma_m16n8k8(part, ah, bh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] += part[i];
+    } else {
+        mma_m16n8k8(acc, ah, bh);
     }
-    mma_m16n8k8(acc, ah, bh);
 }
 
 template <int MT, int NT>
@@ -159,6 +195,18 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float 
     x ^= x >> 31;
     const float u = (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);   // 24 bits -> [0, 1)
     return u >= p;
+}
+
+// BatchNorm forward on one element, cancellation-free: (x - mean) * scale + beta
+__device__ __forceinline__ float bn_apply(float x, float mean, float scale, float beta) {
+    return fmaf(x - mean, scale, beta);
+}
+// BatchNorm backward on one element: p * ((g - m1) - c * (x - mean)), with p = gamma*rstd,
+// m1 = mean(g), c = rstd * mean(g * xhat).  Written with explicit differences: when g is
+// nearly constant over the batch (e.g. right behind a global average pool) g - m1 is exact,
+// whereas a precomputed p*g + q*x + r form carries a systematic 2^-24 * |p*m1| bias per channel.
+__device__ __forceinline__ float bn_back(float g, float x, float p, float m1, float c, float mean) {
+    return p * ((g - m1) - c * (x - mean));
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) {

@@ -71,8 +71,9 @@ __global__ void data_bn_stats_kernel(const float* __restrict__ x, double* __rest
 }
 
 // thread per output row (n, m, t, v): gathers C strided inputs, writes C contiguous outputs.
-__global__ void data_bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, float* __restrict__ y,
+__global__ void data_bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                     const float* __restrict__ scale,
+                                     const float* __restrict__ beta, float* __restrict__ y,
                                      int N, int C, int T, int V, int M) {
     const long long rows = (long long)N * M * T * V;
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < rows;
@@ -85,7 +86,7 @@ __global__ void data_bn_apply_kernel(const float* __restrict__ x, const float* _
         const int n = (int)(q / M);
         for (int c = 0; c < C; ++c) {
             const float val = x[((((size_t)n * C + c) * T + t) * V + v) * M + m];
-            y[r * C + c] = val * scale[v * C + c] + shift[v * C + c];
+            y[r * C + c] = bn_apply(val, mean[v * C + c], scale[v * C + c], beta[v * C + c]);
         }
     }
 }
@@ -128,18 +129,15 @@ __global__ void data_bn_bwd_kernel(const float* __restrict__ x, const float* __r
 // ------------------------------------------------------------------------------ BN coefficients
 __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double* __restrict__ sumsq,
                                    double count, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* running_mean,
-                                   float* running_var, float momentum, float eps, float* scale,
-                                   float* shift, float* mean, float* rstd, int C) {
+                                   float* running_mean, float* running_var, float momentum,
+                                   float eps, float* scale, float* mean, float* rstd, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double mu = sum[c] / count;
     double var = sumsq[c] / count - mu * mu;
     if (var < 0) var = 0;
     const float rs = (float)(1.0 / sqrt(var + (double)eps));
-    const float sc = gamma[c] * rs;
-    scale[c] = sc;
-    shift[c] = beta[c] - (float)mu * sc;
+    scale[c] = gamma[c] * rs;
     if (mean) mean[c] = (float)mu;
     if (rstd) rstd[c] = rs;
     if (running_mean) {
@@ -149,39 +147,35 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sum, const double*
     }
 }
 
-__global__ void bn_eval_coeffs_kernel(const float* gamma, const float* beta, const float* rm,
-                                      const float* rv, float eps, float* scale, float* shift,
+__global__ void bn_eval_coeffs_kernel(const float* gamma, const float* rv, float eps, float* scale,
                                       int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const float sc = gamma[c] * rsqrtf(rv[c] + eps);
-    scale[c] = sc;
-    shift[c] = beta[c] - rm[c] * sc;
+    scale[c] = gamma[c] / sqrtf(rv[c] + eps);
 }
 
 // y = gamma*xhat + beta, xhat = (x-mean)*rstd:  dx = gamma*rstd*(g - mean(g) - xhat*mean(g*xhat))
-//    = p*g + q*x + r,  p = gamma*rstd, q = -p*rstd*m2, r = -p*m1 + p*rstd*m2*mean
+//    = p*((g - m1) - c*(x - mean)),  p = gamma*rstd, m1 = mean(g), c = rstd*mean(g*xhat)
 __global__ void bn_bwd_coeffs_kernel(const double* sg, const double* sgx, double count,
-                                     const float* gamma, const float* mean, const float* rstd,
-                                     float* p, float* q, float* r, float* dgamma, float* dbeta,
-                                     int C) {
+                                     const float* gamma, const float* rstd, float* p, float* m1,
+                                     float* cc, float* dgamma, float* dbeta, int C) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    const double m1 = sg[c] / count, m2 = sgx[c] / count;
-    const double pp = (double)gamma[c] * (double)rstd[c];
-    p[c] = (float)pp;
-    q[c] = (float)(-pp * rstd[c] * m2);
-    r[c] = (float)(-pp * m1 + pp * rstd[c] * m2 * mean[c]);
+    p[c] = gamma[c] * rstd[c];
+    m1[c] = (float)(sg[c] / count);
+    cc[c] = (float)((double)rstd[c] * (sgx[c] / count));
     if (dgamma) dgamma[c] = (float)sgx[c];
     if (dbeta) dbeta[c] = (float)sg[c];
 }
 
 // ------------------------------------------------------------------------------ block tail
 // mode: 0 no residual, 1 identity (res = block input), 2 conv+BN (res*scale_r + shift_r)
-__global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* __restrict__ scale2,
-                                      const float* __restrict__ shift2, const float* __restrict__ res,
+__global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* __restrict__ mean2,
+                                      const float* __restrict__ scale2,
+                                      const float* __restrict__ beta2, const float* __restrict__ res,
+                                      const float* __restrict__ mean_r,
                                       const float* __restrict__ scale_r,
-                                      const float* __restrict__ shift_r, float* __restrict__ out,
+                                      const float* __restrict__ beta_r, float* __restrict__ out,
                                       long long n4, int C, int mode, float drop_p, float keep_scale,
                                       uint64_t seed) {
     const int c4 = C >> 2;
@@ -189,9 +183,9 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
          i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % c4) * 4;
         const float4 uu = ld4(u + i * 4);
-        const float4 sc = ld4(scale2 + c), sh = ld4(shift2 + c);
-        float y[4] = {uu.x * sc.x + sh.x, uu.y * sc.y + sh.y, uu.z * sc.z + sh.z,
-                      uu.w * sc.w + sh.w};
+        const float4 mu = ld4(mean2 + c), sc = ld4(scale2 + c), be = ld4(beta2 + c);
+        float y[4] = {bn_apply(uu.x, mu.x, sc.x, be.x), bn_apply(uu.y, mu.y, sc.y, be.y),
+                      bn_apply(uu.z, mu.z, sc.z, be.z), bn_apply(uu.w, mu.w, sc.w, be.w)};
         if (drop_p > 0.f) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -202,9 +196,9 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
             y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
         } else if (mode == 2) {
             const float4 r = ld4(res + i * 4);
-            const float4 a = ld4(scale_r + c), b = ld4(shift_r + c);
-            y[0] += r.x * a.x + b.x; y[1] += r.y * a.y + b.y;
-            y[2] += r.z * a.z + b.z; y[3] += r.w * a.w + b.w;
+            const float4 m = ld4(mean_r + c), a = ld4(scale_r + c), b = ld4(beta_r + c);
+            y[0] += bn_apply(r.x, m.x, a.x, b.x); y[1] += bn_apply(r.y, m.y, a.y, b.y);
+            y[2] += bn_apply(r.z, m.z, a.z, b.z); y[3] += bn_apply(r.w, m.w, a.w, b.w);
         }
         st4(out + i * 4, make_float4(fmaxf(y[0], 0.f), fmaxf(y[1], 0.f), fmaxf(y[2], 0.f),
                                      fmaxf(y[3], 0.f)));
@@ -383,13 +377,14 @@ ISTGCN_API int istgcn_data_bn_stats(const float* x, double* sum, double* sumsq, 
     return finish_launch("data_bn_stats");
 }
 
-ISTGCN_API int istgcn_data_bn_apply(const float* x, const float* scale, const float* shift, float* y,
-                                    int N, int C, int T, int V, int M, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(x && scale && shift && y, ISTGCN_E_ARG, "data_bn_apply: null pointer");
+ISTGCN_API int istgcn_data_bn_apply(const float* x, const float* mean, const float* scale,
+                                    const float* beta, float* y, int N, int C, int T, int V, int M,
+                                    istgcn_stream_t s) {
+    ISTGCN_REQUIRE(x && mean && scale && beta && y, ISTGCN_E_ARG, "data_bn_apply: null pointer");
     const long long rows = (long long)N * M * T * V;
     if (rows == 0) return 0;
-    data_bn_apply_kernel<<<ew_grid(rows, 256), 256, 0, (cudaStream_t)s>>>(x, scale, shift, y, N, C,
-                                                                          T, V, M);
+    data_bn_apply_kernel<<<ew_grid(rows, 256), 256, 0, (cudaStream_t)s>>>(x, mean, scale, beta, y, N,
+                                                                          C, T, V, M);
     return finish_launch("data_bn_apply");
 }
 
@@ -409,54 +404,51 @@ ISTGCN_API int istgcn_data_bn_bwd(const float* x, const float* g, const float* m
 }
 
 ISTGCN_API int istgcn_bn_finalize(const double* sum, const double* sumsq, double count,
-                                  const float* gamma, const float* beta, float* running_mean,
-                                  float* running_var, float momentum, float eps, float* scale,
-                                  float* shift, float* mean, float* rstd, int C,
-                                  istgcn_stream_t s) {
-    ISTGCN_REQUIRE(sum && sumsq && gamma && beta && scale && shift, ISTGCN_E_ARG,
+                                  const float* gamma, float* running_mean, float* running_var,
+                                  float momentum, float eps, float* scale, float* mean, float* rstd,
+                                  int C, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(sum && sumsq && gamma && scale && mean && rstd, ISTGCN_E_ARG,
                    "bn_finalize: null pointer");
     ISTGCN_REQUIRE(count > 0, ISTGCN_E_SHAPE, "bn_finalize: empty batch");
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(
-        sum, sumsq, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, mean,
-        rstd, C);
+        sum, sumsq, count, gamma, running_mean, running_var, momentum, eps, scale, mean, rstd, C);
     return finish_launch("bn_finalize");
 }
 
-ISTGCN_API int istgcn_bn_eval_coeffs(const float* gamma, const float* beta,
-                                     const float* running_mean, const float* running_var, float eps,
-                                     float* scale, float* shift, int C, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(gamma && beta && running_mean && running_var && scale && shift, ISTGCN_E_ARG,
-                   "bn_eval_coeffs: null pointer");
-    bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(
-        gamma, beta, running_mean, running_var, eps, scale, shift, C);
+ISTGCN_API int istgcn_bn_eval_coeffs(const float* gamma, const float* running_var, float eps,
+                                     float* scale, int C, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(gamma && running_var && scale, ISTGCN_E_ARG, "bn_eval_coeffs: null pointer");
+    bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(gamma, running_var, eps,
+                                                                        scale, C);
     return finish_launch("bn_eval_coeffs");
 }
 
 ISTGCN_API int istgcn_bn_bwd_coeffs(const double* sg, const double* sgx, double count,
-                                    const float* gamma, const float* mean, const float* rstd,
-                                    float* p, float* q, float* r, float* dgamma, float* dbeta, int C,
-                                    istgcn_stream_t s) {
-    ISTGCN_REQUIRE(sg && sgx && gamma && mean && rstd && p && q && r, ISTGCN_E_ARG,
+                                    const float* gamma, const float* rstd, float* p, float* m1,
+                                    float* c, float* dgamma, float* dbeta, int C, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(sg && sgx && gamma && rstd && p && m1 && c, ISTGCN_E_ARG,
                    "bn_bwd_coeffs: null pointer");
-    bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(sg, sgx, count, gamma, mean,
-                                                                       rstd, p, q, r, dgamma, dbeta,
-                                                                       C);
+    bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)s>>>(sg, sgx, count, gamma, rstd, p,
+                                                                       m1, c, dgamma, dbeta, C);
     return finish_launch("bn_bwd_coeffs");
 }
 
-ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* scale2, const float* shift2,
-                                     const float* res, const float* scale_r, const float* shift_r,
-                                     float* out, long long rows, int C, float drop_p,
-                                     uint64_t drop_seed, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(u && scale2 && shift2 && out, ISTGCN_E_ARG, "block_tail_fwd: null pointer");
+ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const float* scale2,
+                                     const float* beta2, const float* res, const float* mean_r,
+                                     const float* scale_r, const float* beta_r, float* out,
+                                     long long rows, int C, float drop_p, uint64_t drop_seed,
+                                     istgcn_stream_t s) {
+    ISTGCN_REQUIRE(u && mean2 && scale2 && beta2 && out, ISTGCN_E_ARG, "block_tail_fwd: null pointer");
+    ISTGCN_REQUIRE(scale_r == nullptr || (res && mean_r && beta_r), ISTGCN_E_ARG,
+                   "block_tail_fwd: residual BatchNorm needs res, mean_r and beta_r");
     ISTGCN_REQUIRE(C % 4 == 0, ISTGCN_E_SHAPE, "block_tail_fwd: C=%d not a multiple of 4", C);
     ISTGCN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, ISTGCN_E_ARG, "block_tail_fwd: dropout p=%f", drop_p);
     const int mode = res == nullptr ? 0 : (scale_r == nullptr ? 1 : 2);
     const long long n4 = rows * C / 4;
     if (n4 == 0) return 0;
     block_tail_fwd_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)s>>>(
-        u, scale2, shift2, res, scale_r, shift_r, out, n4, C, mode, drop_p, 1.f / (1.f - drop_p),
-        drop_seed);
+        u, mean2, scale2, beta2, res, mean_r, scale_r, beta_r, out, n4, C, mode, drop_p,
+        1.f / (1.f - drop_p), drop_seed);
     return finish_launch("block_tail_fwd");
 }
 

@@ -212,30 +212,36 @@ static int launch_gcn_fwd(const GcnFwdParams& p, cudaStream_t s) {
 }
 
 // --------------------------------------------------------------------------- backward: input
+constexpr int kLdG = 132;   // Gs[128][4*32 + 4]
+
+// BatchNorm backward folded into the load of the upstream gradient:
+// dz[r][c] = p[c] * ((g[r][c] - m1[c]) - cc[c] * (z[r][c] - mu[c]))     (p == NULL: dz = g)
+struct BnBack {
+    const float *p, *m1, *cc, *mu;
+};
+__device__ __forceinline__ float4 make_dz(const float* __restrict__ g, const float* __restrict__ z,
+                                          const BnBack& b, long long off, int c) {
+    float4 gv = ld4(g + off);
+    if (b.p) {
+        const float4 zv = ld4(z + off), pv = ld4(b.p + c), mv = ld4(b.m1 + c), cv = ld4(b.cc + c),
+                     uv = ld4(b.mu + c);
+        gv.x = bn_back(gv.x, zv.x, pv.x, mv.x, cv.x, uv.x);
+        gv.y = bn_back(gv.y, zv.y, pv.y, mv.y, cv.y, uv.y);
+        gv.z = bn_back(gv.z, zv.z, pv.z, mv.z, cv.z, uv.z);
+        gv.w = bn_back(gv.w, zv.w, pv.w, mv.w, cv.w, uv.w);
+    }
+    return gv;
+}
+
 struct GcnBwdXParams {
-    const float *g, *z, *p, *q, *r0, *x, *Wc, *vals, *add_in;
+    const float *g, *z;
+    BnBack bn;
+    const float *x, *Wc, *vals, *add_in;
     const int *src_ptr, *src_kw, *src_id;
     float *gin, *dvals;
     int frames, V, K, Cin, Cout, nnz, tiles;
     FrameMap fm;
 };
-
-constexpr int kLdG = 132;   // Gs[128][4*32 + 4]
-
-// dz[r][c] = p[c]*g[r][c] + q[c]*z[r][c] + r0[c]  (q == NULL: dz = g)
-__device__ __forceinline__ float4 make_dz(const float* __restrict__ g, const float* __restrict__ z,
-                                          const float* __restrict__ p, const float* __restrict__ q,
-                                          const float* __restrict__ r0, long long off, int c) {
-    float4 gv = ld4(g + off);
-    if (q) {
-        const float4 zv = ld4(z + off), pv = ld4(p + c), qv = ld4(q + c), rv = ld4(r0 + c);
-        gv.x = pv.x * gv.x + qv.x * zv.x + rv.x;
-        gv.y = pv.y * gv.y + qv.y * zv.y + rv.y;
-        gv.z = pv.z * gv.z + qv.z * zv.z + rv.z;
-        gv.w = pv.w * gv.w + qv.w * zv.w + rv.w;
-    }
-    return gv;
-}
 
 template <bool PRECISE>
 __global__ void __launch_bounds__(kThreads) gcn_bwd_x_kernel(GcnBwdXParams p) {
@@ -288,7 +294,7 @@ __global__ void __launch_bounds__(kThreads) gcn_bwd_x_kernel(GcnBwdXParams p) {
                     const int r = i >> 3, c4 = (i & 7) * 4;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < valid_rows)
-                        v = make_dz(p.g, p.z, p.p, p.q, p.r0, (row0 + r) * Cout + c0 + c4, c0 + c4);
+                        v = make_dz(p.g, p.z, p.bn, (row0 + r) * Cout + c0 + c4, c0 + c4);
                     st4(DZs + r * kLdA + c4, v);
                 }
                 // Wt[k*32 + i][c] = Wc[(k*Cin + ci0 + i)][c0 + c]
@@ -367,7 +373,9 @@ static size_t gcn_bwd_x_smem() {
 
 // -------------------------------------------------------------------------- backward: weights
 struct GcnBwdWParams {
-    const float *g, *z, *p, *q, *r0, *x, *vals;
+    const float *g, *z;
+    BnBack bn;
+    const float *x, *vals;
     const int *dst_ptr, *dst_src, *dst_id;
     float *dWc, *dbiasterm;
     int frames, V, K, Cin, Cout, nnz, tiles, mblocks, nblocks;
@@ -426,7 +434,7 @@ __global__ void __launch_bounds__(kThreads) gcn_bwd_w_kernel(GcnBwdWParams p) {
             const int r = i / (NB / 4), c4 = (i % (NB / 4)) * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (r < valid_rows)
-                v = make_dz(p.g, p.z, p.p, p.q, p.r0, (row0 + r) * Cout + n0 + c4, n0 + c4);
+                v = make_dz(p.g, p.z, p.bn, (row0 + r) * Cout + n0 + c4, n0 + c4);
             st4(DZs + r * LDZ + c4, v);
         }
         __syncthreads();
@@ -525,18 +533,20 @@ ISTGCN_API int istgcn_gcn_fwd(const float* x, const float* Wc, const float* bias
     return precise ? launch_gcn_fwd<64, true>(p, st) : launch_gcn_fwd<64, false>(p, st);
 }
 
-ISTGCN_API int istgcn_gcn_bwd_x(const float* g, const float* z, const float* p, const float* q,
-                                const float* r0, const float* x, const float* Wc, const float* vals,
+ISTGCN_API int istgcn_gcn_bwd_x(const float* g, const float* z, const float* bn_p,
+                                const float* bn_m1, const float* bn_c, const float* bn_mu,
+                                const float* x, const float* Wc, const float* vals,
                                 const int* src_ptr, const int* src_kw, const int* src_id, int nnz,
                                 const float* add_in, float* gin, float* dvals, int frames, int V,
                                 int K, int Cin, int Cout, int t_in, int t_out, int t_stride,
                                 int math, istgcn_stream_t s) {
     ISTGCN_REQUIRE(g && x && Wc && vals && src_ptr && src_kw && src_id && gin, ISTGCN_E_ARG,
                    "gcn_bwd_x: null pointer");
-    ISTGCN_REQUIRE(q == nullptr || (z && p && r0), ISTGCN_E_ARG, "gcn_bwd_x: q needs z, p and r0");
+    ISTGCN_REQUIRE(bn_p == nullptr || (z && bn_m1 && bn_c && bn_mu), ISTGCN_E_ARG,
+                   "gcn_bwd_x: bn_p needs z, bn_m1, bn_c and bn_mu");
     if (int e = check_gcn_dims("gcn_bwd_x", frames, V, K, Cin, Cout, nnz)) return e;
     if (frames == 0) return 0;
-    GcnBwdXParams pr{g, z, p, q, r0, x, Wc, vals, add_in, src_ptr, src_kw, src_id, gin, dvals,
+    GcnBwdXParams pr{g, z, {bn_p, bn_m1, bn_c, bn_mu}, x, Wc, vals, add_in, src_ptr, src_kw, src_id, gin, dvals,
                      frames, V, K, Cin, Cout, nnz, 0, {t_in, t_out, t_stride}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     pr.tiles = (frames + F - 1) / F;
@@ -553,18 +563,20 @@ ISTGCN_API int istgcn_gcn_bwd_x(const float* g, const float* z, const float* p, 
     return finish_launch("gcn_bwd_x");
 }
 
-ISTGCN_API int istgcn_gcn_bwd_w(const float* g, const float* z, const float* p, const float* q,
-                                const float* r0, const float* x, const float* vals,
+ISTGCN_API int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p,
+                                const float* bn_m1, const float* bn_c, const float* bn_mu,
+                                const float* x, const float* vals,
                                 const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
                                 float* dWc, float* dbiasterm, int frames, int V, int K, int Cin,
                                 int Cout, int t_in, int t_out, int t_stride, int math,
                                 istgcn_stream_t s) {
     ISTGCN_REQUIRE(g && x && vals && dst_ptr && dst_src && dst_id && dWc, ISTGCN_E_ARG,
                    "gcn_bwd_w: null pointer");
-    ISTGCN_REQUIRE(q == nullptr || (z && p && r0), ISTGCN_E_ARG, "gcn_bwd_w: q needs z, p and r0");
+    ISTGCN_REQUIRE(bn_p == nullptr || (z && bn_m1 && bn_c && bn_mu), ISTGCN_E_ARG,
+                   "gcn_bwd_w: bn_p needs z, bn_m1, bn_c and bn_mu");
     if (int e = check_gcn_dims("gcn_bwd_w", frames, V, K, Cin, Cout, nnz)) return e;
     if (frames == 0) return 0;
-    GcnBwdWParams pr{g, z, p, q, r0, x, vals, dst_ptr, dst_src, dst_id, dWc, dbiasterm,
+    GcnBwdWParams pr{g, z, {bn_p, bn_m1, bn_c, bn_mu}, x, vals, dst_ptr, dst_src, dst_id, dWc, dbiasterm,
                      frames, V, K, Cin, Cout, nnz, 0, 0, 0, {t_in, t_out, t_stride}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     pr.tiles = (frames + F - 1) / F;

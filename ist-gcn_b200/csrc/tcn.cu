@@ -27,7 +27,7 @@ __host__ __device__ inline int ld_t(int bp) { return bp == 8 ? 8 : 24; }       /
 
 // ----------------------------------------------------------------------------------- down
 struct TcnDownParams {
-    const float *z, *scale1, *shift1, *Wd, *bd;
+    const float *z, *mean1, *scale1, *beta1, *Wd, *bd;
     float* h1;
     long long rows;
     int C, bp;
@@ -57,11 +57,12 @@ __global__ void __launch_bounds__(kThreads) tcn_down_kernel(TcnDownParams p) {
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r < valid) {
                     const float4 zv = ld4(p.z + (row0 + r) * C + c0 + c4);
-                    const float4 sc = ld4(p.scale1 + c0 + c4), sh = ld4(p.shift1 + c0 + c4);
-                    v.x = fmaxf(zv.x * sc.x + sh.x, 0.f);
-                    v.y = fmaxf(zv.y * sc.y + sh.y, 0.f);
-                    v.z = fmaxf(zv.z * sc.z + sh.z, 0.f);
-                    v.w = fmaxf(zv.w * sc.w + sh.w, 0.f);
+                    const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
+                                 be = ld4(p.beta1 + c0 + c4);
+                    v.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
+                    v.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
+                    v.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
+                    v.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
                 }
                 st4(As + r * 36 + c4, v);
             }
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
 
 // --------------------------------------------------------------------------- backward: up
 struct TcnBwdUpParams {
-    const float *go, *u, *p2, *q2, *r2, *h2, *Wu;
+    const float *go, *u, *p2, *m12, *c2, *mean2, *h2, *Wu;
     float *dh2, *dWu, *dbu, *dbeff;
     long long rows;
     int C, bp;
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
                     if (r < valid) {
                         const long long off = (row0 + r) * C + c0 + c4;
                         const float4 gv = ld4(p.go + off), uv = ld4(p.u + off);
-                        const float4 pv = ld4(p.p2 + c0 + c4), qv = ld4(p.q2 + c0 + c4),
-                                     rv = ld4(p.r2 + c0 + c4);
+                        const float4 pv = ld4(p.p2 + c0 + c4), mv = ld4(p.m12 + c0 + c4),
+                                     cv = ld4(p.c2 + c0 + c4), nv = ld4(p.mean2 + c0 + c4);
                         float gy[4] = {gv.x, gv.y, gv.z, gv.w};
                         if (p.drop_p > 0.f) {
 #pragma unroll
@@ -297,10 +298,10 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
                                 gy[j] = dropout_keep(p.seed, (uint64_t)(off + j), p.drop_p)
                                             ? gy[j] * p.keep_scale : 0.f;
                         }
-                        v.x = pv.x * gy[0] + qv.x * uv.x + rv.x;
-                        v.y = pv.y * gy[1] + qv.y * uv.y + rv.y;
-                        v.z = pv.z * gy[2] + qv.z * uv.z + rv.z;
-                        v.w = pv.w * gy[3] + qv.w * uv.w + rv.w;
+                        v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
+                        v.y = bn_back(gy[1], uv.y, pv.y, mv.y, cv.y, nv.y);
+                        v.z = bn_back(gy[2], uv.z, pv.z, mv.z, cv.z, nv.z);
+                        v.w = bn_back(gy[3], uv.w, pv.w, mv.w, cv.w, nv.w);
                     }
                     st4(DUs + r * 36 + c4, v);
                 }
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
 
 // --------------------------------------------------------------------------- backward: down
 struct TcnBwdDownParams {
-    const float *dh1, *z, *scale1, *shift1, *mean1, *rstd1, *Wd;
+    const float *dh1, *z, *scale1, *beta1, *mean1, *rstd1, *Wd;
     float *g1, *dWd;
     double *sg1, *sg1x;
     long long rows;
@@ -573,11 +574,12 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_down_kernel(TcnBwdDownParams
                     float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), av = zv;
                     if (r < valid) {
                         zv = ld4(p.z + (row0 + r) * C + c0 + c4);
-                        const float4 sc = ld4(p.scale1 + c0 + c4), sh = ld4(p.shift1 + c0 + c4);
-                        av.x = fmaxf(zv.x * sc.x + sh.x, 0.f);
-                        av.y = fmaxf(zv.y * sc.y + sh.y, 0.f);
-                        av.z = fmaxf(zv.z * sc.z + sh.z, 0.f);
-                        av.w = fmaxf(zv.w * sc.w + sh.w, 0.f);
+                        const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
+                                     be = ld4(p.beta1 + c0 + c4);
+                        av.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
+                        av.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
+                        av.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
+                        av.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
                     }
                     st4(Zs + r * 36 + c4, zv);
                     st4(As + r * LDA + c4, av);
@@ -677,12 +679,12 @@ static int check_tcn(const char* who, int NM, int T, int V, int C, int bp, int s
 
 using namespace istgcn;
 
-ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* scale1, const float* shift1,
-                              const float* Wd, const float* bd, const float* Weff, const float* beff,
+ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* mean1, const float* scale1,
+                              const float* beta1, const float* Wd, const float* bd, const float* Weff, const float* beff,
                               const float* Wu, const float* bu, float* h1, float* h2, float* u,
                               double* stat_sum, double* stat_sumsq, int NM, int T, int V, int C,
                               int bp, int stride, int math, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(z && scale1 && shift1 && Wd && bd && Weff && beff && Wu && bu && h1 && h2 && u,
+    ISTGCN_REQUIRE(z && mean1 && scale1 && beta1 && Wd && bd && Weff && beff && Wu && bu && h1 && h2 && u,
                    ISTGCN_E_ARG, "tcn_fwd: null pointer");
     if (int e = check_tcn("tcn_fwd", NM, T, V, C, bp, stride)) return e;
     if (NM == 0) return 0;
@@ -690,7 +692,7 @@ ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* scale1, const float* 
     const bool pc = math == ISTGCN_MATH_3XTF32;
     const int Tout = (T - 1) / stride + 1;
     {
-        TcnDownParams p{z, scale1, shift1, Wd, bd, h1, (long long)NM * T * V, C, bp};
+        TcnDownParams p{z, mean1, scale1, beta1, Wd, bd, h1, (long long)NM * T * V, C, bp};
         const size_t smem = sizeof(float) * (kTileRows * 36 + C * ld_t(bp));
         const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 4);
 #define LAUNCH_DOWN(NT, PC)                                          \
@@ -722,16 +724,17 @@ ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* scale1, const float* 
     return 0;
 }
 
-ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float* q2,
-                              const float* r2, const float* z, const float* scale1,
-                              const float* shift1, const float* mean1, const float* rstd1,
+ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float* m12,
+                              const float* c2, const float* mean2, const float* z,
+                              const float* scale1, const float* beta1, const float* mean1,
+                              const float* rstd1,
                               const float* h1, const float* h2, const float* Wd, const float* Weff,
                               const float* Wu, float* dh2_ws, float* dh1_ws, float* g1, double* sg1,
                               double* sg1x, float* dWd, float* dbd, float* dWeff, float* dbeff,
                               float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
                               int stride, float drop_p, uint64_t drop_seed, int math,
                               istgcn_stream_t s) {
-    ISTGCN_REQUIRE(go && u && p2 && q2 && r2 && z && scale1 && shift1 && mean1 && rstd1 && h1 && h2 &&
+    ISTGCN_REQUIRE(go && u && p2 && m12 && c2 && mean2 && z && scale1 && beta1 && mean1 && rstd1 && h1 && h2 &&
                        Wd && Weff && Wu && dh2_ws && dh1_ws && g1 && sg1 && sg1x && dWd && dbd &&
                        dWeff && dbeff && dWu && dbu,
                    ISTGCN_E_ARG, "tcn_bwd: null pointer");
@@ -742,7 +745,7 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
     const bool pc = math == ISTGCN_MATH_3XTF32;
     const int Tout = (T - 1) / stride + 1;
     {
-        TcnBwdUpParams p{go, u, p2, q2, r2, h2, Wu, dh2_ws, dWu, dbu, dbeff,
+        TcnBwdUpParams p{go, u, p2, m12, c2, mean2, h2, Wu, dh2_ws, dWu, dbu, dbeff,
                          (long long)NM * Tout * V, C, bp, drop_p, 1.f / (1.f - drop_p), drop_seed};
         const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * ld_t(bp) + 8 + bp * (C + 4) + C + bp);
         const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 3);
@@ -772,7 +775,7 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
         if (int e = finish_launch("tcn_bwd_t")) return e;
     }
     {
-        TcnBwdDownParams p{dh1_ws, z, scale1, shift1, mean1, rstd1, Wd, g1, dWd, sg1, sg1x,
+        TcnBwdDownParams p{dh1_ws, z, scale1, beta1, mean1, rstd1, Wd, g1, dWd, sg1, sg1x,
                            (long long)NM * T * V, C, bp};
         const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * 40 + kTileRows * ld_g(bp) +
                                              C * ld_g(bp) + 2 * C);

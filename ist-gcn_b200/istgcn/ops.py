@@ -33,16 +33,16 @@ class BNState(object):
         self.eps = float(bn.eps)
 
 
-def _bn_forward_coeffs(training, sum_, sumsq, count, weight, bias, st, C, device):
-    """-> scale, shift, mean, rstd (mean/rstd None in eval mode)."""
+def _bn_forward_coeffs(training, sum_, sumsq, count, weight, st, C, device):
+    """-> mean, scale, rstd for y = (x - mean)*scale + beta (rstd is None in eval mode)."""
     if training:
-        scale, shift, mean, rstd = _coeffs(4, C, device)
-        call('bn_finalize', sum_, sumsq, f64(count), weight, bias, st.running_mean, st.running_var,
-             st.momentum, st.eps, scale, shift, mean, rstd, C)
-        return scale, shift, mean, rstd
-    scale, shift = _coeffs(2, C, device)
-    call('bn_eval_coeffs', weight, bias, st.running_mean, st.running_var, st.eps, scale, shift, C)
-    return scale, shift, None, None
+        scale, mean, rstd = _coeffs(3, C, device)
+        call('bn_finalize', sum_, sumsq, f64(count), weight, st.running_mean, st.running_var,
+             st.momentum, st.eps, scale, mean, rstd, C)
+        return mean, scale, rstd
+    scale, = _coeffs(1, C, device)
+    call('bn_eval_coeffs', weight, st.running_var, st.eps, scale, C)
+    return st.running_mean, scale, None
 
 
 class DataBN(Function):
@@ -56,13 +56,12 @@ class DataBN(Function):
         if training:
             stats = torch.zeros(2, V * C, device=dev, dtype=torch.float64)
             call('data_bn_stats', x, stats[0], stats[1], N, C, T, V, M)
-            scale, shift, mean, rstd = _bn_forward_coeffs(True, stats[0], stats[1], N * M * T, weight,
-                                                          bias, st, V * C, dev)
+            mean, scale, rstd = _bn_forward_coeffs(True, stats[0], stats[1], N * M * T, weight, st,
+                                                   V * C, dev)
         else:
-            scale, shift, mean, rstd = _bn_forward_coeffs(False, None, None, 0, weight, bias, st,
-                                                          V * C, dev)
+            mean, scale, rstd = _bn_forward_coeffs(False, None, None, 0, weight, st, V * C, dev)
         y = torch.empty(N * M, T, V, C, device=dev, dtype=torch.float32)
-        call('data_bn_apply', x, scale, shift, y, N, C, T, V, M)
+        call('data_bn_apply', x, mean, scale, bias.contiguous(), y, N, C, T, V, M)
         ctx.training = training
         ctx.dims = (N, C, T, V, M)
         if training:
@@ -120,16 +119,17 @@ class STBlock(Function):
         z = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
         call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
              stats[0], stats[1], NM * T, V, K, Cin, Cout, 0, 0, 1, math)
-        scale1, shift1, mean1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w,
-                                                          bn1_b, cfg.bn1, Cout, dev)
+        mean1, scale1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w, cfg.bn1,
+                                                  Cout, dev)
+        bn1_b, bn2_b = bn1_b.contiguous(), bn2_b.contiguous()
         h1 = torch.empty(NM, T, V, bp, device=dev, dtype=torch.float32)
         h2 = torch.empty(NM, Tout, V, bp, device=dev, dtype=torch.float32)
         u = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-        call('tcn_fwd', z, scale1, shift1, Wd, bd, Weff, beff, Wu, bu, h1, h2, u, stats[2], stats[3],
+        call('tcn_fwd', z, mean1, scale1, bn1_b, Wd, bd, Weff, beff, Wu, bu, h1, h2, u, stats[2], stats[3],
              NM, T, V, Cout, bp, s, math)
-        scale2, shift2, mean2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w,
-                                                          bn2_b, cfg.bn2, Cout, dev)
-        rres = scale_r = shift_r = mean_r = rstd_r = None
+        mean2, scale2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w, cfg.bn2,
+                                                  Cout, dev)
+        rres = scale_r = mean_r = rstd_r = None
         res = None
         if cfg.res_mode == 1:
             res = x
@@ -141,17 +141,19 @@ class STBlock(Function):
             rres = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
             call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
                  rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
-            scale_r, shift_r, mean_r, rstd_r = _bn_forward_coeffs(
-                training, stats[4], stats[5], R_out, bnr_w, bnr_b, cfg.bnr, Cout, dev)
+            mean_r, scale_r, rstd_r = _bn_forward_coeffs(training, stats[4], stats[5], R_out, bnr_w,
+                                                         cfg.bnr, Cout, dev)
+            bnr_b = bnr_b.contiguous()
             res = rres
         out = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-        call('block_tail_fwd', u, scale2, shift2, res, scale_r, shift_r, out, i64(R_out), Cout,
-             float(drop_p), u64(cfg.seed))
+        call('block_tail_fwd', u, mean2, scale2, bn2_b, res, mean_r, scale_r,
+             bnr_b if cfg.res_mode == 2 else None, out, i64(R_out), Cout, float(drop_p),
+             u64(cfg.seed))
 
         ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
         ctx.dims = (NM, T, Tout, V, Cin, Cout)
         if training:
-            ctx.save_for_backward(x, vals, Wc, z, h1, h2, u, out, rres, scale1, shift1, mean1, rstd1,
+            ctx.save_for_backward(x, vals, Wc, z, h1, h2, u, out, rres, scale1, bn1_b, mean1, rstd1,
                                   mean2, rstd2, mean_r, rstd_r, Wd, Weff, Wu, Wr, bn1_w, bn2_w, bnr_w)
         return out
 
@@ -159,7 +161,7 @@ class STBlock(Function):
     def backward(ctx, gout):
         if not ctx.training:
             raise RuntimeError('istgcn: backward through eval-mode BatchNorm is not supported')
-        (x, vals, Wc, z, h1, h2, u, out, rres, scale1, shift1, mean1, rstd1, mean2, rstd2, mean_r,
+        (x, vals, Wc, z, h1, h2, u, out, rres, scale1, beta1, mean1, rstd1, mean2, rstd2, mean_r,
          rstd_r, Wd, Weff, Wu, Wr, bn1_w, bn2_w, bnr_w) = ctx.saved_tensors
         cfg, math, drop_p, seed = ctx.cfg, ctx.math, ctx.drop_p, ctx.seed
         NM, T, Tout, V, Cin, Cout = ctx.dims
@@ -173,38 +175,36 @@ class STBlock(Function):
         call('block_tail_bwd', gout, out, u, mean2, rstd2, rres, mean_r, rstd_r, go, sums[0], sums[1],
              sums[2] if rres is not None else None, sums[3] if rres is not None else None,
              i64(R_out), Cout, float(drop_p), u64(seed))
-        p2, q2, r2, dg2, db2 = _coeffs(5, Cout, dev)
-        call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, mean2, rstd2, p2, q2, r2, dg2, db2,
-             Cout)
+        p2, m12, c2, dg2, db2 = _coeffs(5, Cout, dev)
+        call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2, Cout)
         dWd, dbd = torch.zeros_like(Wd), torch.zeros(bp, device=dev)
         dWeff, dbeff = torch.zeros_like(Weff), torch.zeros(bp, device=dev)
         dWu, dbu = torch.zeros_like(Wu), torch.zeros(Cout, device=dev)
         g1 = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
         dh2 = torch.empty(R_out, bp, device=dev, dtype=torch.float32)
         dh1 = torch.empty(R_in, bp, device=dev, dtype=torch.float32)
-        call('tcn_bwd', go, u, p2, q2, r2, z, scale1, shift1, mean1, rstd1, h1, h2, Wd, Weff, Wu, dh2,
+        call('tcn_bwd', go, u, p2, m12, c2, mean2, z, scale1, beta1, mean1, rstd1, h1, h2, Wd, Weff, Wu, dh2,
              dh1, g1, sums[4], sums[5], dWd, dbd, dWeff, dbeff, dWu, dbu, NM, T, V, Cout, bp, s,
              float(drop_p), u64(seed), math)
-        p1, q1, r1, dg1, db1 = _coeffs(5, Cout, dev)
-        call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, mean1, rstd1, p1, q1, r1, dg1, db1,
-             Cout)
+        p1, m11, c1, dg1, db1 = _coeffs(5, Cout, dev)
+        call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
         gin = torch.empty_like(x)
         dvals = torch.zeros_like(vals)
-        call('gcn_bwd_x', g1, z, p1, q1, r1, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id, pat.nnz,
+        call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id, pat.nnz,
              go if cfg.res_mode == 1 else None, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
-        call('gcn_bwd_w', g1, z, p1, q1, r1, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz,
+        call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz,
              dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
         dWr = dbtr = dgr = dbr = None
         if cfg.res_mode == 2:
             idn = cfg.ident
-            pr, qr, rr, dgr, dbr = _coeffs(5, Cout, dev)
-            call('bn_bwd_coeffs', sums[2], sums[3], f64(R_out), bnr_w, mean_r, rstd_r, pr, qr, rr, dgr,
-                 dbr, Cout)
-            call('gcn_bwd_x', go, rres, pr, qr, rr, x, Wr, cfg.ones, idn.src_ptr, idn.src_kw,
+            pr, m1r, cr, dgr, dbr = _coeffs(5, Cout, dev)
+            call('bn_bwd_coeffs', sums[2], sums[3], f64(R_out), bnr_w, rstd_r, pr, m1r, cr, dgr, dbr,
+                 Cout)
+            call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr, idn.src_kw,
                  idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
             dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, Cout, device=dev)
-            call('gcn_bwd_w', go, rres, pr, qr, rr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id,
+            call('gcn_bwd_w', go, rres, pr, m1r, cr, mean_r, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id,
                  V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
         return (gin, dvals, dWc, dbt, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr, dbtr,
                 dgr, dbr, None)
@@ -235,10 +235,10 @@ class GraphConv(Function):
         Cout = Wc.shape[1]
         gz = gz.contiguous()
         gin, dvals = torch.empty_like(x), torch.zeros_like(vals)
-        call('gcn_bwd_x', gz, None, None, None, None, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id,
+        call('gcn_bwd_x', gz, None, None, None, None, None, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id,
              pat.nnz, None, gin, dvals, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=x.device)
-        call('gcn_bwd_w', gz, None, None, None, None, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
+        call('gcn_bwd_w', gz, None, None, None, None, None, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
              pat.nnz, dWc, dbt, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
         return gin, dvals, dWc, dbt, None
 
