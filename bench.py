@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- IST-GCN training throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl istgcn|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full training iteration (forward, cross-entropy, backward, SGD-nesterov step)
+of the composite IST-GCN (net.ist_gcn: 'ntu-rgb+d_sym' + 'spatial_3_sym', Inception GCN,
+1x1-bottleneck Inception TCN, 10 blocks, dropout 0.5) on one batch of 64 synthetic NTU-shape
+clips (3, 300, 25, 2) per GPU -- BASELINE.json configs[1] / configs[3].  Weak scaling: every
+rank gets its own 64 clips, BatchNorm statistics stay per rank, gradients are averaged with
+bucketed NCCL all-reduces overlapped with the backward pass.
+
+Rank 0 prints ONE JSON line:
+  value        clips/s over all ranks with the batch resident in HBM (CUDA events, max over ranks)
+  e2e          the same step driven from pinned HOST buffers: H2D copy of the batch and a D2H
+               read of the loss inside the timed region, every step
+  roofline     the dominant kernel (largest share of the step): algorithmic bytes of its launches
+               / their CUDA-event time, against the measured HBM copy bandwidth
+  cpu_baseline the oracle port of the reference (plain PyTorch fp32, all host threads) timed on
+               a bounded sample of the same workload (rank 0, N=1 only)
+``--impl reference`` times only that CPU port (the reference is pure PyTorch; /root/reference
+itself does not exist on the GPU box) and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, 'ist-gcn_b200'), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+WORKLOADS = {
+    'ntu': dict(graph_args=dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), num_class=60,
+                shape=(3, 300, 25, 2), name='IST-GCN fwd+bwd+SGD, NTU-RGB+D shape (3,300,25,2)'),
+    'kinetics': dict(graph_args=dict(layout='openpose_sym', strategy='spatial_3_sym'), num_class=400,
+                     shape=(3, 300, 18, 2), name='IST-GCN fwd+bwd+SGD, Kinetics-skeleton shape (3,300,18,2)'),
+}
+BLOCKS = ((3, 64, 1, 0), (64, 64, 1, 1), (64, 64, 1, 1), (64, 64, 1, 1), (64, 128, 2, 2),
+          (128, 128, 1, 1), (128, 128, 1, 1), (128, 256, 2, 2), (256, 256, 1, 1), (256, 256, 1, 1))
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get('hbm_gbs', 6650.0)), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(index), '--query-gpu=' + self.QUERY,
+                 '--format=csv,noheader,nounits', '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in self.lines:
+            parts = [s.strip() for s in line.split(',')]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def algorithmic_bytes(kernel, batch, shape):
+    """Algorithmic (compulsory) HBM bytes of every launch of ``kernel`` in one training step:
+    per-row figures of DESIGN.md section 4 x rows of each block (fp32 activations)."""
+    C, T, V, M = shape
+    NM = batch * M
+    per_launch = []
+    t = T
+    for cin, cout, s, res in BLOCKS:
+        tout = (t - 1) // s + 1
+        r_in, r_out = NM * t * V, NM * tout * V
+        if kernel == 'gcn_fwd':
+            per_launch.append(4 * r_in * (cin + cout))
+            if res == 2:
+                per_launch.append(4 * r_out * (cin + cout))
+        elif kernel == 'gcn_bwd_x':      # reads g1, z, x (for dA) [+ go], writes gin
+            per_launch.append(4 * r_in * (2 * cout + 2 * cin + (cin if res == 1 else 0)))
+            if res == 2:                  # reads go, rres, x ; read-modify-write of strided gin rows
+                per_launch.append(4 * r_out * (2 * cout + 3 * cin))
+        elif kernel == 'gcn_bwd_w':      # reads g1, z, x
+            per_launch.append(4 * r_in * (2 * cout + cin))
+            if res == 2:
+                per_launch.append(4 * r_out * (2 * cout + cin))
+        elif kernel == 'tcn_fwd':        # reads z, writes u (+ h1, h2 write, h1 read)
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * (r_in * (cout + 2 * bp) + r_out * (cout + bp)))
+        elif kernel == 'tcn_bwd':        # reads go, u, z, h1, h2 (+dh2, dh1 round trips), writes g1
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * (r_out * (2 * cout + 3 * bp) + r_in * (2 * cout + 3 * bp)))
+        elif kernel == 'block_tail_fwd':
+            per_launch.append(4 * r_out * cout * (2 + (1 if res else 0)))
+        elif kernel == 'block_tail_bwd':
+            per_launch.append(4 * r_out * cout * (4 + (1 if res == 2 else 0)))
+        t = tout
+    return per_launch
+
+
+def build_model(workload, device, dropout=0.5):
+    import net.ist_gcn
+    from istgcn import trainer
+    w = WORKLOADS[workload]
+    model = net.ist_gcn.Model(w['shape'][0], w['num_class'], w['graph_args'], True, dropout=dropout)
+    model.apply(trainer.weights_init)
+    return model.to(device)
+
+
+def run_istgcn(args):
+    import istgcn
+    from istgcn import _lib, dp, trainer
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the product path has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+    istgcn.set_math(args.math)
+    w = WORKLOADS[args.workload]
+    torch.manual_seed(0)
+    model = build_model(args.workload, dev)
+    dp.broadcast_state(model)
+    tr = trainer.Trainer(model, base_lr=0.01)
+    torch.manual_seed(1000 + rank)
+    B = args.batch
+    x = torch.randn(B, *w['shape'], device=dev)
+    y = torch.randint(0, w['num_class'], (B,), device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        tr.step(x, y)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = _lib.launch_count
+    _lib.timing = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.step(x, y)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    timing, _lib.timing = _lib.timing, None
+    launches = _lib.launch_count - launches0
+    clocks = sampler.stop() if sampler else None
+    t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = t_ms.item()
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    final_loss = loss.item()
+
+    # per-kernel device time inside the timed region (events on the launching stream)
+    per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in timing.items()}
+    top = max(per_kernel, key=per_kernel.get)
+    peak, peak_src = measured_peaks()
+    alg = algorithmic_bytes(top, B, w['shape'])
+    n_launch = len(timing[top])
+    alg_total = sum(alg) * args.steps if alg else None
+    roof = {'kernel': top, 'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
+            'launches': n_launch, 'share_of_step': per_kernel[top] / ms, 'traffic': None}
+    if alg_total:
+        ach = alg_total / (per_kernel[top] / 1e3) / 1e9
+        roof.update(achieved=ach, frac=ach / peak,
+                    algorithmic_bytes_per_launch=alg_total / n_launch,
+                    avg_launch_ms=per_kernel[top] / n_launch)
+    shares = {k: round(v / ms, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+
+    # end to end through the public API from pinned host buffers
+    xh = torch.randn(B, *w['shape']).pin_memory()
+    yh = torch.randint(0, w['num_class'], (B,)).pin_memory()
+    xd, yd = torch.empty_like(x), torch.empty_like(y)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        yd.copy_(yh, non_blocking=True)
+        return tr.step(xd, yd).item()           # D2H read of the loss
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / dt.item()
+
+    # forward-only (eval) throughput, reported next to the training number
+    with torch.no_grad():
+        for _ in range(2):
+            tr.evaluate(x)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            tr.evaluate(x)
+        e1.record()
+        barrier()
+        fwd = world * B * args.steps / (e0.elapsed_time(e1) / 1e3)
+
+    line = {
+        'metric': 'ist_gcn_train_clips_per_s', 'value': value, 'unit': 'clips/s',
+        'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'tf32' if args.math == 'tf32' else 'fp32(3xtf32)',
+        'data': 'synthetic',
+        'config': {'workload': w['name'], 'clips_per_gpu': B, 'global_batch': B * world,
+                   'dropout': 0.5, 'optimizer': 'SGD(momentum .9, nesterov, wd 1e-4)',
+                   'parallelism': 'dp%d' % world, 'activations': 'fp32 channels-last',
+                   'l2_policy': 'working set (>10 GB of activations per step) is far larger than the 126 MB L2'},
+        'clocks': clocks, 'gpu_launches': launches,
+        'e2e': {'value': e2e_value, 'unit': 'clips/s',
+                'h2d_bytes_per_step': xh.numel() * 4 + yh.numel() * 8, 'd2h_bytes_per_step': 4},
+        'roofline': roof, 'kernel_shares': shares, 'fwd_clips_per_s': fwd, 'loss': final_loss,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_reference(args, steps=1, warmup=1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_reference(args, steps, warmup):
+    """The reference's own algorithm (oracle port: plain PyTorch fp32 conv/einsum/batch_norm)
+    on the host cores: full training steps on a bounded sample of the workload."""
+    from net.utils.graph import Graph
+    from oracle import model_ref
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = Graph(**w['graph_args'])
+    torch.manual_seed(0)
+    state = model_ref.make_state('ist_gcn', w['shape'][0], w['num_class'], g.A, g.A2, g.A3, seed=0)
+    names = [k for k, v in state.items() if v.is_floating_point() and 'running' not in k
+             and k not in ('A', 'A2', 'A3') and '.gcn.branch.bn.' not in k]
+    for k in names:
+        state[k].requires_grad_(True)
+    bs = args.cpu_batch
+    x = torch.randn(bs, *w['shape'])
+    y = torch.randint(0, w['num_class'], (bs,))
+    bufs = [None] * len(names)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = model_ref.forward(state, x, 'ist_gcn', training=True, dropout=0.5)
+        loss = F.cross_entropy(out, y)
+        grads = torch.autograd.grad(loss, [state[k] for k in names], allow_unused=True)
+        with torch.no_grad():
+            ps = [state[k] for k, gr in zip(names, grads) if gr is not None]
+            gs = [gr for gr in grads if gr is not None]
+            model_ref.sgd_nesterov_step(ps, gs, bufs[:len(ps)], 0.01)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    best = min(times)
+    return {'value': bs / best, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d clip(s) of the same shape per step, %d timed step(s), best' % (bs, steps),
+            'torch_threads': torch.get_num_threads(), 's_per_step': best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    base = cpu_reference(args, steps, warmup)
+    line = {'impl': 'reference', 'metric': 'ist_gcn_train_clips_per_s', 'value': base['value'],
+            'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': base['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': w['name'], 'clips_per_step': args.cpu_batch,
+                       'note': 'reference = pure PyTorch; its CPU path timed on the host cores'},
+            'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': 'clips/s', 'h2d_bytes_per_step': 0,
+                    'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='istgcn', choices=['istgcn', 'reference'])
+    ap.add_argument('--workload', default='ntu', choices=sorted(WORKLOADS))
+    ap.add_argument('--batch', type=int, default=64, help='clips per GPU')
+    ap.add_argument('--math', default='tf32', choices=['tf32', '3xtf32'])
+    ap.add_argument('--cpu-batch', type=int, default=4, help='clips per CPU-baseline step')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_istgcn(args)
+
+
+if __name__ == '__main__':
+    main()

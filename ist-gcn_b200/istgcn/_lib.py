@@ -64,10 +64,17 @@ def _conv(a):
     return a                                     # already a ctypes value
 
 
+# kernels launched per C-ABI call (tcn_fwd = down + up, tcn_bwd = up + temporal + down,
+# pool_fwd = kernel behind a memset) -- used for the ``gpu_launches`` count of bench.py
+KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3}
+launch_count = 0          # kernels launched through this binding since import
+timing = None             # set to a dict by bench.py: name -> list of (start_event, end_event)
+
+
 def call(name, *args):
     """Invoke ``istgcn_<name>`` on torch's current CUDA stream; raise on a non-zero status."""
     import torch
-    global _checked_device
+    global _checked_device, launch_count
     lib = load()
     if not _checked_device:
         if not torch.cuda.is_available():
@@ -78,7 +85,15 @@ def call(name, *args):
             raise RuntimeError('istgcn_b200: ' + lib.istgcn_last_error().decode())
         _checked_device = True
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    rc = getattr(lib, 'istgcn_' + name)(*[_conv(a) for a in args], stream)
+    launch_count += KERNELS_PER_CALL.get(name, 1)
+    if timing is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, 'istgcn_' + name)(*[_conv(a) for a in args], stream)
+        e1.record()
+        timing.setdefault(name, []).append((e0, e1))
+    else:
+        rc = getattr(lib, 'istgcn_' + name)(*[_conv(a) for a in args], stream)
     if rc != 0:
         raise RuntimeError('istgcn_%s failed (%d): %s' % (name, rc,
                                                           lib.istgcn_last_error().decode()))
