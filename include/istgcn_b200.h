@@ -115,6 +115,21 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const fl
                      int frames, int V, int K, int Cin, int Cout,
                      int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
 
+/* tcgen05 / TMA / TMEM engine of the same graph convolution (forward form, or input-gradient
+ * form when the lists are grouped by (k, source joint) and the weight is Wc):
+ *   out[(f,w)][n] = sum_{k,ci} (sum_v A[k][v][w] in'[(f,v)][ci]) * w_rows[k*Cout + n][ci]
+ *                   + bias_vc[w][n] + add_rows[(f,w)][n]
+ * with in' = in, or in' = bn_p*((in - bn_m1) - bn_c*(in2 - bn_mu)) when bn_p != NULL.
+ * w_rows is [K*Cout][CinPad] (CinPad = Cin rounded up to 32, padding columns zero), 16-byte
+ * aligned; lptr[K*V+1] / lsrc / lid group the non-zeros by (k, destination joint).
+ * TF32 inputs, fp32 accumulation in tensor memory.                                          */
+int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const float* bn_m1,
+                  const float* bn_c, const float* bn_mu, const float* w_rows, const float* vals,
+                  const int* lptr, const int* lsrc, const int* lid, int nnz,
+                  const float* bias_vc, const float* add_rows, float* out, double* stat_sum,
+                  double* stat_sumsq, int frames, int V, int K, int Cin, int CinPad, int Cout,
+                  istgcn_stream_t s);
+
 /* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
  *   a  = relu((z - mean1)*scale1 + beta1)              (tcn_start: BN + ReLU)
  *   h1 = a Wd + bd                                     (conv_1x1_start, C -> b)

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kThreads) gcn_bwd_x_kernel(GcnBwdXParams p) {
             load_x_slice(xs, p.x, row0, valid_rows, Cin, ci0, tid, p.fm, V);
             __syncthreads();
             // (a) gin[(f,v)][ci] = sum_j val_j * G[(f,w_j)][k_j*32 + ci]  (+ add_in)
-            if (ci0 + lane < Cin) {
+            if (p.gin && ci0 + lane < Cin) {
                 for (int r = warp; r < valid_rows; r += kWarps) {
                     const int f = r / V, v = r - f * V;
                     const float* grow = Gs + f * V * kLdG + lane;
@@ -540,7 +540,7 @@ ISTGCN_API int istgcn_gcn_bwd_x(const float* g, const float* z, const float* bn_
                                 const float* add_in, float* gin, float* dvals, int frames, int V,
                                 int K, int Cin, int Cout, int t_in, int t_out, int t_stride,
                                 int math, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(g && x && Wc && vals && src_ptr && src_kw && src_id && gin, ISTGCN_E_ARG,
+    ISTGCN_REQUIRE(g && x && Wc && vals && src_ptr && src_kw && src_id && (gin || dvals), ISTGCN_E_ARG,
                    "gcn_bwd_x: null pointer");
     ISTGCN_REQUIRE(bn_p == nullptr || (z && bn_m1 && bn_c && bn_mu), ISTGCN_E_ARG,
                    "gcn_bwd_x: bn_p needs z, bn_m1, bn_c and bn_mu");

@@ -30,3 +30,19 @@ def get_math():
 
 def math_flag():
     return _math
+
+
+# tensor-core (tcgen05/TMA/TMEM) engine of the graph convolution; ISTGCN_TC=0 selects the
+# mma.sync engine for every layer (both are this library's own sm_100a kernels).  The '3xtf32'
+# mode always uses the mma.sync engine (error-compensated split).
+_use_tc = os.environ.get('ISTGCN_TC', '1') != '0'
+
+
+def set_tensor_core_engine(flag):
+    global _use_tc
+    old, _use_tc = _use_tc, bool(flag)
+    return old
+
+
+def use_tc():
+    return _use_tc and _math == MATH_TF32

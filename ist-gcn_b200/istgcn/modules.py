@@ -40,7 +40,10 @@ def to_channels_first(x):
 
 def graph_conv_operands(weight, bias, adjs, pattern):
     """Reference-layout conv weight (K*Cout, Cin, 1, 1) + bias and the adjacency stacks
-    [A*imp (, A2*imp2, A3*imp3)] -> (vals[nnz], Wc[K*Cin, Cout], biasterm[V, Cout]).
+    [A*imp (, A2*imp2, A3*imp3)] -> (vals[nnz], Wc[K*Cin, Cout], biasterm[V, Cout], W2) where
+    W2[K*Cout, CinPad] is the weight in its own row order with the input channels zero-padded to
+    a multiple of 32 (the tcgen05 engine's TMA operand; no gradient flows through it, Wc carries
+    the weight gradient).
 
     Three einsums with A, A2, A3 are one with their sum (inceptionv2_gcn.py:69-88); the conv
     bias passes through the aggregation as bias[k, c] * colsum(A_eff[k])[w]."""
@@ -56,7 +59,10 @@ def graph_conv_operands(weight, bias, adjs, pattern):
         biasterm = a_eff.new_zeros(a_eff.shape[1], cout)
     else:
         biasterm = torch.einsum('kc,kw->wc', bias.view(K, cout), a_eff.sum(1))
-    return vals, wc, biasterm
+    w2 = weight.detach().view(kc, cin)
+    if cin % 32:
+        w2 = F.pad(w2, (0, 32 - cin % 32))
+    return vals, wc, biasterm, w2
 
 
 def bottleneck_tcn_operands(conv_start, tcn_1, tcn_2, tcn_3, conv_end, m_imp):
@@ -124,7 +130,7 @@ class FusedBlockMixin(object):
         cfg.training = self.training
         cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
         conv = self._gcn_conv()
-        vals, wc, biasterm = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
+        vals, wc, biasterm, w2 = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
         wd, bd, weff, beff, wu, bu = bottleneck_tcn_operands(
             self.conv_1x1_start, self.tcn_1, self.tcn_2, self.tcn_3, self.conv_1x1_end, m_imp)
         bn1, bn2 = self.tcn_start[0], self.tcn_end[0]
@@ -135,7 +141,7 @@ class FusedBlockMixin(object):
             wr = rconv.weight.view(cout, cin).t()
             btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout)
             bnr_w, bnr_b = rbn.weight, rbn.bias
-        out = ops.STBlock.apply(x, vals, wc, biasterm, bn1.weight, bn1.bias, wd, bd, weff, beff, wu,
+        out = ops.STBlock.apply(x, vals, wc, biasterm, w2, bn1.weight, bn1.bias, wd, bd, weff, beff, wu,
                                 bu, bn2.weight, bn2.bias, wr, btr, bnr_w, bnr_b, cfg)
         if self.training:
             for bn in (bn1, bn2) + ((self.residual[1],) if self._res_mode == 2 else ()):

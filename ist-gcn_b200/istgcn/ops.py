@@ -14,7 +14,7 @@ maps the kernel's gradients back onto the reference's parameter tensors.
 import torch
 from torch.autograd import Function
 
-from . import _lib, math_flag
+from . import _lib, math_flag, use_tc
 from ._lib import call, f64, i64, u64
 
 
@@ -43,6 +43,16 @@ def _bn_forward_coeffs(training, sum_, sumsq, count, weight, st, C, device):
     scale, = _coeffs(1, C, device)
     call('bn_eval_coeffs', weight, st.running_var, st.eps, scale, C)
     return st.running_mean, scale, None
+
+
+def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, Cin, Cout, math):
+    """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise."""
+    if use_tc():
+        call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src,
+             pat.dst_id, pat.nnz, biasterm, None, z, s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout)
+    else:
+        call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
+             s_sum, s_sq, frames, V, K, Cin, Cout, 0, 0, 1, math)
 
 
 class DataBN(Function):
@@ -98,7 +108,7 @@ class STBlock(Function):
     inceptionv2_gcn.py:64-89 as the graph conv)."""
 
     @staticmethod
-    def forward(ctx, x, vals, Wc, biasterm, bn1_w, bn1_b, Wd, bd, Weff, beff, Wu, bu, bn2_w,
+    def forward(ctx, x, vals, Wc, biasterm, W2, bn1_w, bn1_b, Wd, bd, Weff, beff, Wu, bu, bn2_w,
                 bn2_b, Wr, biasterm_r, bnr_w, bnr_b, cfg):
         x = x.contiguous()
         NM, T, V, Cin = x.shape
@@ -117,8 +127,8 @@ class STBlock(Function):
         stats = torch.zeros(6, Cout, device=dev, dtype=torch.float64) if training else [None] * 6
 
         z = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
-        call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
-             stats[0], stats[1], NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        _gcn_forward(x, Wc, W2.contiguous(), biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K,
+                     Cin, Cout, math)
         mean1, scale1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w, cfg.bn1,
                                                   Cout, dev)
         bn1_b, bn2_b = bn1_b.contiguous(), bn2_b.contiguous()
@@ -190,8 +200,17 @@ class STBlock(Function):
         call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
         gin = torch.empty_like(x)
         dvals = torch.zeros_like(vals)
-        call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id, pat.nnz,
-             go if cfg.res_mode == 1 else None, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        add_in = go if cfg.res_mode == 1 else None
+        if use_tc():
+            # input gradient on the tcgen05 engine: the forward kernel run on dz with the
+            # transposed adjacency lists and Wc as the weight; adjacency gradient separately
+            call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
+                 pat.nnz, None, add_in, gin, None, None, NM * T, V, K, Cout, Cout, Cin)
+            call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
+                 pat.src_id, pat.nnz, None, None, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        else:
+            call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
+                 pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
         call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz,
              dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
@@ -206,8 +225,8 @@ class STBlock(Function):
             dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, Cout, device=dev)
             call('gcn_bwd_w', go, rres, pr, m1r, cr, mean_r, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id,
                  V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
-        return (gin, dvals, dWc, dbt, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr, dbtr,
-                dgr, dbr, None)
+        return (gin, dvals, dWc, dbt, None, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr,
+                dbtr, dgr, dbr, None)
 
 
 class GraphConv(Function):
@@ -215,14 +234,14 @@ class GraphConv(Function):
     inceptionv2_gcn.py:64-89.  x (NM, T, V, Cin) channels-last -> (NM, T, V, Cout)."""
 
     @staticmethod
-    def forward(ctx, x, vals, Wc, biasterm, pattern):
+    def forward(ctx, x, vals, Wc, biasterm, W2, pattern):
         x, vals, Wc, biasterm = x.contiguous(), vals.contiguous(), Wc.contiguous(), biasterm.contiguous()
         NM, T, V, Cin = x.shape
         Cout = Wc.shape[1]
         z = torch.empty(NM, T, V, Cout, device=x.device, dtype=torch.float32)
         math = math_flag()
-        call('gcn_fwd', x, Wc, biasterm, vals, pattern.dst_ptr, pattern.dst_src, pattern.dst_id,
-             pattern.nnz, z, None, None, NM * T, V, pattern.K, Cin, Cout, 0, 0, 1, math)
+        _gcn_forward(x, Wc, W2.contiguous(), biasterm, vals, pattern, z, None, None, NM * T, V,
+                     pattern.K, Cin, Cout, math)
         ctx.pattern, ctx.math = pattern, math
         ctx.save_for_backward(x, vals, Wc)
         return z
@@ -240,7 +259,7 @@ class GraphConv(Function):
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=x.device)
         call('gcn_bwd_w', gz, None, None, None, None, None, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
              pat.nnz, dWc, dbt, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
-        return gin, dvals, dWc, dbt, None
+        return gin, dvals, dWc, dbt, None, None
 
 
 class Pool(Function):

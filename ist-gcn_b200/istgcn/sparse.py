@@ -35,6 +35,11 @@ class SparsePattern(object):
             return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
         self.flat_idx = dev(k * V * V + v * V + w, torch.int64)
         self.dst_ptr, self.dst_src, self.dst_id = dev(dst_ptr), dev(v[order_d]), dev(ids[order_d])
+        # transposed adjacency for the input gradient: grouped by (k, v), "source" = w
+        order_t = np.lexsort((w, v, k))                 # by k, then v, then w
+        counts_t = np.bincount(k[order_t] * V + v[order_t], minlength=K * V)
+        self.t_ptr = dev(np.concatenate([[0], np.cumsum(counts_t)]))
+        self.t_src, self.t_id = dev(w[order_t]), dev(ids[order_t])
         self.src_ptr = dev(src_ptr)
         self.src_kw = dev(k[order_s] * V + w[order_s])
         self.src_id = dev(ids[order_s])

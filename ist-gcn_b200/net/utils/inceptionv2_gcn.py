@@ -44,6 +44,6 @@ class Inception2(nn.Module):
         assert A.size(0) == self.kernel_size
         pattern = self._cache.get(A, A2, A3)
         conv = self.branch.conv
-        vals, wc, biasterm = graph_conv_operands(conv.weight, conv.bias, [A, A2, A3], pattern)
-        y = ops.GraphConv.apply(to_channels_last(x.float()), vals, wc, biasterm, pattern)
+        vals, wc, biasterm, w2 = graph_conv_operands(conv.weight, conv.bias, [A, A2, A3], pattern)
+        y = ops.GraphConv.apply(to_channels_last(x.float()), vals, wc, biasterm, w2, pattern)
         return to_channels_first(y), A, A2, A3

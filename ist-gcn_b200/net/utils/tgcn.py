@@ -54,6 +54,6 @@ class ConvTemporalGraphical(nn.Module):
     def forward(self, x, A):
         assert A.size(0) == self.kernel_size
         pattern = self._cache.get(A)
-        vals, wc, biasterm = graph_conv_operands(self.conv.weight, self.conv.bias, [A], pattern)
-        y = ops.GraphConv.apply(to_channels_last(x.float()), vals, wc, biasterm, pattern)
+        vals, wc, biasterm, w2 = graph_conv_operands(self.conv.weight, self.conv.bias, [A], pattern)
+        y = ops.GraphConv.apply(to_channels_last(x.float()), vals, wc, biasterm, w2, pattern)
         return to_channels_first(y), A

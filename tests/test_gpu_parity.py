@@ -385,3 +385,52 @@ def test_cpu_input_raises(env):
     model = net.ist_gcn.Model(3, 60, dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), True)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         model(torch.zeros(1, 3, 8, 25, 2))
+
+
+# ----------------------------------------------------------------------------- tcgen05 engine
+@pytest.mark.parametrize('layout,strategy,cin,cout,nm,t', [
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 64, 64, 4, 37),
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 3, 64, 2, 9),
+    ('ntu-rgb+d', 'spatial', 64, 128, 2, 11),
+    ('openpose_sym', 'spatial_3_sym', 128, 128, 2, 15),
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 128, 256, 2, 40),
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 256, 256, 3, 75),
+])
+def test_tcgen05_engine_matches_oracle(env, layout, strategy, cin, cout, nm, t):
+    """The tcgen05/TMA/TMEM graph-conv kernel (forward and input-gradient forms) vs the fp64
+    oracle: TF32 inputs, so the 2e-2 budget applies (observed ~1e-3)."""
+    from net.utils.graph import Graph
+    from net.utils.inceptionv2_gcn import Inception2
+    from net.utils.tgcn import ConvTemporalGraphical
+    from oracle import model_ref
+    dev = torch.device('cuda')
+    g = Graph(layout, strategy)
+    gen = torch.Generator().manual_seed(cin * 7 + cout)
+    K, V = g.A.shape[0], g.A.shape[1]
+    stacks = [torch.tensor(getattr(g, n), dtype=torch.float32) for n in ('A', 'A2', 'A3') if hasattr(g, n)]
+    adjs = [a * (1 + 0.3 * torch.randn(a.shape, generator=gen)) for a in stacks]
+    x = torch.randn(nm, cin, t, V, generator=gen)
+    mod = (Inception2 if len(adjs) == 3 else ConvTemporalGraphical)(cin, cout, K)
+    conv = mod.branch.conv if len(adjs) == 3 else mod.conv
+    with torch.no_grad():
+        conv.weight.normal_(0, 0.1, generator=gen)
+        conv.bias.normal_(0, 0.1, generator=gen)
+    x64 = x.double().requires_grad_(True)
+    ref = model_ref.graph_conv(x64, conv.weight.detach().double(), conv.bias.detach().double(),
+                               [a.double() for a in adjs])
+    gout = torch.randn(ref.shape, generator=gen)
+    ref.backward(gout.double())
+    mod = mod.to(dev)
+    xg = x.to(dev).requires_grad_(True)
+    old_m, old_t = env.set_math('tf32'), env.set_tensor_core_engine(True)
+    try:
+        out = mod(xg, *[a.to(dev) for a in adjs])[0]
+        out.backward(gout.to(dev))
+        env.set_tensor_core_engine(False)
+        out_mma = mod(xg.detach(), *[a.to(dev) for a in adjs])[0]
+    finally:
+        env.set_math(old_m)
+        env.set_tensor_core_engine(old_t)
+    assert rel(out, ref) < 5e-3
+    assert rel(out, out_mma) < 5e-3
+    assert rel(xg.grad, x64.grad) < 5e-3
