@@ -171,7 +171,7 @@ def run_istgcn(args):
     torch.manual_seed(0)
     model = build_model(args.workload, dev)
     dp.broadcast_state(model)
-    tr = trainer.Trainer(model, base_lr=0.01)
+    tr = trainer.Trainer(model, base_lr=0.01, use_graph=not args.no_graph)
     torch.manual_seed(1000 + rank)
     B = args.batch
     x = torch.randn(B, *w['shape'], device=dev)
@@ -185,9 +185,13 @@ def run_istgcn(args):
     for _ in range(max(3, args.warmup)):
         tr.step(x, y)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # launches per step are counted on an eager iteration (a graph replay re-launches the same
+    # kernels without passing through the Python binding)
     launches0 = _lib.launch_count
-    _lib.timing = {}
+    tr._iteration(x, y, True)
+    launches_per_step = _lib.launch_count - launches0
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -195,9 +199,20 @@ def run_istgcn(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    timing, _lib.timing = _lib.timing, None
-    launches = _lib.launch_count - launches0
     clocks = sampler.stop() if sampler else None
+    launches = launches_per_step * args.steps
+    # per-kernel device time: CUDA events around every launch of an eager pass of the same step
+    # (events cannot be recorded inside a graph replay)
+    _lib.timing = {}
+    prof_steps = min(3, args.steps)
+    ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ep0.record()
+    for _ in range(prof_steps):
+        tr._iteration(x, y, True)
+    ep1.record()
+    barrier()
+    timing, _lib.timing = _lib.timing, None
+    eager_ms = ep0.elapsed_time(ep1)
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -206,21 +221,23 @@ def run_istgcn(args):
     value = world * B * args.steps / (ms / 1e3)
     final_loss = loss.item()
 
-    # per-kernel device time inside the timed region (events on the launching stream)
+    ms_per_step_ = ms / args.steps
     per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in timing.items()}
     top = max(per_kernel, key=per_kernel.get)
     peak, peak_src = measured_peaks()
     alg = algorithmic_bytes(top, B, w['shape'])
     n_launch = len(timing[top])
-    alg_total = sum(alg) * args.steps if alg else None
+    alg_total = sum(alg) * prof_steps if alg else None
     roof = {'kernel': top, 'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
-            'launches': n_launch, 'share_of_step': per_kernel[top] / ms, 'traffic': None}
+            'launches': n_launch, 'share_of_step': per_kernel[top] / prof_steps / ms_per_step_,
+            'traffic': None, 'timed_in': 'eager pass of %d steps (%.1f ms/step)' % (prof_steps, eager_ms / prof_steps)}
     if alg_total:
         ach = alg_total / (per_kernel[top] / 1e3) / 1e9
         roof.update(achieved=ach, frac=ach / peak,
                     algorithmic_bytes_per_launch=alg_total / n_launch,
                     avg_launch_ms=per_kernel[top] / n_launch)
-    shares = {k: round(v / ms, 4) for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+    shares = {k: round(v / prof_steps / ms_per_step_, 4)
+              for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
 
     # end to end through the public API from pinned host buffers
     xh = torch.randn(B, *w['shape']).pin_memory()
@@ -265,6 +282,7 @@ def run_istgcn(args):
         'config': {'workload': w['name'], 'clips_per_gpu': B, 'global_batch': B * world,
                    'dropout': 0.5, 'optimizer': 'SGD(momentum .9, nesterov, wd 1e-4)',
                    'parallelism': 'dp%d' % world, 'activations': 'fp32 channels-last',
+                   'cuda_graph': not args.no_graph,
                    'l2_policy': 'working set (>10 GB of activations per step) is far larger than the 126 MB L2'},
         'clocks': clocks, 'gpu_launches': launches,
         'e2e': {'value': e2e_value, 'unit': 'clips/s',
@@ -348,6 +366,7 @@ def main():
     ap.add_argument('--math', default='tf32', choices=['tf32', '3xtf32'])
     ap.add_argument('--cpu-batch', type=int, default=4, help='clips per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -155,7 +155,8 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
                    const float* Wd, const float* Weff, const float* Wu,
                    float* dh2_ws, float* dh1_ws, float* g1, double* sg1, double* sg1x, float* dWd, float* dbd, float* dWeff,
                    float* dbeff, float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
-                   int stride, float drop_p, uint64_t drop_seed, int math, istgcn_stream_t s);
+                   int stride, float drop_p, uint64_t drop_seed,
+                   const unsigned long long* drop_step, int math, istgcn_stream_t s);
 
 /* ---- block tail: BN2 -> dropout -> + residual -> ReLU (st_gcn_mstcn_1x1.py:262-266) -----
  * out = relu(BN2(u)*keep/(1-p) + res) where res = NULL (0), the block input (identity,
@@ -163,19 +164,23 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
 int istgcn_block_tail_fwd(const float* u, const float* mean2, const float* scale2,
                           const float* beta2, const float* res, const float* mean_r,
                           const float* scale_r, const float* beta_r, float* out, long long rows,
-                          int C, float drop_p, uint64_t drop_seed, istgcn_stream_t s);
+                          int C, float drop_p, uint64_t drop_seed,
+                          const unsigned long long* drop_step, istgcn_stream_t s);
 /* backward reduction pass: go = gout * (out > 0) written to `go` (may alias gout); BN2 sums
  * sum gy, sum gy*uhat with gy = go*keep/(1-p); if rres != NULL also sum go, sum go*rhat.    */
 int istgcn_block_tail_bwd(const float* gout, const float* out, const float* u,
                           const float* mean2, const float* rstd2, const float* rres,
                           const float* mean_r, const float* rstd_r, float* go, double* sg2,
                           double* sg2x, double* sgr, double* sgrx, long long rows, int C,
-                          float drop_p, uint64_t drop_seed, istgcn_stream_t s);
+                          float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                          istgcn_stream_t s);
 
 /* keep-mask of the counter-based dropout the two functions above use (element index =
- * row*C + c); exported so that parity tests can inject the same mask into the oracle.      */
+ * row*C + c); exported so that parity tests can inject the same mask into the oracle.
+ * drop_step (may be NULL) points at a device-resident step counter that is mixed into the
+ * seed, so that a captured CUDA graph draws a fresh mask on every replay.                   */
 int istgcn_dropout_mask(unsigned char* mask, long long n, float p, uint64_t seed,
-                        istgcn_stream_t s);
+                        const unsigned long long* drop_step, istgcn_stream_t s);
 
 /* ---- head: global average pool over (T, V), mean over M, 1x1 conv (st_gcnold.py:89-94) --*/
 int istgcn_pool_fwd(const float* x, float* pooled, int N, int M, int TV, int C,

@@ -209,6 +209,12 @@ __device__ __forceinline__ float bn_back(float g, float x, float p, float m1, fl
     return p * ((g - m1) - c * (x - mean));
 }
 
+// Dropout seed = host value mixed with an optional device-resident step counter, so that a
+// captured CUDA graph draws a fresh mask on every replay.
+__device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const unsigned long long* step) {
+    return step ? seed + static_cast<uint64_t>(*step) * 0xD1B54A32D192ED03ull : seed;
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) {
     return *reinterpret_cast<const float4*>(p);
 }

@@ -177,7 +177,8 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
                                       const float* __restrict__ scale_r,
                                       const float* __restrict__ beta_r, float* __restrict__ out,
                                       long long n4, int C, int mode, float drop_p, float keep_scale,
-                                      uint64_t seed) {
+                                      uint64_t seed0, const unsigned long long* step) {
+    const uint64_t seed = effective_seed(seed0, step);
     const int c4 = C >> 2;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
          i += (long long)gridDim.x * blockDim.x) {
@@ -216,7 +217,8 @@ __global__ void block_tail_bwd_kernel(const float* __restrict__ gout, const floa
                                       double* __restrict__ sg2, double* __restrict__ sg2x,
                                       double* __restrict__ sgr, double* __restrict__ sgrx,
                                       long long rows, int C, float drop_p, float keep_scale,
-                                      uint64_t seed) {
+                                      uint64_t seed0, const unsigned long long* step) {
+    const uint64_t seed = effective_seed(seed0, step);
     __shared__ float red[4][256 * 4 / 4 * 4];   // [quantity][thread*4 + j] -> 4 KB each
     const int c4 = C >> 2;
     const int rows_per_iter = blockDim.x / c4;
@@ -290,7 +292,9 @@ __global__ void block_tail_bwd_kernel(const float* __restrict__ gout, const floa
     }
 }
 
-__global__ void dropout_mask_kernel(unsigned char* mask, long long n, float p, uint64_t seed) {
+__global__ void dropout_mask_kernel(unsigned char* mask, long long n, float p, uint64_t seed0,
+                                    const unsigned long long* step) {
+    const uint64_t seed = effective_seed(seed0, step);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x)
         mask[i] = dropout_keep(seed, (uint64_t)i, p) ? 1 : 0;
@@ -437,7 +441,7 @@ ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const f
                                      const float* beta2, const float* res, const float* mean_r,
                                      const float* scale_r, const float* beta_r, float* out,
                                      long long rows, int C, float drop_p, uint64_t drop_seed,
-                                     istgcn_stream_t s) {
+                                     const unsigned long long* drop_step, istgcn_stream_t s) {
     ISTGCN_REQUIRE(u && mean2 && scale2 && beta2 && out, ISTGCN_E_ARG, "block_tail_fwd: null pointer");
     ISTGCN_REQUIRE(scale_r == nullptr || (res && mean_r && beta_r), ISTGCN_E_ARG,
                    "block_tail_fwd: residual BatchNorm needs res, mean_r and beta_r");
@@ -448,7 +452,7 @@ ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const f
     if (n4 == 0) return 0;
     block_tail_fwd_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)s>>>(
         u, mean2, scale2, beta2, res, mean_r, scale_r, beta_r, out, n4, C, mode, drop_p,
-        1.f / (1.f - drop_p), drop_seed);
+        1.f / (1.f - drop_p), drop_seed, drop_step);
     return finish_launch("block_tail_fwd");
 }
 
@@ -457,7 +461,7 @@ ISTGCN_API int istgcn_block_tail_bwd(const float* gout, const float* out, const 
                                      const float* mean_r, const float* rstd_r, float* go,
                                      double* sg2, double* sg2x, double* sgr, double* sgrx,
                                      long long rows, int C, float drop_p, uint64_t drop_seed,
-                                     istgcn_stream_t s) {
+                                     const unsigned long long* drop_step, istgcn_stream_t s) {
     ISTGCN_REQUIRE(gout && out && u && mean2 && rstd2 && go && sg2 && sg2x, ISTGCN_E_ARG,
                    "block_tail_bwd: null pointer");
     ISTGCN_REQUIRE(C % 4 == 0 && C <= 1024, ISTGCN_E_SHAPE, "block_tail_bwd: C=%d unsupported", C);
@@ -471,19 +475,19 @@ ISTGCN_API int istgcn_block_tail_bwd(const float* gout, const float* out, const 
     if (rres)
         block_tail_bwd_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)s>>>(
             gout, out, u, mean2, rstd2, rres, mean_r, rstd_r, go, sg2, sg2x, sgr, sgrx, rows, C,
-            drop_p, ks, drop_seed);
+            drop_p, ks, drop_seed, drop_step);
     else
         block_tail_bwd_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)s>>>(
             gout, out, u, mean2, rstd2, nullptr, nullptr, nullptr, go, sg2, sg2x, nullptr, nullptr,
-            rows, C, drop_p, ks, drop_seed);
+            rows, C, drop_p, ks, drop_seed, drop_step);
     return finish_launch("block_tail_bwd");
 }
 
 ISTGCN_API int istgcn_dropout_mask(unsigned char* mask, long long n, float p, uint64_t seed,
-                                   istgcn_stream_t s) {
+                                   const unsigned long long* drop_step, istgcn_stream_t s) {
     ISTGCN_REQUIRE(mask, ISTGCN_E_ARG, "dropout_mask: null pointer");
     if (n == 0) return 0;
-    dropout_mask_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)s>>>(mask, n, p, seed);
+    dropout_mask_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)s>>>(mask, n, p, seed, drop_step);
     return finish_launch("dropout_mask");
 }
 

@@ -61,6 +61,52 @@ struct SmemLayout {
     static constexpr int total = bar_off + kNumBars * 8 + 16;
 };
 
+// One destination joint of one partition: acc[f] = sum_j a_j * xs[f][v_j] for FR frames, four
+// channels per lane, entries taken two at a time so that 2*FR 128-bit loads are in flight.
+template <int FR>
+__device__ __forceinline__ void aggregate_joint(float* __restrict__ A, const float* __restrict__ xs,
+                                                const int2* __restrict__ s_ent, int beg, int end,
+                                                int fstride, int V, int w, int c4) {
+    float4 acc[FR];
+#pragma unroll
+    for (int f = 0; f < FR; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = beg;
+    for (; j + 1 < end; j += 2) {
+        const int2 e0 = s_ent[j], e1 = s_ent[j + 1];
+        const float a0 = __int_as_float(e0.y), a1 = __int_as_float(e1.y);
+        const float* x0 = xs + e0.x;
+        const float* x1 = xs + e1.x;
+        float4 u0[FR], u1[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            u0[f] = ld4(x0 + f * fstride);
+            u1[f] = ld4(x1 + f * fstride);
+        }
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            acc[f].x = fmaf(a1, u1[f].x, fmaf(a0, u0[f].x, acc[f].x));
+            acc[f].y = fmaf(a1, u1[f].y, fmaf(a0, u0[f].y, acc[f].y));
+            acc[f].z = fmaf(a1, u1[f].z, fmaf(a0, u0[f].z, acc[f].z));
+            acc[f].w = fmaf(a1, u1[f].w, fmaf(a0, u0[f].w, acc[f].w));
+        }
+    }
+    if (j < end) {
+        const int2 e0 = s_ent[j];
+        const float a0 = __int_as_float(e0.y);
+        const float* x0 = xs + e0.x;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            const float4 xv = ld4(x0 + f * fstride);
+            acc[f].x = fmaf(a0, xv.x, acc[f].x);
+            acc[f].y = fmaf(a0, xv.y, acc[f].y);
+            acc[f].z = fmaf(a0, xv.z, acc[f].z);
+            acc[f].w = fmaf(a0, xv.w, acc[f].w);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < FR; ++f) st4(A + atom_index(f * V + w, c4), acc[f]);
+}
+
 template <int NCOLS>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
@@ -97,10 +143,10 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
     for (int i = tid; i < kNA * kAtomBytes / 4; i += kThreadsTC) As[i] = 0.f;
     for (int i = tid; i < 2 * NCOLS; i += kThreadsTC) s_sum[i] = 0.f;
     if (tid == 0) {
-        for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], kAggThreads); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], kAggThreads / 32); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < kNX; ++i) { mbar_init(&x_full[i], 128); mbar_init(&x_empty[i], kAggThreads); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 128); }
+        for (int i = 0; i < kNX; ++i) { mbar_init(&x_full[i], 4); mbar_init(&x_empty[i], kAggThreads / 32); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) tma_prefetch_desc(&wmap);
@@ -223,7 +269,8 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                 }
             }
             tc_fence_before();
-            mbar_arrive(&t_empty[buf]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
     } else if (warp < 4 || warp >= 16) {
         // =========================== loaders: input slice -> Xs[xb][row][32]
@@ -282,7 +329,8 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                         xs[i] = v;
                     }
                 }
-                mbar_arrive(&x_full[xb]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x_full[xb]);
             }
         }
     } else {
@@ -308,34 +356,20 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                     float* A = As + sa * (kAtomBytes / 4);
                     if (active) {
                         const int beg = s_ptr[k * V + w], end = s_ptr[k * V + w + 1];
-                        float4 acc[8];
-#pragma unroll
-                        for (int f = 0; f < 8; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        int2 nxt = beg < end ? s_ent[beg] : make_int2(0, 0);
-                        for (int j = beg; j < end; ++j) {
-                            const int2 cur = nxt;
-                            if (j + 1 < end) nxt = s_ent[j + 1];
-                            const float a = __int_as_float(cur.y);
-                            const float* xp = xs + cur.x;
-#pragma unroll
-                            for (int f = 0; f < 8; ++f) {
-                                if (f < F) {
-                                    const float4 xv = ld4(xp + f * fstride);
-                                    acc[f].x = fmaf(a, xv.x, acc[f].x);
-                                    acc[f].y = fmaf(a, xv.y, acc[f].y);
-                                    acc[f].z = fmaf(a, xv.z, acc[f].z);
-                                    acc[f].w = fmaf(a, xv.w, acc[f].w);
-                                }
-                            }
+                        switch (F) {       // frames per tile: 5 (V=25), 7 (V=18), 8 (V<=16) ...
+                            case 5: aggregate_joint<5>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+                            case 7: aggregate_joint<7>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+                            case 8: aggregate_joint<8>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+                            case 6: aggregate_joint<6>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+                            default: aggregate_joint<4>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
                         }
-#pragma unroll
-                        for (int f = 0; f < 8; ++f)
-                            if (f < F) st4(A + atom_index(f * V + w, c4), acc[f]);
                     }
                     fence_proxy_async();
-                    mbar_arrive(&a_full[sa]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_full[sa]);
                 }
-                mbar_arrive(&x_empty[xb]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&x_empty[xb]);
             }
         }
     }

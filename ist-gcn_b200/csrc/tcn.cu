@@ -239,6 +239,7 @@ struct TcnBwdUpParams {
     int C, bp;
     float drop_p, keep_scale;
     uint64_t seed;
+    const unsigned long long* step;
 };
 
 template <int NT, bool PRECISE>
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc_w[ch][i] = 0.f;
     const int wn = warp & 3, wk = warp >> 2;    // n-tile of the chunk, K-half (64 rows)
+    const uint64_t eseed = effective_seed(p.seed, p.step);
 
     const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
                         if (p.drop_p > 0.f) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j)
-                                gy[j] = dropout_keep(p.seed, (uint64_t)(off + j), p.drop_p)
+                                gy[j] = dropout_keep(eseed, (uint64_t)(off + j), p.drop_p)
                                             ? gy[j] * p.keep_scale : 0.f;
                         }
                         v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
@@ -732,8 +734,8 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
                               const float* Wu, float* dh2_ws, float* dh1_ws, float* g1, double* sg1,
                               double* sg1x, float* dWd, float* dbd, float* dWeff, float* dbeff,
                               float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
-                              int stride, float drop_p, uint64_t drop_seed, int math,
-                              istgcn_stream_t s) {
+                              int stride, float drop_p, uint64_t drop_seed,
+                              const unsigned long long* drop_step, int math, istgcn_stream_t s) {
     ISTGCN_REQUIRE(go && u && p2 && m12 && c2 && mean2 && z && scale1 && beta1 && mean1 && rstd1 && h1 && h2 &&
                        Wd && Weff && Wu && dh2_ws && dh1_ws && g1 && sg1 && sg1x && dWd && dbd &&
                        dWeff && dbeff && dWu && dbu,
@@ -746,7 +748,8 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
     const int Tout = (T - 1) / stride + 1;
     {
         TcnBwdUpParams p{go, u, p2, m12, c2, mean2, h2, Wu, dh2_ws, dWu, dbu, dbeff,
-                         (long long)NM * Tout * V, C, bp, drop_p, 1.f / (1.f - drop_p), drop_seed};
+                         (long long)NM * Tout * V, C, bp, drop_p, 1.f / (1.f - drop_p), drop_seed,
+                         drop_step};
         const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * ld_t(bp) + 8 + bp * (C + 4) + C + bp);
         const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 3);
 #define LAUNCH_BU(NT, PC)                                            \

@@ -45,6 +45,7 @@ class GradBuckets(object):
             self._close(cur)
         self._handles = []
         self._hooks = []
+        self.defer = False          # True: hooks only count, finish() launches every collective
         for b_idx, b in enumerate(self.buckets):
             for n, p in b['params']:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b_idx)))
@@ -64,7 +65,7 @@ class GradBuckets(object):
         def hook(param):
             b = self.buckets[b_idx]
             b['pending'] -= 1
-            if b['pending'] == 0:
+            if b['pending'] == 0 and not self.defer:
                 self._launch(b)
         return hook
 

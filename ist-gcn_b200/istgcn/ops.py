@@ -18,6 +18,21 @@ from . import _lib, math_flag, use_tc
 from ._lib import call, f64, i64, u64
 
 
+_step_counters = {}
+
+
+def step_counter(device):
+    """Device-resident training-step counter (int64[1]) mixed into every dropout seed; the
+    trainer increments it once per step (inside the captured graph when graphs are used)."""
+    device = torch.device(device)
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.type, index)
+    device = torch.device(device.type, index)
+    if key not in _step_counters:
+        _step_counters[key] = torch.zeros(1, dtype=torch.int64, device=device)
+    return _step_counters[key]
+
+
 def _coeffs(n, C, device):
     buf = torch.empty(n, C, device=device, dtype=torch.float32)
     return [buf[i] for i in range(n)]
@@ -158,7 +173,7 @@ class STBlock(Function):
         out = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
         call('block_tail_fwd', u, mean2, scale2, bn2_b, res, mean_r, scale_r,
              bnr_b if cfg.res_mode == 2 else None, out, i64(R_out), Cout, float(drop_p),
-             u64(cfg.seed))
+             u64(cfg.seed), step_counter(dev))
 
         ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
         ctx.dims = (NM, T, Tout, V, Cin, Cout)
@@ -184,7 +199,7 @@ class STBlock(Function):
         go = torch.empty_like(gout)
         call('block_tail_bwd', gout, out, u, mean2, rstd2, rres, mean_r, rstd_r, go, sums[0], sums[1],
              sums[2] if rres is not None else None, sums[3] if rres is not None else None,
-             i64(R_out), Cout, float(drop_p), u64(seed))
+             i64(R_out), Cout, float(drop_p), u64(seed), step_counter(dev))
         p2, m12, c2, dg2, db2 = _coeffs(5, Cout, dev)
         call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2, Cout)
         dWd, dbd = torch.zeros_like(Wd), torch.zeros(bp, device=dev)
@@ -195,7 +210,7 @@ class STBlock(Function):
         dh1 = torch.empty(R_in, bp, device=dev, dtype=torch.float32)
         call('tcn_bwd', go, u, p2, m12, c2, mean2, z, scale1, beta1, mean1, rstd1, h1, h2, Wd, Weff, Wu, dh2,
              dh1, g1, sums[4], sums[5], dWd, dbd, dWeff, dbeff, dWu, dbu, NM, T, V, Cout, bp, s,
-             float(drop_p), u64(seed), math)
+             float(drop_p), u64(seed), step_counter(dev), math)
         p1, m11, c1, dg1, db1 = _coeffs(5, Cout, dev)
         call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
         gin = torch.empty_like(x)
@@ -286,5 +301,5 @@ def dropout_mask(numel, p, seed, device):
     """The keep-mask STBlock's counter-based dropout uses for a (rows, C) tensor of ``numel``
     elements and ``seed`` -- exported for parity tests."""
     mask = torch.empty(numel, device=device, dtype=torch.uint8)
-    call('dropout_mask', mask, _lib.i64(numel), float(p), u64(seed))
+    call('dropout_mask', mask, _lib.i64(numel), float(p), u64(seed), step_counter(torch.device(device)))
     return mask

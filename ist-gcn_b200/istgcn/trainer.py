@@ -34,26 +34,78 @@ def adjust_lr(optimizer, base_lr, step, epoch):
 
 class Trainer(object):
     """model + SGD(nesterov) + gradient buckets; ``step(x, label)`` is one iteration of
-    recognition.py:249-298 (forward, loss, zero_grad, backward, optimizer step)."""
+    recognition.py:249-298 (forward, loss, zero_grad, backward, optimizer step).
+
+    ``use_graph=True`` captures the iteration in a CUDA graph after two eager warm-up steps and
+    replays it afterwards: the block launches ~800 small kernels per step (the fused kernels plus
+    the tiny parameter-regrouping ops), which is launch-bound from Python at B200 speeds.  With
+    more than one rank the graph holds forward + backward only; the bucket all-reduces and the
+    optimiser step run right after the replay (the collective is 4.4 MB, i.e. latency-bound, so
+    little is lost against the eager mode where it overlaps the backward pass)."""
 
     def __init__(self, model, base_lr=0.1, weight_decay=1e-4, nesterov=True, momentum=0.9,
-                 bucket_bytes=2 << 20, group=None):
+                 bucket_bytes=2 << 20, group=None, use_graph=False):
         self.model = model
         self.buckets = dp.GradBuckets(list(model.named_parameters()), bucket_bytes, group)
         params = [p for b in self.buckets.buckets for _, p in b['params']]
         self.optimizer = torch.optim.SGD(params, lr=base_lr, momentum=momentum, nesterov=nesterov,
                                          weight_decay=weight_decay, foreach=True)
         self.base_lr = base_lr
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
+        self._eager_steps = 0
 
-    def step(self, x, label):
+    # one iteration; ``with_optimizer`` False leaves the averaged gradients in the buckets
+    def _iteration(self, x, label, with_optimizer):
+        from . import ops
         self.model.train()
+        ops.step_counter(x.device).add_(1)
         self.buckets.zero()
         output = self.model(x)
         loss = F.cross_entropy(output, label)
         loss.backward()
-        self.buckets.finish()
-        self.optimizer.step()
+        if with_optimizer:
+            self.buckets.finish()
+            self.optimizer.step()
         return loss
+
+    def invalidate_graph(self):
+        """Call after changing the learning rate (it is baked into the captured kernels)."""
+        self._graph = None
+
+    def set_lr(self, lr):
+        for group in self.optimizer.param_groups:
+            if group['lr'] != lr:
+                group['lr'] = lr
+                self.invalidate_graph()
+
+    def step(self, x, label):
+        if not self.use_graph:
+            return self._iteration(x, label, True)
+        single = self.buckets.world == 1
+        if self._eager_steps < 2:               # momentum buffers, caches, cuda handles
+            self._eager_steps += 1
+            return self._iteration(x, label, True)
+        if self._graph is None:
+            sx, sy = torch.empty_like(x), torch.empty_like(label)
+            sx.copy_(x)
+            sy.copy_(label)
+            self.buckets.defer = not single
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                sloss = self._iteration(sx, sy, single)
+            self._graph, self._static = graph, (sx, sy, sloss)
+            # the capture itself did not execute anything: fall through to the first replay
+        sx, sy, sloss = self._static
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(label, non_blocking=True)
+        self._graph.replay()
+        if not single:
+            self.buckets.finish()
+            self.optimizer.step()
+        return sloss
 
     @torch.no_grad()
     def evaluate(self, x):
