@@ -122,13 +122,23 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const fl
  * with in' = in, or in' = bn_p*((in - bn_m1) - bn_c*(in2 - bn_mu)) when bn_p != NULL.
  * w_rows is [K*Cout][CinPad] (CinPad = Cin rounded up to 32, padding columns zero), 16-byte
  * aligned; lptr[K*V+1] / lsrc / lid group the non-zeros by (k, destination joint).
- * TF32 inputs, fp32 accumulation in tensor memory.                                          */
+ * in_out (may be NULL) receives a copy of in' ([rows][Cin]): the input-gradient call uses it to
+ * materialise dz for the two kernels below.  TF32 inputs, fp32 accumulation in tensor memory. */
 int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const float* bn_m1,
                   const float* bn_c, const float* bn_mu, const float* w_rows, const float* vals,
                   const int* lptr, const int* lsrc, const int* lid, int nnz,
-                  const float* bias_vc, const float* add_rows, float* out, double* stat_sum,
+                  const float* bias_vc, const float* add_rows, float* out, float* in_out,
+                  double* stat_sum,
                   double* stat_sumsq, int frames, int V, int K, int Cin, int CinPad, int Cout,
                   istgcn_stream_t s);
+
+/* adjacency gradient on the tcgen05 engine (both operands fed by TMA):
+ *   dvals[id] += sum_{f,ci} x[(f,v)][ci] * (dz Wc_k^T)[(f,w)][ci]   over the non-zeros (k,v,w)
+ * dz [frames*V][Cout] (gradient w.r.t. the graph-conv output), Wc [K*Cin][Cout]; lists grouped
+ * by (k, destination w) with lsrc = source joint v, lid = canonical id.  Cout % 32 == 0.     */
+int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const int* lptr,
+                        const int* lsrc, const int* lid, int nnz, float* dvals, int frames, int V,
+                        int K, int Cin, int Cout, istgcn_stream_t s);
 
 /* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
  *   a  = relu((z - mean1)*scale1 + beta1)              (tcn_start: BN + ReLU)

@@ -222,4 +222,17 @@ __device__ __forceinline__ void st4(float* p, const float4& v) {
     *reinterpret_cast<float4*>(p) = v;
 }
 
+// Cooperative tile staging with memory-level parallelism: every thread first issues COUNT
+// independent 16-byte loads (items tid + u*kThreads, u < COUNT, offset by `base`) and only then
+// stores them, so COUNT*kThreads*16 bytes are in flight per CTA instead of one load per thread.
+// ld(i) -> float4 (returns zeros / the transformed value for item i), st(i, v).
+template <int COUNT, typename LD, typename ST>
+__device__ __forceinline__ void stage4(int tid, int base, LD ld, ST st) {
+    float4 v[COUNT];
+#pragma unroll
+    for (int u = 0; u < COUNT; ++u) v[u] = ld(base + tid + u * kThreads);
+#pragma unroll
+    for (int u = 0; u < COUNT; ++u) st(base + tid + u * kThreads, v[u]);
+}
+
 }  // namespace istgcn

@@ -42,13 +42,15 @@ __device__ __forceinline__ void load_x_slice(float* xs, const float* __restrict_
                                              int valid_rows, int Cin, int ci0, int tid,
                                              const FrameMap& fm, int V) {
     if ((Cin & 3) == 0) {
-        for (int i = tid; i < kTileRows * 8; i += kThreads) {
-            const int r = i >> 3, c4 = (i & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < valid_rows && ci0 + c4 < Cin)
-                v = ld4(x + map_row(fm, row0 + r, V) * Cin + ci0 + c4);
-            st4(xs + r * 32 + c4, v);
-        }
+        stage4<kTileRows * 8 / kThreads>(
+            tid, 0,
+            [&](int i) {
+                const int r = i >> 3, c4 = (i & 7) * 4;
+                return (r < valid_rows && ci0 + c4 < Cin)
+                           ? ld4(x + map_row(fm, row0 + r, V) * Cin + ci0 + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            },
+            [&](int i, const float4& v) { st4(xs + (i >> 3) * 32 + (i & 7) * 4, v); });
     } else {
         for (int i = tid; i < kTileRows * 32; i += kThreads) {
             const int r = i >> 5, c = i & 31;
@@ -136,13 +138,16 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
             for (int k = 0; k < K; ++k) {
                 if (k > 0) __syncthreads();    // mma of partition k-1 finished with As / Bs
                 // Bs[i][n] = Wc[(k*Cin + ci0 + i)][n0 + n]
-                for (int i = tid; i < 32 * (NCOLS / 4); i += kThreads) {
-                    const int r = i / (NCOLS / 4), c4 = (i % (NCOLS / 4)) * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ci0 + r < Cin)
-                        v = ld4(p.Wc + (size_t)(k * Cin + ci0 + r) * Cout + n0 + c4);
-                    st4(Bs + r * LDB + c4, v);
-                }
+                stage4<32 * (NCOLS / 4) / kThreads>(
+                    tid, 0,
+                    [&](int i) {
+                        const int r = i / (NCOLS / 4), c4 = (i % (NCOLS / 4)) * 4;
+                        return ci0 + r < Cin ? ld4(p.Wc + (size_t)(k * Cin + ci0 + r) * Cout + n0 + c4)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                    },
+                    [&](int i, const float4& v) {
+                        st4(Bs + (i / (NCOLS / 4)) * LDB + (i % (NCOLS / 4)) * 4, v);
+                    });
                 if (k == 0) __syncthreads();   // xs visible before the first aggregation
                 aggregate_partition<8>(As, kLdA, xs, s_ptr, s_src, s_val, k, V, F, warp, lane);
                 __syncthreads();
@@ -290,21 +295,25 @@ __global__ void __launch_bounds__(kThreads) gcn_bwd_x_kernel(GcnBwdXParams p) {
             for (int c0 = 0; c0 < Cout; c0 += 32) {
                 __syncthreads();
                 // DZs[r][c] for c in [c0, c0+32)
-                for (int i = tid; i < kTileRows * 8; i += kThreads) {
-                    const int r = i >> 3, c4 = (i & 7) * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < valid_rows)
-                        v = make_dz(p.g, p.z, p.bn, (row0 + r) * Cout + c0 + c4, c0 + c4);
-                    st4(DZs + r * kLdA + c4, v);
-                }
+                stage4<kTileRows * 8 / kThreads>(
+                    tid, 0,
+                    [&](int i) {
+                        const int r = i >> 3, c4 = (i & 7) * 4;
+                        return r < valid_rows
+                                   ? make_dz(p.g, p.z, p.bn, (row0 + r) * Cout + c0 + c4, c0 + c4)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    },
+                    [&](int i, const float4& v) { st4(DZs + (i >> 3) * kLdA + (i & 7) * 4, v); });
                 // Wt[k*32 + i][c] = Wc[(k*Cin + ci0 + i)][c0 + c]
-                for (int i = tid; i < kTileRows * 8; i += kThreads) {
-                    const int r = i >> 3, c4 = (i & 7) * 4;
-                    const int k = r >> 5, ci = ci0 + (r & 31);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (k < K && ci < Cin) v = ld4(p.Wc + (size_t)(k * Cin + ci) * Cout + c0 + c4);
-                    st4(Wt + r * kLdA + c4, v);
-                }
+                stage4<kTileRows * 8 / kThreads>(
+                    tid, 0,
+                    [&](int i) {
+                        const int r = i >> 3, c4 = (i & 7) * 4;
+                        const int k = r >> 5, ci = ci0 + (r & 31);
+                        return (k < K && ci < Cin) ? ld4(p.Wc + (size_t)(k * Cin + ci) * Cout + c0 + c4)
+                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+                    },
+                    [&](int i, const float4& v) { st4(Wt + (i >> 3) * kLdA + (i & 7) * 4, v); });
                 __syncthreads();
                 warp_mma<2, 8, false, true, PRECISE>(acc, DZs + warp_m * 32 * kLdA, kLdA,
                                                      Wt + warp_n * 64 * kLdA, kLdA, 32, lane);
@@ -430,13 +439,17 @@ __global__ void __launch_bounds__(kThreads) gcn_bwd_w_kernel(GcnBwdWParams p) {
         for (int sl = 0; sl < MB / 32; ++sl)
             load_x_slice(xs + sl * kTileRows * 32, p.x, row0, valid_rows, Cin, ci_base + sl * 32, tid,
                          p.fm, V);
-        for (int i = tid; i < kTileRows * (NB / 4); i += kThreads) {
-            const int r = i / (NB / 4), c4 = (i % (NB / 4)) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < valid_rows)
-                v = make_dz(p.g, p.z, p.bn, (row0 + r) * Cout + n0 + c4, n0 + c4);
-            st4(DZs + r * LDZ + c4, v);
-        }
+#pragma unroll 1
+        for (int base = 0; base < kTileRows * (NB / 4); base += 8 * kThreads)
+            stage4<8>(
+                tid, base,
+                [&](int i) {
+                    const int r = i / (NB / 4), c4 = (i % (NB / 4)) * 4;
+                    return r < valid_rows
+                               ? make_dz(p.g, p.z, p.bn, (row0 + r) * Cout + n0 + c4, n0 + c4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                },
+                [&](int i, const float4& v) { st4(DZs + (i / (NB / 4)) * LDZ + (i % (NB / 4)) * 4, v); });
         __syncthreads();
         for (int sl = 0; sl < MB / 32; ++sl)
             aggregate_partition<8>(Xs + sl * 32, LDX, xs + sl * kTileRows * 32, s_ptr, s_src, s_val,

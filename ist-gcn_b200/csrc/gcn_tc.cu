@@ -44,6 +44,7 @@ struct GcnTcParams {
     const float* bias_vc;         // [V][Cout] added per (joint, channel)   (forward) or NULL
     const float* add_rows;        // [rows][Cout] added per row             (backward) or NULL
     float* out;                   // [rows][Cout]
+    float* in_out;                // optional copy of the (transformed) input, [rows][Cin]
     double *stat_sum, *stat_sumsq;
     int frames, V, K, Cin, CinPad, Cout, nnz, tiles;
 };
@@ -313,6 +314,8 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                             v[u].z = bn_back(v[u].z, zv[u].z, pv.z, mv.z, cv.z, uv.z);
                             v[u].w = bn_back(v[u].w, zv[u].w, pv.w, mv.w, cv.w, uv.w);
                         }
+                        if (p.in_out && r < valid && ci0 + c4 < Cin)
+                            st4(p.in_out + (row0 + r) * Cin + ci0 + c4, v[u]);
                         st4(xs + r * 32 + c4, v[u]);
                     }
                 } else {
@@ -325,6 +328,7 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                             if (p.bn.p)
                                 v = bn_back(v, p.in2[off], p.bn.p[ci0 + c], p.bn.m1[ci0 + c],
                                             p.bn.cc[ci0 + c], p.bn.mu[ci0 + c]);
+                            if (p.in_out) p.in_out[off] = v;
                         }
                         xs[i] = v;
                     }
@@ -449,7 +453,7 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
                              const float* bn_c, const float* bn_mu, const float* w_rows,
                              const float* vals, const int* lptr, const int* lsrc, const int* lid,
                              int nnz, const float* bias_vc, const float* add_rows, float* out,
-                             double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
+                             float* in_out, double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
                              int CinPad, int Cout, istgcn_stream_t s) {
     ISTGCN_REQUIRE(in && w_rows && vals && lptr && lsrc && lid && out, ISTGCN_E_ARG,
                    "gcn_tc: null pointer");
@@ -466,7 +470,7 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
                    "gcn_tc: weight pointer must be 16-byte aligned");
     if (frames == 0) return 0;
     tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_vc, add_rows,
-                      out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout, nnz, 0};
+                      out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout, nnz, 0};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     p.tiles = (frames + F - 1) / F;
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);

@@ -52,20 +52,23 @@ __global__ void __launch_bounds__(kThreads) tcn_down_kernel(TcnDownParams p) {
         zero_acc<1, NT>(acc);
         for (int c0 = 0; c0 < C; c0 += 32) {
             __syncthreads();
-            for (int i = tid; i < kTileRows * 8; i += kThreads) {
-                const int r = i >> 3, c4 = (i & 7) * 4;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (r < valid) {
-                    const float4 zv = ld4(p.z + (row0 + r) * C + c0 + c4);
-                    const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
-                                 be = ld4(p.beta1 + c0 + c4);
-                    v.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
-                    v.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
-                    v.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
-                    v.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
-                }
-                st4(As + r * 36 + c4, v);
-            }
+            stage4<kTileRows * 8 / kThreads>(
+                tid, 0,
+                [&](int i) {
+                    const int r = i >> 3, c4 = (i & 7) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < valid) {
+                        const float4 zv = ld4(p.z + (row0 + r) * C + c0 + c4);
+                        const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
+                                     be = ld4(p.beta1 + c0 + c4);
+                        v.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
+                        v.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
+                        v.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
+                        v.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
+                    }
+                    return v;
+                },
+                [&](int i, const float4& v) { st4(As + (i >> 3) * 36 + (i & 7) * 4, v); });
             __syncthreads();
             warp_mma<1, NT, false, false, PRECISE>(acc, As + warp * 16 * 36, 36, Ws + c0 * LDW, LDW,
                                                    32, lane);
@@ -285,28 +288,31 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
             const int c0 = ch * 32;
             if (c0 < C) {
                 __syncthreads();
-                for (int i = tid; i < kTileRows * 8; i += kThreads) {
-                    const int r = i >> 3, c4 = (i & 7) * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                stage4<kTileRows * 8 / kThreads>(
+                    tid, 0,
+                    [&](int i) {
+                        const int r = i >> 3, c4 = (i & 7) * 4;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (r < valid) {
-                        const long long off = (row0 + r) * C + c0 + c4;
-                        const float4 gv = ld4(p.go + off), uv = ld4(p.u + off);
-                        const float4 pv = ld4(p.p2 + c0 + c4), mv = ld4(p.m12 + c0 + c4),
-                                     cv = ld4(p.c2 + c0 + c4), nv = ld4(p.mean2 + c0 + c4);
-                        float gy[4] = {gv.x, gv.y, gv.z, gv.w};
-                        if (p.drop_p > 0.f) {
+                            const long long off = (row0 + r) * C + c0 + c4;
+                            const float4 gv = ld4(p.go + off), uv = ld4(p.u + off);
+                            const float4 pv = ld4(p.p2 + c0 + c4), mv = ld4(p.m12 + c0 + c4),
+                                         cv = ld4(p.c2 + c0 + c4), nv = ld4(p.mean2 + c0 + c4);
+                            float gy[4] = {gv.x, gv.y, gv.z, gv.w};
+                            if (p.drop_p > 0.f) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                gy[j] = dropout_keep(eseed, (uint64_t)(off + j), p.drop_p)
-                                            ? gy[j] * p.keep_scale : 0.f;
+                                for (int j = 0; j < 4; ++j)
+                                    gy[j] = dropout_keep(eseed, (uint64_t)(off + j), p.drop_p)
+                                                ? gy[j] * p.keep_scale : 0.f;
+                            }
+                            v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
+                            v.y = bn_back(gy[1], uv.y, pv.y, mv.y, cv.y, nv.y);
+                            v.z = bn_back(gy[2], uv.z, pv.z, mv.z, cv.z, nv.z);
+                            v.w = bn_back(gy[3], uv.w, pv.w, mv.w, cv.w, nv.w);
                         }
-                        v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
-                        v.y = bn_back(gy[1], uv.y, pv.y, mv.y, cv.y, nv.y);
-                        v.z = bn_back(gy[2], uv.z, pv.z, mv.z, cv.z, nv.z);
-                        v.w = bn_back(gy[3], uv.w, pv.w, mv.w, cv.w, nv.w);
-                    }
-                    st4(DUs + r * 36 + c4, v);
-                }
+                        return v;
+                    },
+                    [&](int i, const float4& v) { st4(DUs + (i >> 3) * 36 + (i & 7) * 4, v); });
                 __syncthreads();
                 // dh2[rows][j] += DU[rows][c0..] * Wu[j][c0..]^T
                 warp_mma<1, NT, false, true, PRECISE>(acc_h, DUs + warp * 16 * 36, 36, Wus + c0, LDWU,
@@ -571,21 +577,27 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_down_kernel(TcnBwdDownParams
             const int c0 = ch * 32;
             if (c0 < C) {
                 __syncthreads();
-                for (int i = tid; i < kTileRows * 8; i += kThreads) {
-                    const int r = i >> 3, c4 = (i & 7) * 4;
-                    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f), av = zv;
-                    if (r < valid) {
-                        zv = ld4(p.z + (row0 + r) * C + c0 + c4);
-                        const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
-                                     be = ld4(p.beta1 + c0 + c4);
-                        av.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
-                        av.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
-                        av.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
-                        av.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
-                    }
-                    st4(Zs + r * 36 + c4, zv);
-                    st4(As + r * LDA + c4, av);
-                }
+                stage4<kTileRows * 8 / kThreads>(
+                    tid, 0,
+                    [&](int i) {
+                        const int r = i >> 3, c4 = (i & 7) * 4;
+                        return r < valid ? ld4(p.z + (row0 + r) * C + c0 + c4)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    },
+                    [&](int i, const float4& zv) {
+                        const int r = i >> 3, c4 = (i & 7) * 4;
+                        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (r < valid) {
+                            const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
+                                         be = ld4(p.beta1 + c0 + c4);
+                            av.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
+                            av.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
+                            av.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
+                            av.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
+                        }
+                        st4(Zs + r * 36 + c4, zv);
+                        st4(As + r * LDA + c4, av);
+                    });
                 __syncthreads();
                 // da[rows][c0..c0+32) = dh1[rows][j] * Wd[c][j]^T  (K = bp)
                 float acc[1][4][4];

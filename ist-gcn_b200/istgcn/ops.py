@@ -64,7 +64,7 @@ def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, C
     """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise."""
     if use_tc():
         call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src,
-             pat.dst_id, pat.nnz, biasterm, None, z, s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout)
+             pat.dst_id, pat.nnz, biasterm, None, z, None, s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout)
     else:
         call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
              s_sum, s_sq, frames, V, K, Cin, Cout, 0, 0, 1, math)
@@ -219,10 +219,11 @@ class STBlock(Function):
         if use_tc():
             # input gradient on the tcgen05 engine: the forward kernel run on dz with the
             # transposed adjacency lists and Wc as the weight; adjacency gradient separately
+            dz = torch.empty_like(z)
             call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
-                 pat.nnz, None, add_in, gin, None, None, NM * T, V, K, Cout, Cout, Cin)
-            call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
-                 pat.src_id, pat.nnz, None, None, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+                 pat.nnz, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin)
+            call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
+                 NM * T, V, K, Cin, Cout)
         else:
             call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
                  pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
