@@ -118,16 +118,21 @@ def algorithmic_bytes(kernel, batch, shape):
     for cin, cout, s, res in BLOCKS:
         tout = (t - 1) // s + 1
         r_in, r_out = NM * t * V, NM * tout * V
-        if kernel == 'gcn_fwd':
-            per_launch.append(4 * r_in * (cin + cout))
+        if kernel == 'gcn_fwd':          # residual 1x1 conv (mma.sync engine): reads x, writes r
             if res == 2:
                 per_launch.append(4 * r_out * (cin + cout))
-        elif kernel == 'gcn_bwd_x':      # reads g1, z, x (for dA) [+ go], writes gin
-            per_launch.append(4 * r_in * (2 * cout + 2 * cin + (cin if res == 1 else 0)))
-            if res == 2:                  # reads go, rres, x ; read-modify-write of strided gin rows
-                per_launch.append(4 * r_out * (2 * cout + 3 * cin))
-        elif kernel == 'gcn_bwd_w':      # reads g1, z, x
+        elif kernel == 'gcn_tc':         # forward: reads x, writes z; input gradient: reads g1, z
+            per_launch.append(4 * r_in * (cin + cout))                      # [+ go], writes gin + dz
+        elif kernel == 'gcn_tc_bwd':
+            per_launch.append(4 * r_in * (3 * cout + cin + (cin if res == 1 else 0)))
+        elif kernel == 'gcn_tc_dvals':   # reads dz, x
+            per_launch.append(4 * r_in * (cout + cin))
+        elif kernel == 'gcn_tc_dw':      # reads dz, x (+ dz again for the bias-term column sums)
             per_launch.append(4 * r_in * (2 * cout + cin))
+        elif kernel == 'gcn_bwd_x':      # residual conv only: reads go, rres, read-modify-write gin
+            if res == 2:
+                per_launch.append(4 * r_out * (2 * cout + 2 * cin))
+        elif kernel == 'gcn_bwd_w':
             if res == 2:
                 per_launch.append(4 * r_out * (2 * cout + cin))
         elif kernel == 'tcn_fwd':        # reads z, writes u (+ h1, h2 write, h1 read)
@@ -226,6 +231,8 @@ def run_istgcn(args):
     top = max(per_kernel, key=per_kernel.get)
     peak, peak_src = measured_peaks()
     alg = algorithmic_bytes(top, B, w['shape'])
+    if top == 'gcn_tc':                  # the same entry point serves forward and input gradient
+        alg = alg + algorithmic_bytes('gcn_tc_bwd', B, w['shape'])
     n_launch = len(timing[top])
     alg_total = sum(alg) * prof_steps if alg else None
     roof = {'kernel': top, 'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,

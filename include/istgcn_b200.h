@@ -140,6 +140,14 @@ int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const 
                         const int* lsrc, const int* lid, int nnz, float* dvals, int frames, int V,
                         int K, int Cin, int Cout, istgcn_stream_t s);
 
+/* weight gradient on the tcgen05 engine: dWc[K*Cin][Cout] += X'^T dz with both operands read
+ * MN-major (contraction over the rows of the frame tile), accumulators resident in tensor memory
+ * for the whole kernel; dbiasterm[V][Cout] += sum over frames of dz (may be NULL).  Outputs are
+ * caller-zeroed; lists grouped by (k, destination w); Cout % 32 == 0.                        */
+int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* vals, const int* lptr,
+                     const int* lsrc, const int* lid, int nnz, float* dWc, float* dbiasterm,
+                     int frames, int V, int K, int Cin, int Cout, istgcn_stream_t s);
+
 /* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
  *   a  = relu((z - mean1)*scale1 + beta1)              (tcn_start: BN + ReLU)
  *   h1 = a Wd + bd                                     (conv_1x1_start, C -> b)

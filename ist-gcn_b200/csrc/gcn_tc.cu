@@ -62,52 +62,6 @@ struct SmemLayout {
     static constexpr int total = bar_off + kNumBars * 8 + 16;
 };
 
-// One destination joint of one partition: acc[f] = sum_j a_j * xs[f][v_j] for FR frames, four
-// channels per lane, entries taken two at a time so that 2*FR 128-bit loads are in flight.
-template <int FR>
-__device__ __forceinline__ void aggregate_joint(float* __restrict__ A, const float* __restrict__ xs,
-                                                const int2* __restrict__ s_ent, int beg, int end,
-                                                int fstride, int V, int w, int c4) {
-    float4 acc[FR];
-#pragma unroll
-    for (int f = 0; f < FR; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
-    int j = beg;
-    for (; j + 1 < end; j += 2) {
-        const int2 e0 = s_ent[j], e1 = s_ent[j + 1];
-        const float a0 = __int_as_float(e0.y), a1 = __int_as_float(e1.y);
-        const float* x0 = xs + e0.x;
-        const float* x1 = xs + e1.x;
-        float4 u0[FR], u1[FR];
-#pragma unroll
-        for (int f = 0; f < FR; ++f) {
-            u0[f] = ld4(x0 + f * fstride);
-            u1[f] = ld4(x1 + f * fstride);
-        }
-#pragma unroll
-        for (int f = 0; f < FR; ++f) {
-            acc[f].x = fmaf(a1, u1[f].x, fmaf(a0, u0[f].x, acc[f].x));
-            acc[f].y = fmaf(a1, u1[f].y, fmaf(a0, u0[f].y, acc[f].y));
-            acc[f].z = fmaf(a1, u1[f].z, fmaf(a0, u0[f].z, acc[f].z));
-            acc[f].w = fmaf(a1, u1[f].w, fmaf(a0, u0[f].w, acc[f].w));
-        }
-    }
-    if (j < end) {
-        const int2 e0 = s_ent[j];
-        const float a0 = __int_as_float(e0.y);
-        const float* x0 = xs + e0.x;
-#pragma unroll
-        for (int f = 0; f < FR; ++f) {
-            const float4 xv = ld4(x0 + f * fstride);
-            acc[f].x = fmaf(a0, xv.x, acc[f].x);
-            acc[f].y = fmaf(a0, xv.y, acc[f].y);
-            acc[f].z = fmaf(a0, xv.z, acc[f].z);
-            acc[f].w = fmaf(a0, xv.w, acc[f].w);
-        }
-    }
-#pragma unroll
-    for (int f = 0; f < FR; ++f) st4(A + atom_index(f * V + w, c4), acc[f]);
-}
-
 template <int NCOLS>
 __global__ void __launch_bounds__(kThreadsTC, 1)
 gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
@@ -360,13 +314,7 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                     float* A = As + sa * (kAtomBytes / 4);
                     if (active) {
                         const int beg = s_ptr[k * V + w], end = s_ptr[k * V + w + 1];
-                        switch (F) {       // frames per tile: 5 (V=25), 7 (V=18), 8 (V<=16) ...
-                            case 5: aggregate_joint<5>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
-                            case 7: aggregate_joint<7>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
-                            case 8: aggregate_joint<8>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
-                            case 6: aggregate_joint<6>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
-                            default: aggregate_joint<4>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
-                        }
+                        aggregate_joint_any(F, A, xs, s_ent, beg, end, fstride, V, w, c4);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -401,7 +349,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows) {
+int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows,
+                    bool atom32) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* sym = nullptr;
@@ -418,7 +367,8 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] box %d", (int)r, rows, cols,

@@ -112,14 +112,19 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, ui
 //   MN-major operand : the same tile read the other way: 32 tf32 along M/N per 128-B row, the
 //                      8 rows of a 1024-B group are 8 consecutive K; SBO = 1024 (next 8 K),
 //                      LBO = byte distance between 32-wide M/N groups.
+//   MN-major TF32    : only SWIZZLE_128B_BASE32B (layout type 1) is legal (cutlass
+//                      sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the only
+//                      available smem layout"): 128-B rows, 32-B chunks XORed with row % 4,
+//                      swizzle atom = 4 K-rows (512 B), so SBO = 512 and a K-step of 8 rows =
+//                      start address + 1024 B.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_bytes,
-                                              uint32_t sbo_bytes) {
+                                              uint32_t sbo_bytes, uint32_t layout_type = 2) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
     d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-    d |= 1ull << 46;          // version = 1
-    d |= 2ull << 61;          // layout_type = SWIZZLE_128B
+    d |= 1ull << 46;                                        // version = 1
+    d |= static_cast<uint64_t>(layout_type) << 61;          // 2 = SWIZZLE_128B, 1 = 128B_BASE32B
     return d;
 }
 
@@ -134,6 +139,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, bool a_mn_major,
 // XORed with row % 8 -- the layout both TMA and tcgen05 use for SWIZZLE_128B)
 __device__ __forceinline__ int atom_index(int row, int e) {
     return ((row >> 3) << 8) + ((row & 7) << 5) + ((((e >> 2) ^ (row & 7)) << 2) | (e & 3));
+}
+
+// the same for the 32-byte-atom variant (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B / UMMA
+// SWIZZLE_128B_BASE32B): 32-byte chunk index XORed with row % 4
+__device__ __forceinline__ int atom_index32(int row, int e) {
+    return (row << 5) + ((((e >> 3) ^ (row & 3)) << 3) | (e & 7));
 }
 
 // TMEM -> registers: this warp's 32 lanes x 32 consecutive columns
@@ -170,10 +181,72 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
     return v[0];
 }
 
+// One destination joint of one partition: acc[f] = sum_j a_j * xs[f][v_j] for FR frames, four
+// channels per lane, entries taken two at a time so that 2*FR 128-bit loads are in flight.
+template <int FR, bool SW32>
+__device__ __forceinline__ void aggregate_joint(float* __restrict__ A, const float* __restrict__ xs,
+                                                const int2* __restrict__ s_ent, int beg, int end,
+                                                int fstride, int V, int w, int c4) {
+    float4 acc[FR];
+#pragma unroll
+    for (int f = 0; f < FR; ++f) acc[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int j = beg;
+    for (; j + 1 < end; j += 2) {
+        const int2 e0 = s_ent[j], e1 = s_ent[j + 1];
+        const float a0 = __int_as_float(e0.y), a1 = __int_as_float(e1.y);
+        const float* x0 = xs + e0.x;
+        const float* x1 = xs + e1.x;
+        float4 u0[FR], u1[FR];
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            u0[f] = ld4(x0 + f * fstride);
+            u1[f] = ld4(x1 + f * fstride);
+        }
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            acc[f].x = fmaf(a1, u1[f].x, fmaf(a0, u0[f].x, acc[f].x));
+            acc[f].y = fmaf(a1, u1[f].y, fmaf(a0, u0[f].y, acc[f].y));
+            acc[f].z = fmaf(a1, u1[f].z, fmaf(a0, u0[f].z, acc[f].z));
+            acc[f].w = fmaf(a1, u1[f].w, fmaf(a0, u0[f].w, acc[f].w));
+        }
+    }
+    if (j < end) {
+        const int2 e0 = s_ent[j];
+        const float a0 = __int_as_float(e0.y);
+        const float* x0 = xs + e0.x;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            const float4 xv = ld4(x0 + f * fstride);
+            acc[f].x = fmaf(a0, xv.x, acc[f].x);
+            acc[f].y = fmaf(a0, xv.y, acc[f].y);
+            acc[f].z = fmaf(a0, xv.z, acc[f].z);
+            acc[f].w = fmaf(a0, xv.w, acc[f].w);
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < FR; ++f)
+        st4(A + (SW32 ? atom_index32(f * V + w, c4) : atom_index(f * V + w, c4)), acc[f]);
+}
+
+// dispatch on the number of frames per tile: 5 (V=25), 7 (V=18), 8 (V<=16), ...
+template <bool SW32 = false>
+__device__ __forceinline__ void aggregate_joint_any(int F, float* __restrict__ A,
+                                                    const float* __restrict__ xs,
+                                                    const int2* __restrict__ s_ent, int beg, int end,
+                                                    int fstride, int V, int w, int c4) {
+    switch (F) {
+        case 5: aggregate_joint<5, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        case 7: aggregate_joint<7, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        case 8: aggregate_joint<8, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        case 6: aggregate_joint<6, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        default: aggregate_joint<4, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+    }
+}
+
 // Host: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda needed).
 // 2-D fp32 row-major matrix [rows][cols] -> tiles of [box_rows][32 floats], SWIZZLE_128B.
 int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long long cols,
-                    int box_rows);
+                    int box_rows, bool atom32 = false);
 
 }  // namespace tc
 }  // namespace istgcn

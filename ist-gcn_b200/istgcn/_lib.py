@@ -16,7 +16,7 @@ SYMBOLS = (
     'istgcn_last_error', 'istgcn_version', 'istgcn_check_device',
     'istgcn_data_bn_stats', 'istgcn_data_bn_apply', 'istgcn_data_bn_bwd',
     'istgcn_bn_finalize', 'istgcn_bn_eval_coeffs', 'istgcn_bn_bwd_coeffs',
-    'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals',
+    'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
     'istgcn_block_tail_fwd', 'istgcn_block_tail_bwd', 'istgcn_dropout_mask',
     'istgcn_pool_fwd', 'istgcn_pool_bwd',
@@ -66,7 +66,7 @@ def _conv(a):
 
 # kernels launched per C-ABI call (tcn_fwd = down + up, tcn_bwd = up + temporal + down,
 # pool_fwd = kernel behind a memset) -- used for the ``gpu_launches`` count of bench.py
-KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3}
+KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2}
 launch_count = 0          # kernels launched through this binding since import
 timing = None             # set to a dict by bench.py: name -> list of (start_event, end_event)
 

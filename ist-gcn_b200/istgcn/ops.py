@@ -228,8 +228,12 @@ class STBlock(Function):
             call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
                  pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
-        call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz,
-             dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+        if use_tc():
+            call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc, dbt,
+                 NM * T, V, K, Cin, Cout)
+        else:
+            call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src,
+                 pat.dst_id, pat.nnz, dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
         dWr = dbtr = dgr = dbr = None
         if cfg.res_mode == 2:
             idn = cfg.ident

@@ -12,7 +12,7 @@ per parameter tensor at these sizes (tools/diag_grads.py prints the table), i.e.
 amplifies rounding noise by ~1e4 in the backward pass.  A fixed 1e-4 on gradients is therefore
 not a property even of the reference against itself, so gradient parity is CALIBRATED:
   '3xtf32'  per-tensor relative L2 error vs the fp64 oracle <= max(1e-4, 8 x the error of the
-            fp32 oracle vs the fp64 oracle for the same tensor, 4 x the WORST such fp32-oracle
+            fp32 oracle vs the fp64 oracle for the same tensor, 8 x the WORST such fp32-oracle
             error over all tensors) and cosine similarity of the full gradient >= 0.9999.
             (The backward pass is ~100x more sensitive to forward rounding than the forward
             itself - tools/diag_chain.py - so a tensor on which fp32 PyTorch happens to be
@@ -321,7 +321,7 @@ def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
             assert mine.abs().max().item() < (1e-4 if math == '3xtf32' else 2e-2) * gmax, k
             continue
         e_mine, e_ref = rel_l2(mine, g64[k]), rel_l2(g32[k], g64[k])
-        errs[k] = e_mine / max(1e-4, 8 * e_ref, 4 * worst_ref) if math == '3xtf32' else e_mine / 0.35
+        errs[k] = e_mine / max(1e-4, 8 * e_ref, 8 * worst_ref) if math == '3xtf32' else e_mine / 0.35
     assert not report(errs, 1.0), report(errs, 1.0)
     cos = dot / (n1 ** 0.5 * n2 ** 0.5)
     assert cos > (0.9999 if math == '3xtf32' else 0.98), cos
