@@ -123,13 +123,15 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const fl
  * w_rows is [K*Cout][CinPad] (CinPad = Cin rounded up to 32, padding columns zero), 16-byte
  * aligned; lptr[K*V+1] / lsrc / lid group the non-zeros by (k, destination joint).
  * in_out (may be NULL) receives a copy of in' ([rows][Cin]): the input-gradient call uses it to
- * materialise dz for the two kernels below.  TF32 inputs, fp32 accumulation in tensor memory. */
+ * materialise dz for the two kernels below.  map_side selects where the temporal stride of the
+ * residual branch applies (0: none, 1: input rows are read from frame n*t_in + to*t_stride,
+ * 2: output / add_rows rows are written there).  TF32 inputs, fp32 accumulation in TMEM.     */
 int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const float* bn_m1,
                   const float* bn_c, const float* bn_mu, const float* w_rows, const float* vals,
                   const int* lptr, const int* lsrc, const int* lid, int nnz,
                   const float* bias_vc, const float* add_rows, float* out, float* in_out,
-                  double* stat_sum,
-                  double* stat_sumsq, int frames, int V, int K, int Cin, int CinPad, int Cout,
+                  double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
+                  int CinPad, int Cout, int t_in, int t_out, int t_stride, int map_side,
                   istgcn_stream_t s);
 
 /* adjacency gradient on the tcgen05 engine (both operands fed by TMA):
@@ -146,7 +148,8 @@ int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const 
  * caller-zeroed; lists grouped by (k, destination w); Cout % 32 == 0.                        */
 int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* vals, const int* lptr,
                      const int* lsrc, const int* lid, int nnz, float* dWc, float* dbiasterm,
-                     int frames, int V, int K, int Cin, int Cout, istgcn_stream_t s);
+                     int frames, int V, int K, int Cin, int Cout,
+                     int t_in, int t_out, int t_stride, istgcn_stream_t s);
 
 /* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
  *   a  = relu((z - mean1)*scale1 + beta1)              (tcn_start: BN + ReLU)

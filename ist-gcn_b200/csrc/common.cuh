@@ -222,6 +222,20 @@ __device__ __forceinline__ void st4(float* p, const float4& v) {
     *reinterpret_cast<float4*>(p) = v;
 }
 
+// Temporal stride of the residual branch (st_gcnold.py:186-193): output frame f = n*t_out + to
+// reads input frame n*t_in + to*stride.  t_out == 0 means "same frames" (the graph convolution).
+struct FrameMap {
+    int t_in, t_out, stride;
+};
+__device__ __forceinline__ long long map_row(const FrameMap& m, long long row, int V) {
+    if (m.t_out == 0) return row;
+    const long long f = row / V;
+    const int v = (int)(row - f * V);
+    const long long n = f / m.t_out;
+    const int to = (int)(f - n * m.t_out);
+    return (n * m.t_in + (long long)to * m.stride) * V + v;
+}
+
 // Cooperative tile staging with memory-level parallelism: every thread first issues COUNT
 // independent 16-byte loads (items tid + u*kThreads, u < COUNT, offset by `base`) and only then
 // stores them, so COUNT*kThreads*16 bytes are in flight per CTA instead of one load per thread.

@@ -23,20 +23,6 @@ __device__ __forceinline__ int frames_in_tile(int V) {
     return f > 8 ? 8 : f;
 }
 
-// Temporal stride of the residual branch (st_gcnold.py:186-193): output frame f = n*t_out + to
-// reads input frame n*t_in + to*stride.  t_out == 0 means "same frames" (the graph convolution).
-struct FrameMap {
-    int t_in, t_out, stride;
-};
-__device__ __forceinline__ long long map_row(const FrameMap& m, long long row, int V) {
-    if (m.t_out == 0) return row;
-    const long long f = row / V;
-    const int v = (int)(row - f * V);
-    const long long n = f / m.t_out;
-    const int to = (int)(f - n * m.t_out);
-    return (n * m.t_in + (long long)to * m.stride) * V + v;
-}
-
 // xs[128][32] <- x rows map(row0 + r), r < valid_rows, channels [ci0, ci0+32) (zero beyond)
 __device__ __forceinline__ void load_x_slice(float* xs, const float* __restrict__ x, long long row0,
                                              int valid_rows, int Cin, int ci0, int tid,

@@ -47,6 +47,7 @@ struct GcnTcParams {
     float* in_out;                // optional copy of the (transformed) input, [rows][Cin]
     double *stat_sum, *stat_sumsq;
     int frames, V, K, Cin, CinPad, Cout, nnz, tiles;
+    FrameMap in_map, out_map;     // temporal stride of the residual branch (t_out == 0: none)
 };
 
 template <int NCOLS>
@@ -188,10 +189,11 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                             }
                         }
                     }
-                    float* o = p.out + (row0 + r) * Cout + cg;
+                    const long long orow = map_row(p.out_map, row0 + r, V);
+                    float* o = p.out + orow * Cout + cg;
                     if ((Cout & 3) == 0) {
                         if (p.add_rows) {
-                            const float* a = p.add_rows + (row0 + r) * Cout + cg;
+                            const float* a = p.add_rows + orow * Cout + cg;
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 if (cg + j < Cout) {
@@ -207,7 +209,7 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j)
                             if (cg + j < Cout)
-                                o[j] = v[j] + (p.add_rows ? p.add_rows[(row0 + r) * Cout + cg + j] : 0.f);
+                                o[j] = v[j] + (p.add_rows ? p.add_rows[orow * Cout + cg + j] : 0.f);
                     }
                 }
                 if (p.stat_sum) {
@@ -251,7 +253,7 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         zv[u] = v[u];
                         if (r < valid && ci0 + c4 < Cin) {
-                            const long long off = (row0 + r) * Cin + ci0 + c4;
+                            const long long off = map_row(p.in_map, row0 + r, V) * Cin + ci0 + c4;
                             v[u] = ld4(p.in + off);
                             if (p.bn.p) zv[u] = ld4(p.in2 + off);
                         }
@@ -277,12 +279,12 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                         const int r = i >> 5, c = i & 31;
                         float v = 0.f;
                         if (r < valid && ci0 + c < Cin) {
-                            const long long off = (row0 + r) * Cin + ci0 + c;
+                            const long long off = map_row(p.in_map, row0 + r, V) * Cin + ci0 + c;
                             v = p.in[off];
                             if (p.bn.p)
                                 v = bn_back(v, p.in2[off], p.bn.p[ci0 + c], p.bn.m1[ci0 + c],
                                             p.bn.cc[ci0 + c], p.bn.mu[ci0 + c]);
-                            if (p.in_out) p.in_out[off] = v;
+                            if (p.in_out) p.in_out[(row0 + r) * Cin + ci0 + c] = v;
                         }
                         xs[i] = v;
                     }
@@ -403,8 +405,9 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
                              const float* bn_c, const float* bn_mu, const float* w_rows,
                              const float* vals, const int* lptr, const int* lsrc, const int* lid,
                              int nnz, const float* bias_vc, const float* add_rows, float* out,
-                             float* in_out, double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
-                             int CinPad, int Cout, istgcn_stream_t s) {
+                             float* in_out, double* stat_sum, double* stat_sumsq, int frames, int V,
+                             int K, int Cin, int CinPad, int Cout, int t_in, int t_out, int t_stride,
+                             int map_side, istgcn_stream_t s) {
     ISTGCN_REQUIRE(in && w_rows && vals && lptr && lsrc && lid && out, ISTGCN_E_ARG,
                    "gcn_tc: null pointer");
     ISTGCN_REQUIRE(bn_p == nullptr || (in2 && bn_m1 && bn_c && bn_mu), ISTGCN_E_ARG,
@@ -420,7 +423,10 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
                    "gcn_tc: weight pointer must be 16-byte aligned");
     if (frames == 0) return 0;
     tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_vc, add_rows,
-                      out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout, nnz, 0};
+                      out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout, nnz, 0,
+                      {0, 0, 1}, {0, 0, 1}};
+    if (map_side == 1) p.in_map = {t_in, t_out, t_stride};
+    if (map_side == 2) p.out_map = {t_in, t_out, t_stride};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     p.tiles = (frames + F - 1) / F;
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);

@@ -64,7 +64,8 @@ def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, C
     """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise."""
     if use_tc():
         call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src,
-             pat.dst_id, pat.nnz, biasterm, None, z, None, s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout)
+             pat.dst_id, pat.nnz, biasterm, None, z, None, s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout,
+             0, 0, 1, 0)
     else:
         call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
              s_sum, s_sq, frames, V, K, Cin, Cout, 0, 0, 1, math)
@@ -164,8 +165,14 @@ class STBlock(Function):
                 cfg.ones = torch.ones(V, device=dev, dtype=torch.float32)
             Wr, biasterm_r = Wr.contiguous(), biasterm_r.contiguous()
             rres = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-            call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
-                 rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+            if use_tc():     # strided 1x1 conv = K=1 / identity-adjacency case of the tcgen05 engine
+                W2r = Wr.t().contiguous()                      # (Cout, Cin): rows n, cols ci
+                call('gcn_tc', x, None, None, None, None, None, W2r, cfg.ones, idn.dst_ptr,
+                     idn.dst_src, idn.dst_id, V, biasterm_r, None, rres, None, stats[4], stats[5],
+                     NM * Tout, V, 1, Cin, Cin, Cout, T, Tout, s, 1)
+            else:
+                call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
+                     rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
             mean_r, scale_r, rstd_r = _bn_forward_coeffs(training, stats[4], stats[5], R_out, bnr_w,
                                                          cfg.bnr, Cout, dev)
             bnr_b = bnr_b.contiguous()
@@ -221,7 +228,7 @@ class STBlock(Function):
             # transposed adjacency lists and Wc as the weight; adjacency gradient separately
             dz = torch.empty_like(z)
             call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
-                 pat.nnz, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin)
+                 pat.nnz, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin, 0, 0, 1, 0)
             call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
                  NM * T, V, K, Cin, Cout)
         else:
@@ -230,7 +237,7 @@ class STBlock(Function):
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
         if use_tc():
             call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc, dbt,
-                 NM * T, V, K, Cin, Cout)
+                 NM * T, V, K, Cin, Cout, 0, 0, 1)
         else:
             call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src,
                  pat.dst_id, pat.nnz, dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
@@ -240,11 +247,20 @@ class STBlock(Function):
             pr, m1r, cr, dgr, dbr = _coeffs(5, Cout, dev)
             call('bn_bwd_coeffs', sums[2], sums[3], f64(R_out), bnr_w, rstd_r, pr, m1r, cr, dgr, dbr,
                  Cout)
-            call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr, idn.src_kw,
-                 idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
             dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, Cout, device=dev)
-            call('gcn_bwd_w', go, rres, pr, m1r, cr, mean_r, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id,
-                 V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+            if use_tc():
+                dyr = torch.empty_like(rres)
+                call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
+                     idn.t_id, V, None, gin, gin, dyr, None, None, NM * Tout, V, 1, Cout, Cout, Cin,
+                     T, Tout, s, 2)
+                call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr, dbtr,
+                     NM * Tout, V, 1, Cin, Cout, T, Tout, s)
+            else:
+                call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr,
+                     idn.src_kw, idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, Cout, T, Tout, s,
+                     math)
+                call('gcn_bwd_w', go, rres, pr, m1r, cr, mean_r, x, cfg.ones, idn.dst_ptr, idn.dst_src,
+                     idn.dst_id, V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
         return (gin, dvals, dWc, dbt, None, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr,
                 dbtr, dgr, dbr, None)
 

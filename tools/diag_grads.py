@@ -4,7 +4,7 @@ import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'ist-gcn_b200')); sys.path.insert(0, ROOT)
 import torch, torch.nn.functional as F
-import istgcn, net.ist_gcn
+import istgcn, net.ist_gcn, net.st_gcn_mstcn_1x1
 from oracle import model_ref
 from net.utils.graph import Graph
 spec = importlib.util.spec_from_file_location('mg', os.path.join(ROOT, 'tests/golden/make_golden.py'))
@@ -22,14 +22,14 @@ torch.backends.cuda.matmul.allow_tf32 = False; torch.backends.cudnn.allow_tf32 =
 def oracle(dtype, dev):
     lv = {k: (v.detach().clone().to(dev, dtype).requires_grad_(True) if v.is_floating_point() and 'running' not in k and k not in ('A','A2','A3')
               else (v.to(dev, dtype) if v.is_floating_point() else v.to(dev))) for k, v in state.items()}
-    out = model_ref.forward(lv, x.to(dev, dtype), 'ist_gcn', training=True)
+    out = model_ref.forward(lv, x.to(dev, dtype), name.replace('_kinetics', ''), training=True)
     F.cross_entropy(out, label.to(dev)).backward()
     return out.detach().cpu().double(), {k: v.grad.detach().cpu().double() for k, v in lv.items() if getattr(v, 'grad', None) is not None}
 
 o64, g64 = oracle(torch.float64, 'cpu')
 o32, g32 = oracle(torch.float32, 'cpu')
 o32g, g32g = oracle(torch.float32, 'cuda')
-m = net.ist_gcn.Model(shape[1], ncls, g_args, True); m.load_state_dict(state); m = m.cuda().train()
+m = (net.ist_gcn if 'ist_gcn' in name else net.st_gcn_mstcn_1x1).Model(shape[1], ncls, g_args, True); m.load_state_dict(state); m = m.cuda().train()
 istgcn.set_math(mode)
 out = m(x.cuda()); F.cross_entropy(out, label.cuda()).backward()
 gm = {k: p.grad.detach().cpu().double() for k, p in m.named_parameters() if p.grad is not None}
