@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
     float* h1s = ds + TO * V * LDH;             // [256][LDT] (+8)
     float* Wts = h1s + kUpRows * LDT + 8;       // [15*BP][LDWT]
     float* s_dbd = Wts + kTaps * BP * LDWT;     // [BP]
+    int2* s_row = reinterpret_cast<int2*>(s_dbd + BP + (BP & 1));   // [256] {frame in tile, v*LDH}
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
@@ -428,16 +429,23 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
             if (r < valid) v = ld4(p.h1 + (((size_t)n * p.T + ti0) * V + r) * BP + c4);
             st4(h1s + r * LDT + c4, v);
         }
+        for (int r = tid; r < kUpRows; r += kThreads) {
+            const int ti_l = r / V;
+            s_row[r] = r < valid ? make_int2(ti_l, (r - ti_l * V) * LDH) : make_int2(-1, 0);
+        }
         __syncthreads();
-        // gather offset of dh2 row feeding input row r at tap: -1 if none
-        auto src_off = [&](int r, int tap) -> int {
-            if (r >= valid) return -1;
-            const int ti_l = r / V, v = r - ti_l * V;
-            const int num = ti0 + ti_l + kHalf - tap;
+        // gather offset of the dh2 row that feeds input row (frame ri.x, joint) at `tap`; -1: none
+        auto src_off = [&](int2 ri, int tap) -> int {
+            if (ri.x < 0) return -1;
+            const int num = ti0 + ri.x + kHalf - tap;
             if (num < 0) return -1;
-            const int to = num / s;
-            if (to * s != num || to >= p.Tout) return -1;
-            return ((to - to_lo) * V + v) * LDH;
+            int to = num;
+            if (s == 2) {
+                if (num & 1) return -1;
+                to = num >> 1;
+            }
+            if (to >= p.Tout) return -1;
+            return (to - to_lo) * V * LDH + ri.y;
         };
         // ---- dh1
         for (int mt = warp; mt * 16 < valid; mt += kWarps) {
@@ -446,8 +454,9 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+            const int2 ri0 = s_row[mt * 16 + g], ri1 = s_row[mt * 16 + g + 8];
             for (int tap = 0; tap < kTaps; ++tap) {
-                const int o0 = src_off(mt * 16 + g, tap), o1 = src_off(mt * 16 + g + 8, tap);
+                const int o0 = src_off(ri0, tap), o1 = src_off(ri1, tap);
 #pragma unroll
                 for (int kk = 0; kk < NT; ++kk) {       // k = co
                     float a[4];
@@ -495,7 +504,7 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
                         a[i] = h1s[(k0 + t + 4 * (i >> 1)) * LDT + g + 8 * (i & 1)];
-                    const int o0 = src_off(k0 + t, tap), o1 = src_off(k0 + t + 4, tap);
+                    const int o0 = src_off(s_row[k0 + t], tap), o1 = src_off(s_row[k0 + t + 4], tap);
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         float b[2];
@@ -779,7 +788,7 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
         p.tiles_per_sample = (T + p.TT - 1) / p.TT;
         const int TO = (p.TT - 1 + 2 * kHalf) / stride + 2;
         const size_t smem = sizeof(float) * ((size_t)TO * V * ld_g(bp) + kUpRows * ld_t(bp) + 8 +
-                                             kTaps * bp * ld_g(bp) + bp);
+                                             kTaps * bp * ld_g(bp) + bp + 2) + kUpRows * sizeof(int2);
         const int grid = grid_for((long long)NM * p.tiles_per_sample, 2);
 #define LAUNCH_BT(NT, PC)                                            \
     set_smem(tcn_bwd_t_kernel<NT, PC>, smem);                        \

@@ -325,7 +325,7 @@ def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
             # 3-element importance vectors / 8-wide biases: near-cancelling sums whose relative
             # error is dominated by summation-order noise (fp32 PyTorch itself is at 1e-2..3e-2
             # here); they are bounded in absolute terms and through the global cosine below
-            assert (mine - g64[k]).abs().max().item() < 2e-2 * gmax, k
+            assert (mine - g64[k]).abs().max().item() < (2e-2 if math == '3xtf32' else 0.2) * gmax, k
             continue
         errs[k] = e_mine / max(1e-4, 8 * e_ref, 8 * worst_ref) if math == '3xtf32' else e_mine / 0.35
     assert not report(errs, 1.0), report(errs, 1.0)
