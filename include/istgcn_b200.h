@@ -118,18 +118,22 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const fl
 /* tcgen05 / TMA / TMEM engine of the same graph convolution (forward form, or input-gradient
  * form when the lists are grouped by (k, source joint) and the weight is Wc):
  *   out[(f,w)][n] = sum_{k,ci} (sum_v A[k][v][w] in'[(f,v)][ci]) * w_rows[k*Cout + n][ci]
- *                   + bias_vc[w][n] + add_rows[(f,w)][n]
+ *                   + sum_k colsum[k][w] * bias_k[k][n] + add_rows[(f,w)][n]
  * with in' = in, or in' = bn_p*((in - bn_m1) - bn_c*(in2 - bn_mu)) when bn_p != NULL.
  * w_rows is [K*Cout][CinPad] (CinPad = Cin rounded up to 32, padding columns zero), 16-byte
  * aligned; lptr[K*V+1] / lsrc / lid group the non-zeros by (k, destination joint).
  * in_out (may be NULL) receives a copy of in' ([rows][Cin]): the input-gradient call uses it to
- * materialise dz for the two kernels below.  map_side selects where the temporal stride of the
+ * materialise dz for the two kernels below.  bias_k [K][Cout] is the conv bias and colsum [K][V]
+ * the column sums of A[k] (the bias passes through the aggregation; both NULL: no bias).
+ * Whole output tiles leave through TMA tile stores; when add_rows == out the kernel accumulates
+ * in place with TMA reduce-add.  map_side selects where the temporal stride of the
  * residual branch applies (0: none, 1: input rows are read from frame n*t_in + to*t_stride,
  * 2: output / add_rows rows are written there).  TF32 inputs, fp32 accumulation in TMEM.     */
 int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const float* bn_m1,
                   const float* bn_c, const float* bn_mu, const float* w_rows, const float* vals,
                   const int* lptr, const int* lsrc, const int* lid, int nnz,
-                  const float* bias_vc, const float* add_rows, float* out, float* in_out,
+                  const float* bias_k, const float* colsum, const float* add_rows, float* out,
+                  float* in_out,
                   double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
                   int CinPad, int Cout, int t_in, int t_out, int t_stride, int map_side,
                   istgcn_stream_t s);

@@ -185,6 +185,13 @@ __device__ __forceinline__ float group_sum_g(float v) {
     return v;
 }
 
+__device__ __forceinline__ double group_sum_g(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;
+}
+
 // Counter-based dropout keep decision: one 64-bit mix per element, identical in the forward
 // and backward kernels (nn.Dropout's Philox stream cannot be reproduced from a custom kernel;
 // parity tests read the mask back through istgcn_dropout_mask).

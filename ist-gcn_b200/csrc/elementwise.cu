@@ -42,31 +42,31 @@ int num_sms() {
 __global__ void data_bn_stats_kernel(const float* __restrict__ x, double* __restrict__ sum,
                                      double* __restrict__ sumsq, int C, int T, int V, int M,
                                      int t_per_cta) {
-    extern __shared__ float sh[];            // [2][V]
+    extern __shared__ double shd[];           // [2][V]
     const int VM = V * M;
     const int groups = blockDim.x / VM;
     const int nc = blockIdx.x;               // n*C + c
     const int c = nc % C;
     const int t0 = blockIdx.y * t_per_cta;
     const int t1 = min(T, t0 + t_per_cta);
-    for (int i = threadIdx.x; i < 2 * V; i += blockDim.x) sh[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * V; i += blockDim.x) shd[i] = 0.0;
     __syncthreads();
     const int grp = threadIdx.x / VM, vm = threadIdx.x % VM;
     if (grp < groups) {
         const float* slab = x + (size_t)nc * T * VM;
-        float s = 0.f, q = 0.f;
+        double s = 0.0, q = 0.0;
         for (int t = t0 + grp; t < t1; t += groups) {
             const float v = slab[(size_t)t * VM + vm];
             s += v;
-            q += v * v;
+            q += (double)v * v;
         }
-        atomicAdd(&sh[vm / M], s);
-        atomicAdd(&sh[V + vm / M], q);
+        atomicAdd(&shd[vm / M], s);
+        atomicAdd(&shd[V + vm / M], q);
     }
     __syncthreads();
     for (int v = threadIdx.x; v < V; v += blockDim.x) {
-        atomicAdd(&sum[v * C + c], (double)sh[v]);
-        atomicAdd(&sumsq[v * C + c], (double)sh[V + v]);
+        atomicAdd(&sum[v * C + c], shd[v]);
+        atomicAdd(&sumsq[v * C + c], shd[V + v]);
     }
 }
 
@@ -376,7 +376,7 @@ ISTGCN_API int istgcn_data_bn_stats(const float* x, double* sum, double* sumsq, 
     const int slices = T >= 64 ? 4 : 1;
     const int tpc = (T + slices - 1) / slices;
     dim3 grid(N * C, slices);
-    data_bn_stats_kernel<<<grid, 256, 2 * V * sizeof(float), (cudaStream_t)s>>>(x, sum, sumsq, C, T,
+    data_bn_stats_kernel<<<grid, 256, 2 * V * sizeof(double), (cudaStream_t)s>>>(x, sum, sumsq, C, T,
                                                                                 V, M, tpc);
     return finish_launch("data_bn_stats");
 }

@@ -88,9 +88,11 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
     float* xs = smem;                          // [128][32]
     float* As = xs + kTileRows * 32;           // [128][36]
     float* Bs = As + kTileRows * kLdA;         // [32][LDB]
-    float* s_sum = Bs + 32 * LDB;              // [NCOLS]
-    float* s_sq = s_sum + NCOLS;               // [NCOLS]
-    float* s_val = s_sq + NCOLS;               // [nnz]
+    // BatchNorm partial sums in double: sum(x^2) - sum(x)^2/n cancels badly for channels whose
+    // mean dwarfs their spread, and fp32 partials made the variance order-dependent at 1e-4
+    double* s_sum = reinterpret_cast<double*>(Bs + 32 * LDB);   // [NCOLS]
+    double* s_sq = s_sum + NCOLS;                                // [NCOLS]
+    float* s_val = reinterpret_cast<float*>(s_sq + NCOLS);       // [nnz]
     int* s_src = reinterpret_cast<int*>(s_val + kMaxNnz);
     int* s_ptr = s_src + kMaxNnz;              // [K*V+1]
 
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
     }
     for (int i = tid; i <= K * V; i += kThreads) s_ptr[i] = p.dst_ptr[i];
     for (int i = tid; i < kTileRows * kLdA; i += kThreads) As[i] = 0.f;
-    for (int i = tid; i < 2 * NCOLS; i += kThreads) s_sum[i] = 0.f;
+    for (int i = tid; i < 2 * NCOLS; i += kThreads) s_sum[i] = 0.0;
     __syncthreads();
 
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int cl = warp_n * (NCOLS / 2) + nt * 8 + 2 * t;     // local column of c0
-            float cs0 = 0.f, cs1 = 0.f, cq0 = 0.f, cq1 = 0.f;
+            double cs0 = 0.0, cs1 = 0.0, cq0 = 0.0, cq1 = 0.0;
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
                         const float v1 = acc[mt][nt][2 * h + 1] + b.y;
                         *reinterpret_cast<float2*>(p.z + (row0 + r) * Cout + n0 + cl) =
                             make_float2(v0, v1);
-                        cs0 += v0; cs1 += v1; cq0 += v0 * v0; cq1 += v1 * v1;
+                        cs0 += v0; cs1 += v1; cq0 += (double)v0 * v0; cq1 += (double)v1 * v1;
                     }
                 }
             }
@@ -176,15 +178,15 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
     if (p.stat_sum) {
         __syncthreads();
         for (int c = tid; c < NCOLS; c += kThreads) {
-            atomicAdd(&p.stat_sum[n0 + c], (double)s_sum[c]);
-            atomicAdd(&p.stat_sumsq[n0 + c], (double)s_sq[c]);
+            atomicAdd(&p.stat_sum[n0 + c], s_sum[c]);
+            atomicAdd(&p.stat_sumsq[n0 + c], s_sq[c]);
         }
     }
 }
 
 template <int NCOLS>
 static size_t gcn_fwd_smem() {
-    return sizeof(float) * (kTileRows * 32 + kTileRows * kLdA + 32 * (NCOLS + 8) + 2 * NCOLS +
+    return sizeof(float) * (kTileRows * 32 + kTileRows * kLdA + 32 * (NCOLS + 8) + 4 * NCOLS +
                             kMaxNnz) +
            sizeof(int) * (kMaxNnz + kMaxKV + 4);
 }

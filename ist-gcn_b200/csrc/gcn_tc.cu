@@ -25,11 +25,31 @@
 namespace istgcn {
 namespace tc {
 
+#ifndef ISTGCN_TC_PROF
+#define ISTGCN_TC_PROF 0      // 1: per-role clock64 accounting of CTA 0 (tools/dbg_tc_time.py)
+#endif
+#if ISTGCN_TC_PROF
+__device__ unsigned long long g_prof[32];
+#define PROF_DECL long long prof[32] = {0}
+#define PROF_T0() long long _t0 = clock64()
+#define PROF_ADD(i) do { long long _t1 = clock64(); if (blockIdx.x == 0 && blockIdx.y == 0) prof[i] += _t1 - _t0; _t0 = _t1; } while (0)
+#else
+#define PROF_T0()
+#define PROF_ADD(i)
+#define PROF_DECL
+#endif
+
 constexpr int kThreadsTC = 576;     // 18 warps, see the role table above
 constexpr int kAggThreads = 256;    // warps 8-15
-constexpr int kNA = 4;            // A-operand ring (16 KB atoms)
-constexpr int kNB = 3;            // weight ring
-constexpr int kNX = 3;            // input-slice ring
+// Ring geometry per output-tile width (smem budget 227 KB).  The aggregated operand ring is made
+// of NH half-slots of two atoms each; the aggregators hand a whole 32-channel slice (all K
+// partitions = up to two half-slots) to the MMA issuer with ONE barrier round trip, because a
+// round trip costs ~600 cycles and used to dominate the slice time when paid per atom.  The
+// weight ring must cover the TMA round trip (~1.5 us) or the MMA issuer starves on b_full.
+template <int NCOLS> struct Rings { static constexpr int NH = 3, NB = 2, NX = 2; };
+template <> struct Rings<64> { static constexpr int NH = 3, NB = 6, NX = 3; };
+template <> struct Rings<128> { static constexpr int NH = 3, NB = 4, NX = 2; };
+constexpr int kNC = 4;            // slice-ready barriers (>= slices in flight)
 
 struct BnBackTC {
     const float *p, *m1, *cc, *mu;
@@ -41,44 +61,54 @@ struct GcnTcParams {
     BnBackTC bn;
     const float* vals;
     const int *lptr, *lsrc, *lid; // lists grouped by (k, destination joint)
-    const float* bias_vc;         // [V][Cout] added per (joint, channel)   (forward) or NULL
+    const float* bias_k;          // [K][Cout] conv bias and colsum[K][V] = column sums of A_eff[k]:
+    const float* colsum;          //   bias term = sum_k colsum[k][w] * bias_k[k][n]  (forward) or NULL
     const float* add_rows;        // [rows][Cout] added per row             (backward) or NULL
     float* out;                   // [rows][Cout]
     float* in_out;                // optional copy of the (transformed) input, [rows][Cin]
     double *stat_sum, *stat_sumsq;
     int frames, V, K, Cin, CinPad, Cout, nnz, tiles;
     FrameMap in_map, out_map;     // temporal stride of the residual branch (t_out == 0: none)
+    int tma_out;                  // 0: direct stores, 1: TMA tile store, 2: TMA reduce-add (add_rows == out)
 };
 
 template <int NCOLS>
 struct SmemLayout {
+    static constexpr int kNH = Rings<NCOLS>::NH, kNA = 2 * kNH, kNB = Rings<NCOLS>::NB;
     static constexpr int kBAtomBytes = NCOLS * 128;
     static constexpr int a_off = 0;
     static constexpr int b_off = a_off + kNA * kAtomBytes;
+    static constexpr int kNX = Rings<NCOLS>::NX;
     static constexpr int x_off = b_off + kNB * kBAtomBytes;
-    static constexpr int list_off = x_off + kNX * kAtomRows * 32 * 4;            // vals, src, ptr
-    static constexpr int stat_off = list_off + kMaxNnz * 8 + (kMaxKV + 4) * 4;   // 2 * NCOLS floats
-    static constexpr int bar_off = stat_off + 2 * NCOLS * 4;
-    static constexpr int kNumBars = 2 * kNA + 2 * kNB + 2 * kNX + 4;
+    static constexpr int stage_off = x_off + kNX * kAtomRows * 32 * 4;           // 4 x [32 rows][128 B]
+    static constexpr int list_off = stage_off + 4 * 4096;                        // vals, src, ptr
+    static constexpr int bias_off = list_off + kMaxNnz * 8 + (kMaxKV + 4) * 4;   // [4][NCOLS] floats
+    static constexpr int stat_off = bias_off + 4 * NCOLS * 4;                    // 2 * NCOLS doubles
+    static constexpr int bar_off = stat_off + 2 * NCOLS * 8;
+    static_assert(bar_off + 512 <= 232448, "shared-memory budget exceeded");
+    static constexpr int kNumBars = kNC + kNH + 2 * kNB + 2 * kNX + 4;
     static constexpr int total = bar_off + kNumBars * 8 + 16;
 };
 
 template <int NCOLS>
 __global__ void __launch_bounds__(kThreadsTC, 1)
-gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
+gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap omap,
+              const __grid_constant__ CUtensorMap omap_last, GcnTcParams p) {
     using L = SmemLayout<NCOLS>;
+    constexpr int kNA = L::kNA, kNH = L::kNH, kNB = L::kNB, kNX = L::kNX;
     extern __shared__ __align__(1024) uint8_t smem[];
     float* As = reinterpret_cast<float*>(smem + L::a_off);
     uint8_t* Bs = smem + L::b_off;
     float* Xs = reinterpret_cast<float*>(smem + L::x_off);
     int2* s_ent = reinterpret_cast<int2*>(smem + L::list_off);     // {source row offset, value}
     int* s_ptr = reinterpret_cast<int*>(s_ent + kMaxNnz);
-    float* s_sum = reinterpret_cast<float*>(smem + L::stat_off);
-    float* s_sq = s_sum + NCOLS;
+    float* s_bias = reinterpret_cast<float*>(smem + L::bias_off);
+    double* s_sum = reinterpret_cast<double*>(smem + L::stat_off);   // double: see gcn.cu
+    double* s_sq = s_sum + NCOLS;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off);
     uint64_t* a_full = bars;
-    uint64_t* a_empty = a_full + kNA;
-    uint64_t* b_full = a_empty + kNA;
+    uint64_t* a_empty = a_full + kNC;
+    uint64_t* b_full = a_empty + kNH;
     uint64_t* b_empty = b_full + kNB;
     uint64_t* x_full = b_empty + kNB;
     uint64_t* x_empty = x_full + kNX;
@@ -90,6 +120,7 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
     const int V = p.V, K = p.K, Cin = p.Cin, Cout = p.Cout;
     const int F = (kAtomRows / V) > 8 ? 8 : (kAtomRows / V);
     const int nchunk = p.CinPad / 32;
+    const int nh = (K + 1) >> 1;                    // half-slots per slice
     const int n0 = blockIdx.y * NCOLS;
 
     // ---- one-time setup
@@ -97,15 +128,24 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
         s_ent[i] = make_int2(p.lsrc[i] * 32, __float_as_int(p.vals[p.lid[i]]));
     for (int i = tid; i <= K * V; i += kThreadsTC) s_ptr[i] = p.lptr[i];
     for (int i = tid; i < kNA * kAtomBytes / 4; i += kThreadsTC) As[i] = 0.f;
-    for (int i = tid; i < 2 * NCOLS; i += kThreadsTC) s_sum[i] = 0.f;
+    for (int i = tid; i < 2 * NCOLS; i += kThreadsTC) s_sum[i] = 0.0;
+    if (p.bias_k)
+        for (int i = tid; i < K * NCOLS; i += kThreadsTC) {
+            const int k = i / NCOLS, c = i % NCOLS;
+            s_bias[i] = n0 + c < Cout ? p.bias_k[(size_t)k * Cout + n0 + c] : 0.f;
+        }
     if (tid == 0) {
-        for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], kAggThreads / 32); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < kNC; ++i) mbar_init(&a_full[i], kAggThreads / 32);
+        for (int i = 0; i < kNH; ++i) mbar_init(&a_empty[i], 1);
         for (int i = 0; i < kNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < kNX; ++i) { mbar_init(&x_full[i], 4); mbar_init(&x_empty[i], kAggThreads / 32); }
         for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&wmap);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&wmap);
+        if (p.tma_out) { tma_prefetch_desc(&omap); tma_prefetch_desc(&omap_last); }
+    }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * NCOLS);
     fence_proxy_async();                       // zero-filled A atoms visible to the tensor core
     tc_fence_before();
@@ -117,33 +157,48 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
         // =========================== TMA producer (weights)
         if (lane == 0) {
             uint32_t it = 0;
+            PROF_DECL; PROF_T0();
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
                 for (int ch = 0; ch < nchunk; ++ch)
                     for (int k = 0; k < K; ++k, ++it) {
                         const int sb = it % kNB;
+                        PROF_ADD(1);
                         mbar_wait(&b_empty[sb], ((it / kNB) & 1) ^ 1);
+                        PROF_ADD(0);
                         mbar_arrive_expect_tx(&b_full[sb], L::kBAtomBytes);
                         // weight matrix rows = k*Cout + n, cols = ci
                         tma_load_2d(Bs + sb * L::kBAtomBytes, &wmap, &b_full[sb], ch * 32,
                                     k * Cout + n0);
                     }
+            PROF_ADD(1);
+#if ISTGCN_TC_PROF
+            if (blockIdx.x == 0 && blockIdx.y == 0) { g_prof[0] += prof[0]; g_prof[1] += prof[1]; }
+#endif
         }
     } else if (warp == 1) {
         // =========================== MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(128, NCOLS, false, false);
-            uint32_t it = 0, tcount = 0;
+            uint32_t it = 0, tcount = 0, cc = 0;
+            PROF_DECL; PROF_T0();
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
                 const int buf = tcount & 1;
+                PROF_ADD(5);
                 mbar_wait(&t_empty[buf], ((tcount >> 1) & 1) ^ 1);
+                PROF_ADD(2);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * NCOLS;
                 uint32_t first = 1;
-                for (int ch = 0; ch < nchunk; ++ch)
+                for (int ch = 0; ch < nchunk; ++ch, ++cc) {
+                    PROF_ADD(5);
+                    mbar_wait(&a_full[cc % kNC], (cc / kNC) & 1);
+                    PROF_ADD(3);
                     for (int k = 0; k < K; ++k, ++it) {
-                        const int sa = it % kNA, sb = it % kNB;
-                        mbar_wait(&a_full[sa], (it / kNA) & 1);
+                        const uint32_t hidx = cc * nh + (k >> 1);
+                        const int sa = (hidx % kNH) * 2 + (k & 1), sb = it % kNB;
+                        PROF_ADD(5);
                         mbar_wait(&b_full[sb], (it / kNB) & 1);
+                        PROF_ADD(4);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(As) + sa * kAtomBytes;
                         const uint32_t b_addr = smem_u32(Bs) + sb * L::kBAtomBytes;
@@ -154,41 +209,73 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                                         first ? 0u : 1u);
                             first = 0;
                         }
-                        tc_commit(&a_empty[sa]);
                         tc_commit(&b_empty[sb]);
+                        if ((k & 1) || k == K - 1) tc_commit(&a_empty[hidx % kNH]);
                     }
+                }
                 tc_commit(&t_full[buf]);
             }
+            PROF_ADD(5);
+#if ISTGCN_TC_PROF
+            if (blockIdx.x == 0 && blockIdx.y == 0) for (int i = 2; i <= 5; ++i) g_prof[i] += prof[i];
+#endif
         }
     } else if (warp >= 4 && warp < 8) {
         // =========================== epilogue: TMEM -> registers -> global
         const int ew = warp - 4;                        // == warp % 4: TMEM lanes 32*ew .. +31
         const int r = ew * 32 + lane;
+        const int w = r % V;
+        uint8_t* stage = smem + L::stage_off + ew * 4096;      // [32 rows][128 B], SWIZZLE_128B
+        const CUtensorMap* om = ew == 3 ? &omap_last : &omap;   // warp 3 owns F*V - 96 rows
+        float cs[4] = {0.f, 0.f, 0.f, 0.f};                    // colsum(A_eff[k])[w] of this row
+        if (p.bias_k && r < F * V)
+            for (int k = 0; k < K; ++k) cs[k] = p.colsum[k * V + w];
         uint32_t tcount = 0;
+        PROF_DECL; PROF_T0();
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
             const int buf = tcount & 1;
             const int f0 = tile * F;
             const int valid = min(F, p.frames - f0) * V;
             const long long row0 = (long long)f0 * V;
             const bool ok = r < valid;
-            const int w = r % V;
+            const bool tma = p.tma_out && valid == F * V;       // whole tile: coalesced TMA store
+            PROF_ADD(8);
             mbar_wait(&t_full[buf], (tcount >> 1) & 1);
+            PROF_ADD(7);
             tc_fence_after();
             for (int c0 = 0; c0 < NCOLS; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * NCOLS + c0, v);
                 const int cg = n0 + c0;                  // global output column of v[0]
-                if (ok) {
-                    if (p.bias_vc) {
-                        const float* b = p.bias_vc + (size_t)w * Cout + cg;
+                if (p.bias_k) {
+                    for (int k = 0; k < K; ++k) {
+                        const float ck = cs[k];
+                        const float* b = s_bias + k * NCOLS + c0;    // warp-uniform: broadcast reads
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
-                            if (cg + j < Cout) {
-                                const float4 bv = ld4(b + j);
-                                v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
-                            }
+                            const float4 bv = *reinterpret_cast<const float4*>(b + j);
+                            v[j] = fmaf(ck, bv.x, v[j]); v[j + 1] = fmaf(ck, bv.y, v[j + 1]);
+                            v[j + 2] = fmaf(ck, bv.z, v[j + 2]); v[j + 3] = fmaf(ck, bv.w, v[j + 3]);
                         }
                     }
+                }
+                if (tma) {
+                    // registers -> swizzled staging tile -> one TMA store (or reduce-add) of
+                    // 32 rows x 128 B: full-line writes instead of 32 partial lines per instruction
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+                            make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && cg < Cout) {
+                        if (p.tma_out == 2) tma_reduce_add_2d(stage, om, cg, (int)(row0 + ew * 32));
+                        else tma_store_2d(stage, om, cg, (int)(row0 + ew * 32));
+                        bulk_commit();
+                    }
+                } else if (ok) {
                     const long long orow = map_row(p.out_map, row0 + r, V);
                     float* o = p.out + orow * Cout + cg;
                     if ((Cout & 3) == 0) {
@@ -219,29 +306,37 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                         v[j] = ok ? v[j] : 0.f;
                         q[j] = v[j] * v[j];
                     }
-                    const float cs = warp_column_sums(v, lane);
+                    const float csum = warp_column_sums(v, lane);
                     const float cq = warp_column_sums(q, lane);
-                    atomicAdd(&s_sum[c0 + lane], cs);
-                    atomicAdd(&s_sq[c0 + lane], cq);
+                    atomicAdd(&s_sum[c0 + lane], (double)csum);
+                    atomicAdd(&s_sq[c0 + lane], (double)cq);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
+        if (lane == 0) bulk_wait_all();
+        PROF_ADD(8);
+#if ISTGCN_TC_PROF
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 128) { g_prof[7] += prof[7]; g_prof[8] += prof[8]; }
+#endif
     } else if (warp < 4 || warp >= 16) {
         // =========================== loaders: input slice -> Xs[xb][row][32]
         // 128 threads, 8 independent 16-byte loads each per slice (all issued before the first
         // use) so that ~16 KB per SM are in flight
         const int lt = warp < 4 ? tid - 64 : tid - 16 * 32 + 64;
         uint32_t it = 0;
+        PROF_DECL; PROF_T0();
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int f0 = tile * F;
             const int valid = min(F, p.frames - f0) * V;
             const long long row0 = (long long)f0 * V;
             for (int ch = 0; ch < nchunk; ++ch, ++it) {
                 const int xb = it % kNX;
+                PROF_ADD(10);
                 mbar_wait(&x_empty[xb], ((it / kNX) & 1) ^ 1);
+                PROF_ADD(9);
                 float* xs = Xs + xb * kAtomRows * 32;
                 const int ci0 = ch * 32;
                 if ((Cin & 3) == 0) {
@@ -293,6 +388,10 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
                 if (lane == 0) mbar_arrive(&x_full[xb]);
             }
         }
+        PROF_ADD(10);
+#if ISTGCN_TC_PROF
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 64) { g_prof[9] += prof[9]; g_prof[10] += prof[10]; }
+#endif
     } else {
         // =========================== aggregators: Xs -> A atoms (SWIZZLE_128B, K-major)
         // 8 warps x 4 lane groups = 32 destination slots: group q of warp aw owns joint
@@ -304,28 +403,39 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
         const int w = aw + 8 * q;
         const bool active = w < V;
         const int fstride = V * 32;
-        uint32_t it = 0, xit = 0;
+        uint32_t xit = 0;
+        PROF_DECL; PROF_T0();
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             for (int ch = 0; ch < nchunk; ++ch, ++xit) {
                 const int xb = xit % kNX;
+                PROF_ADD(14);
                 mbar_wait(&x_full[xb], (xit / kNX) & 1);
+                PROF_ADD(12);
                 const float* xs = Xs + xb * kAtomRows * 32 + c4;
-                for (int k = 0; k < K; ++k, ++it) {
-                    const int sa = it % kNA;
-                    mbar_wait(&a_empty[sa], ((it / kNA) & 1) ^ 1);
-                    float* A = As + sa * (kAtomBytes / 4);
+                for (int k = 0; k < K; ++k) {
+                    const uint32_t hidx = xit * nh + (k >> 1);
+                    PROF_ADD(14);
+                    if (!(k & 1)) mbar_wait(&a_empty[hidx % kNH], ((hidx / kNH) & 1) ^ 1);
+                    PROF_ADD(13);
+                    float* A = As + ((hidx % kNH) * 2 + (k & 1)) * (kAtomBytes / 4);
                     if (active) {
                         const int beg = s_ptr[k * V + w], end = s_ptr[k * V + w + 1];
                         aggregate_joint_any(F, A, xs, s_ent, beg, end, fstride, V, w, c4);
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&a_full[sa]);
                 }
+                PROF_ADD(14);
+                fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&x_empty[xb]);
+                if (lane == 0) {
+                    mbar_arrive(&a_full[xit % kNC]);
+                    mbar_arrive(&x_empty[xb]);
+                }
+                PROF_ADD(15);
             }
         }
+#if ISTGCN_TC_PROF
+        if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 256) for (int i = 12; i <= 15; ++i) g_prof[i] += prof[i];
+#endif
     }
 
     // ---- teardown
@@ -334,8 +444,8 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, GcnTcParams p) {
     if (p.stat_sum) {
         for (int c = tid; c < NCOLS; c += kThreadsTC) {
             if (n0 + c < Cout) {
-                atomicAdd(&p.stat_sum[n0 + c], (double)s_sum[c]);
-                atomicAdd(&p.stat_sumsq[n0 + c], (double)s_sq[c]);
+                atomicAdd(&p.stat_sum[n0 + c], s_sum[c]);
+                atomicAdd(&p.stat_sumsq[n0 + c], s_sq[c]);
             }
         }
     }
@@ -381,7 +491,8 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
 }
 
 template <int NCOLS>
-static int launch_tc(const CUtensorMap& map, const GcnTcParams& p, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& map, const CUtensorMap& omap, const CUtensorMap& omap_last,
+                     const GcnTcParams& p, cudaStream_t s) {
     using L = SmemLayout<NCOLS>;
     auto kern = gcn_tc_kernel<NCOLS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
@@ -389,7 +500,7 @@ static int launch_tc(const CUtensorMap& map, const GcnTcParams& p, cudaStream_t 
     int nx = num_sms() / ny;
     if (nx < 1) nx = 1;
     if (nx > p.tiles) nx = p.tiles;
-    kern<<<dim3(nx, ny), kThreadsTC, L::total, s>>>(map, p);
+    kern<<<dim3(nx, ny), kThreadsTC, L::total, s>>>(map, omap, omap_last, p);
     return finish_launch("gcn_tc");
 }
 
@@ -398,13 +509,24 @@ static int launch_tc(const CUtensorMap& map, const GcnTcParams& p, cudaStream_t 
 
 using namespace istgcn;
 
+#if ISTGCN_TC_PROF
+extern "C" int istgcn_debug_prof(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tc::g_prof, sizeof(unsigned long long) * 32);
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(tc::g_prof, z, sizeof(z));
+    return 0;
+}
+#endif
+
 // Tensor-core graph convolution, forward or input-gradient form (see the file header).
 //   w_rows[K*Cout][CinPad]: weight with rows k*Cout + n and the 32-padded input channels as
 //   columns (forward: the conv weight (K*Cout, Cin) itself, zero-padded when Cin < 32).
 ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const float* bn_m1,
                              const float* bn_c, const float* bn_mu, const float* w_rows,
                              const float* vals, const int* lptr, const int* lsrc, const int* lid,
-                             int nnz, const float* bias_vc, const float* add_rows, float* out,
+                             int nnz, const float* bias_k, const float* colsum, const float* add_rows,
+                             float* out,
                              float* in_out, double* stat_sum, double* stat_sumsq, int frames, int V,
                              int K, int Cin, int CinPad, int Cout, int t_in, int t_out, int t_stride,
                              int map_side, istgcn_stream_t s) {
@@ -422,9 +544,11 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
     ISTGCN_REQUIRE((reinterpret_cast<uintptr_t>(w_rows) & 15) == 0, ISTGCN_E_ARG,
                    "gcn_tc: weight pointer must be 16-byte aligned");
     if (frames == 0) return 0;
-    tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_vc, add_rows,
-                      out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout, nnz, 0,
-                      {0, 0, 1}, {0, 0, 1}};
+    ISTGCN_REQUIRE((bias_k == nullptr) == (colsum == nullptr), ISTGCN_E_ARG,
+                   "gcn_tc: pass bias_k and colsum together");
+    tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_k, colsum,
+                      add_rows, out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout,
+                      nnz, 0, {0, 0, 1}, {0, 0, 1}, 0};
     if (map_side == 1) p.in_map = {t_in, t_out, t_stride};
     if (map_side == 2) p.out_map = {t_in, t_out, t_stride};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
@@ -432,8 +556,18 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
     CUtensorMap map;
     if (int e = tc::encode_tile_map(&map, w_rows, (long long)K * Cout, CinPad, ncols)) return e;
+    // whole-tile outputs leave through TMA (plain store, or reduce-add when the kernel accumulates
+    // in place); strided output maps, partial tiles and odd widths use the direct path
+    CUtensorMap omap = map, omap_last = map;
+    const int last_rows = F * V - 96;
+    if (Cout % 32 == 0 && map_side != 2 && last_rows >= 1 && (add_rows == nullptr || add_rows == out) &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        if (int e = tc::encode_tile_map(&omap, out, (long long)frames * V, Cout, 32)) return e;
+        if (int e = tc::encode_tile_map(&omap_last, out, (long long)frames * V, Cout, last_rows)) return e;
+        p.tma_out = add_rows ? 2 : 1;
+    }
     cudaStream_t st = (cudaStream_t)s;
-    if (ncols == 256) return tc::launch_tc<256>(map, p, st);
-    if (ncols == 128) return tc::launch_tc<128>(map, p, st);
-    return tc::launch_tc<64>(map, p, st);
+    if (ncols == 256) return tc::launch_tc<256>(map, omap, omap_last, p, st);
+    if (ncols == 128) return tc::launch_tc<128>(map, omap, omap_last, p, st);
+    return tc::launch_tc<64>(map, omap, omap_last, p, st);
 }

@@ -25,6 +25,20 @@ constexpr int kTaps = 15, kHalf = 7;
 __host__ __device__ inline int ld_g(int bp) { return bp + 4; }                 // g-indexed rows
 __host__ __device__ inline int ld_t(int bp) { return bp == 8 ? 8 : 24; }       // t-indexed rows
 
+// Register prefetch of one [128 rows x 32 channels] slice of a row-major [rows][C] matrix (4
+// float4 per thread).  The slice for step i+1 is requested before the math of step i starts, so
+// the DRAM latency hides behind the tensor-core work instead of sitting in front of it.
+__device__ __forceinline__ void prefetch_slice(float4 (&v)[4], const float* __restrict__ base,
+                                               long long row0, long long rows, int C, int c0,
+                                               int tid) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int i = tid + u * kThreads;
+        const long long r = row0 + (i >> 3);
+        v[u] = r < rows ? ld4(base + r * C + c0 + (i & 7) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 // ----------------------------------------------------------------------------------- down
 struct TcnDownParams {
     const float *z, *mean1, *scale1, *beta1, *Wd, *bd;
@@ -45,6 +59,8 @@ __global__ void __launch_bounds__(kThreads) tcn_down_kernel(TcnDownParams p) {
     const int C = p.C;
     for (int i = tid; i < C * BP; i += kThreads) Ws[(i / BP) * LDW + (i % BP)] = p.Wd[i];
     const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
+    float4 zr[4];
+    if (blockIdx.x < tiles) prefetch_slice(zr, p.z, (long long)blockIdx.x * kTileRows, p.rows, C, 0, tid);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long row0 = tile * kTileRows;
         const int valid = (int)min((long long)kTileRows, p.rows - row0);
@@ -52,23 +68,27 @@ __global__ void __launch_bounds__(kThreads) tcn_down_kernel(TcnDownParams p) {
         zero_acc<1, NT>(acc);
         for (int c0 = 0; c0 < C; c0 += 32) {
             __syncthreads();
-            stage4<kTileRows * 8 / kThreads>(
-                tid, 0,
-                [&](int i) {
-                    const int r = i >> 3, c4 = (i & 7) * 4;
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < valid) {
-                        const float4 zv = ld4(p.z + (row0 + r) * C + c0 + c4);
-                        const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
-                                     be = ld4(p.beta1 + c0 + c4);
-                        v.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
-                        v.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
-                        v.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
-                        v.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
-                    }
-                    return v;
-                },
-                [&](int i, const float4& v) { st4(As + (i >> 3) * 36 + (i & 7) * 4, v); });
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = tid + u * kThreads;
+                const int r = i >> 3, c4 = (i & 7) * 4;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r < valid) {
+                    const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
+                                 be = ld4(p.beta1 + c0 + c4);
+                    v.x = fmaxf(bn_apply(zr[u].x, mu.x, sc.x, be.x), 0.f);
+                    v.y = fmaxf(bn_apply(zr[u].y, mu.y, sc.y, be.y), 0.f);
+                    v.z = fmaxf(bn_apply(zr[u].z, mu.z, sc.z, be.z), 0.f);
+                    v.w = fmaxf(bn_apply(zr[u].w, mu.w, sc.w, be.w), 0.f);
+                }
+                st4(As + r * 36 + c4, v);
+            }
+            {   // next slice: same tile, or the first slice of this CTA's next tile
+                const bool same = c0 + 32 < C;
+                const long long nrow0 = same ? row0 : (tile + gridDim.x) * kTileRows;
+                if (same || tile + gridDim.x < tiles)
+                    prefetch_slice(zr, p.z, nrow0, p.rows, C, same ? c0 + 32 : 0, tid);
+            }
             __syncthreads();
             warp_mma<1, NT, false, false, PRECISE>(acc, As + warp * 16 * 36, 36, Ws + c0 * LDW, LDW,
                                                    32, lane);
@@ -109,14 +129,15 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
     float* h2s = hs + TI * V * LDH;             // [256][LDH]
     float* Wts = h2s + kUpRows * LDH;           // [15*BP][LDW]
     float* Wus = Wts + kTaps * BP * LDW;        // [BP][LDU]
-    float* s_sum = Wus + BP * LDU;              // [C]
-    float* s_sq = s_sum + C;                    // [C]
+    // BatchNorm partial sums in double (see gcn.cu: the one-pass variance cancels in fp32)
+    double* s_sum = reinterpret_cast<double*>(Wus + BP * LDU);   // [C]
+    double* s_sq = s_sum + C;                                    // [C]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
     for (int i = tid; i < kTaps * BP * BP; i += kThreads) Wts[(i / BP) * LDW + (i % BP)] = p.Weff[i];
     for (int i = tid; i < BP * C; i += kThreads) Wus[(i / C) * LDU + (i % C)] = p.Wu[i];
-    for (int i = tid; i < 2 * C; i += kThreads) s_sum[i] = 0.f;
+    for (int i = tid; i < 2 * C; i += kThreads) s_sum[i] = 0.0;
 
     const int total = p.NM * p.tiles_per_sample;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -203,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
                 }
                 const int c = nt * 8 + 2 * t;
                 const float b0 = p.bu[c], b1 = p.bu[c + 1];
-                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+                double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = mt * 16 + g + 8 * h;
@@ -211,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
                         const float v0 = acc[2 * h] + b0, v1 = acc[2 * h + 1] + b1;
                         *reinterpret_cast<float2*>(
                             p.u + (((size_t)n * p.Tout + to0) * V + r) * C + c) = make_float2(v0, v1);
-                        s0 += v0; s1 += v1; q0 += v0 * v0; q1 += v1 * v1;
+                        s0 += v0; s1 += v1; q0 += (double)v0 * v0; q1 += (double)v1 * v1;
                     }
                 }
                 if (p.stat_sum) {
@@ -228,8 +249,8 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
     if (p.stat_sum) {
         __syncthreads();
         for (int c = tid; c < C; c += kThreads) {
-            atomicAdd(&p.stat_sum[c], (double)s_sum[c]);
-            atomicAdd(&p.stat_sumsq[c], (double)s_sq[c]);
+            atomicAdd(&p.stat_sum[c], s_sum[c]);
+            atomicAdd(&p.stat_sumsq[c], s_sq[c]);
         }
     }
 }
@@ -271,6 +292,11 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
     const uint64_t eseed = effective_seed(p.seed, p.step);
 
     const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
+    float4 gr[4], ur[4];
+    if (blockIdx.x < tiles) {
+        prefetch_slice(gr, p.go, (long long)blockIdx.x * kTileRows, p.rows, C, 0, tid);
+        prefetch_slice(ur, p.u, (long long)blockIdx.x * kTileRows, p.rows, C, 0, tid);
+    }
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long row0 = tile * kTileRows;
         const int valid = (int)min((long long)kTileRows, p.rows - row0);
@@ -288,31 +314,38 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) 
             const int c0 = ch * 32;
             if (c0 < C) {
                 __syncthreads();
-                stage4<kTileRows * 8 / kThreads>(
-                    tid, 0,
-                    [&](int i) {
-                        const int r = i >> 3, c4 = (i & 7) * 4;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r < valid) {
-                            const long long off = (row0 + r) * C + c0 + c4;
-                            const float4 gv = ld4(p.go + off), uv = ld4(p.u + off);
-                            const float4 pv = ld4(p.p2 + c0 + c4), mv = ld4(p.m12 + c0 + c4),
-                                         cv = ld4(p.c2 + c0 + c4), nv = ld4(p.mean2 + c0 + c4);
-                            float gy[4] = {gv.x, gv.y, gv.z, gv.w};
-                            if (p.drop_p > 0.f) {
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    gy[j] = dropout_keep(eseed, (uint64_t)(off + j), p.drop_p)
-                                                ? gy[j] * p.keep_scale : 0.f;
-                            }
-                            v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
-                            v.y = bn_back(gy[1], uv.y, pv.y, mv.y, cv.y, nv.y);
-                            v.z = bn_back(gy[2], uv.z, pv.z, mv.z, cv.z, nv.z);
-                            v.w = bn_back(gy[3], uv.w, pv.w, mv.w, cv.w, nv.w);
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int i = tid + uu * kThreads;
+                    const int r = i >> 3, c4 = (i & 7) * 4;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < valid) {
+                        const long long off = (row0 + r) * C + c0 + c4;
+                        const float4 gv = gr[uu], uv = ur[uu];
+                        const float4 pv = ld4(p.p2 + c0 + c4), mv = ld4(p.m12 + c0 + c4),
+                                     cv = ld4(p.c2 + c0 + c4), nv = ld4(p.mean2 + c0 + c4);
+                        float gy[4] = {gv.x, gv.y, gv.z, gv.w};
+                        if (p.drop_p > 0.f) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                gy[j] = dropout_keep(eseed, (uint64_t)(off + j), p.drop_p)
+                                            ? gy[j] * p.keep_scale : 0.f;
                         }
-                        return v;
-                    },
-                    [&](int i, const float4& v) { st4(DUs + (i >> 3) * 36 + (i & 7) * 4, v); });
+                        v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
+                        v.y = bn_back(gy[1], uv.y, pv.y, mv.y, cv.y, nv.y);
+                        v.z = bn_back(gy[2], uv.z, pv.z, mv.z, cv.z, nv.z);
+                        v.w = bn_back(gy[3], uv.w, pv.w, mv.w, cv.w, nv.w);
+                    }
+                    st4(DUs + r * 36 + c4, v);
+                }
+                {   // request the next slice of go / u before the math of this one
+                    const bool same = c0 + 32 < C;
+                    const long long nrow0 = same ? row0 : (tile + gridDim.x) * kTileRows;
+                    if (same || tile + gridDim.x < tiles) {
+                        prefetch_slice(gr, p.go, nrow0, p.rows, C, same ? c0 + 32 : 0, tid);
+                        prefetch_slice(ur, p.u, nrow0, p.rows, C, same ? c0 + 32 : 0, tid);
+                    }
+                }
                 __syncthreads();
                 // dh2[rows][j] += DU[rows][c0..] * Wu[j][c0..]^T
                 warp_mma<1, NT, false, true, PRECISE>(acc_h, DUs + warp * 16 * 36, 36, Wus + c0, LDWU,
@@ -571,6 +604,8 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_down_kernel(TcnBwdDownParams
     const int wm = warp & 1, wk = warp >> 1;    // m-tile (16 channels) of the chunk, K-quarter
 
     const long long tiles = (p.rows + kTileRows - 1) / kTileRows;
+    float4 zr[4];
+    if (blockIdx.x < tiles) prefetch_slice(zr, p.z, (long long)blockIdx.x * kTileRows, p.rows, C, 0, tid);
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const long long row0 = tile * kTileRows;
         const int valid = (int)min((long long)kTileRows, p.rows - row0);
@@ -586,27 +621,29 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_down_kernel(TcnBwdDownParams
             const int c0 = ch * 32;
             if (c0 < C) {
                 __syncthreads();
-                stage4<kTileRows * 8 / kThreads>(
-                    tid, 0,
-                    [&](int i) {
-                        const int r = i >> 3, c4 = (i & 7) * 4;
-                        return r < valid ? ld4(p.z + (row0 + r) * C + c0 + c4)
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-                    },
-                    [&](int i, const float4& zv) {
-                        const int r = i >> 3, c4 = (i & 7) * 4;
-                        float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (r < valid) {
-                            const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
-                                         be = ld4(p.beta1 + c0 + c4);
-                            av.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
-                            av.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
-                            av.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
-                            av.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
-                        }
-                        st4(Zs + r * 36 + c4, zv);
-                        st4(As + r * LDA + c4, av);
-                    });
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int i = tid + uu * kThreads;
+                    const int r = i >> 3, c4 = (i & 7) * 4;
+                    const float4 zv = r < valid ? zr[uu] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r < valid) {
+                        const float4 mu = ld4(p.mean1 + c0 + c4), sc = ld4(p.scale1 + c0 + c4),
+                                     be = ld4(p.beta1 + c0 + c4);
+                        av.x = fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f);
+                        av.y = fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f);
+                        av.z = fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f);
+                        av.w = fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f);
+                    }
+                    st4(Zs + r * 36 + c4, zv);
+                    st4(As + r * LDA + c4, av);
+                }
+                {
+                    const bool same = c0 + 32 < C;
+                    const long long nrow0 = same ? row0 : (tile + gridDim.x) * kTileRows;
+                    if (same || tile + gridDim.x < tiles)
+                        prefetch_slice(zr, p.z, nrow0, p.rows, C, same ? c0 + 32 : 0, tid);
+                }
                 __syncthreads();
                 // da[rows][c0..c0+32) = dh1[rows][j] * Wd[c][j]^T  (K = bp)
                 float acc[1][4][4];
@@ -734,7 +771,7 @@ ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* mean1, const float* s
         p.tiles_per_sample = (Tout + p.TT - 1) / p.TT;
         const int TI = (p.TT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)TI * V * ld_g(bp) + kUpRows * ld_g(bp) +
-                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 2 * C);
+                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 4 * C);
         const int grid = grid_for((long long)NM * p.tiles_per_sample, 2);
 #define LAUNCH_UP(NT, PC)                                            \
     set_smem(tcn_up_kernel<NT, PC>, smem);                           \

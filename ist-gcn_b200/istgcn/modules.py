@@ -40,8 +40,8 @@ def to_channels_first(x):
 
 def graph_conv_operands(weight, bias, adjs, pattern):
     """Reference-layout conv weight (K*Cout, Cin, 1, 1) + bias and the adjacency stacks
-    [A*imp (, A2*imp2, A3*imp3)] -> (vals[nnz], Wc[K*Cin, Cout], biasterm[V, Cout], W2) where
-    W2[K*Cout, CinPad] is the weight in its own row order with the input channels zero-padded to
+    [A*imp (, A2*imp2, A3*imp3)] -> (vals[nnz], Wc[K*Cin, Cout], biasterm[V, Cout], (W2, bias_k, colsum))
+    where W2[K*Cout, CinPad] is the weight in its own row order with the input channels zero-padded to
     a multiple of 32 (the tcgen05 engine's TMA operand; no gradient flows through it, Wc carries
     the weight gradient).
 
@@ -62,7 +62,11 @@ def graph_conv_operands(weight, bias, adjs, pattern):
     w2 = weight.detach().view(kc, cin)
     if cin % 32:
         w2 = F.pad(w2, (0, 32 - cin % 32))
-    return vals, wc, biasterm, w2
+    if bias is None:
+        tc_ops = (w2, None, None)
+    else:       # the tcgen05 epilogue rebuilds the bias term from its two factors
+        tc_ops = (w2, bias.detach().view(K, cout), a_eff.detach().sum(1).contiguous())
+    return vals, wc, biasterm, tc_ops
 
 
 def bottleneck_tcn_operands(conv_start, tcn_1, tcn_2, tcn_3, conv_end, m_imp):

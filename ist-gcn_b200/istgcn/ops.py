@@ -63,9 +63,11 @@ def _bn_forward_coeffs(training, sum_, sumsq, count, weight, st, C, device):
 def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, Cin, Cout, math):
     """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise."""
     if use_tc():
+        W2, bias_k, colsum = W2        # graph_conv_operands: weight rows + the bias-term factors
+        W2 = W2.contiguous()
         call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src,
-             pat.dst_id, pat.nnz, biasterm, None, z, None, s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout,
-             0, 0, 1, 0)
+             pat.dst_id, pat.nnz, None if bias_k is None else bias_k.contiguous(), colsum, None, z, None,
+             s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout, 0, 0, 1, 0)
     else:
         call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
              s_sum, s_sq, frames, V, K, Cin, Cout, 0, 0, 1, math)
@@ -143,7 +145,7 @@ class STBlock(Function):
         stats = torch.zeros(6, Cout, device=dev, dtype=torch.float64) if training else [None] * 6
 
         z = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
-        _gcn_forward(x, Wc, W2.contiguous(), biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K,
+        _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K,
                      Cin, Cout, math)
         mean1, scale1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w, cfg.bn1,
                                                   Cout, dev)
@@ -168,7 +170,8 @@ class STBlock(Function):
             if use_tc():     # strided 1x1 conv = K=1 / identity-adjacency case of the tcgen05 engine
                 W2r = Wr.t().contiguous()                      # (Cout, Cin): rows n, cols ci
                 call('gcn_tc', x, None, None, None, None, None, W2r, cfg.ones, idn.dst_ptr,
-                     idn.dst_src, idn.dst_id, V, biasterm_r, None, rres, None, stats[4], stats[5],
+                     idn.dst_src, idn.dst_id, V, biasterm_r[0].contiguous(), cfg.ones, None, rres, None,
+                     stats[4], stats[5],
                      NM * Tout, V, 1, Cin, Cin, Cout, T, Tout, s, 1)
             else:
                 call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
@@ -228,7 +231,7 @@ class STBlock(Function):
             # transposed adjacency lists and Wc as the weight; adjacency gradient separately
             dz = torch.empty_like(z)
             call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
-                 pat.nnz, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin, 0, 0, 1, 0)
+                 pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin, 0, 0, 1, 0)
             call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
                  NM * T, V, K, Cin, Cout)
         else:
@@ -251,7 +254,7 @@ class STBlock(Function):
             if use_tc():
                 dyr = torch.empty_like(rres)
                 call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
-                     idn.t_id, V, None, gin, gin, dyr, None, None, NM * Tout, V, 1, Cout, Cout, Cin,
+                     idn.t_id, V, None, None, gin, gin, dyr, None, None, NM * Tout, V, 1, Cout, Cout, Cin,
                      T, Tout, s, 2)
                 call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr, dbtr,
                      NM * Tout, V, 1, Cin, Cout, T, Tout, s)
@@ -276,7 +279,7 @@ class GraphConv(Function):
         Cout = Wc.shape[1]
         z = torch.empty(NM, T, V, Cout, device=x.device, dtype=torch.float32)
         math = math_flag()
-        _gcn_forward(x, Wc, W2.contiguous(), biasterm, vals, pattern, z, None, None, NM * T, V,
+        _gcn_forward(x, Wc, W2, biasterm, vals, pattern, z, None, None, NM * T, V,
                      pattern.K, Cin, Cout, math)
         ctx.pattern, ctx.math = pattern, math
         ctx.save_for_backward(x, vals, Wc)
