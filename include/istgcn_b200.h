@@ -85,15 +85,19 @@ int istgcn_bn_bwd_coeffs(const double* sg, const double* sgx, double count, cons
  * biasterm[V][Cout] = sum_k bias[k*Cout+c] * colsum(A_eff[k])[w].  `frames` = N*M*T.
  * stat_sum/stat_sumsq (double[Cout], caller-zeroed, may be NULL) receive the BatchNorm
  * statistics of z.
- * Temporal stride: with t_out > 0, output frame f = n*t_out + to reads input frame
- * n*t_in + to*t_stride (and gin / add_in of the backward use the same mapping).  With K = 1
- * and an identity adjacency this is the strided 1x1 convolution of the residual branch
- * (net/st_gcnold.py:186-193); t_out = 0 means "same frames".                               */
+ * Temporal map: with t_out > 0, output frame f = n*t_out + to reads input frame
+ * n*t_in + to*t_stride + t_offset (zeros when that frame is outside [0, t_in): the temporal
+ * padding), and gin / add_in of the backward use the same mapping.  With K = 1 and an identity
+ * adjacency this is the strided 1x1 convolution of the residual branch
+ * (net/st_gcnold.py:186-193) and, with t_offset = tap - pad, one tap of the (kt x 1) temporal
+ * convolution (net/st_gcnold.py:165-171): the taps are summed through add_rows (partial sums of
+ * the previous taps, may alias z; NULL for the first).  biasterm may be NULL.  t_out = 0 means
+ * "same frames".                                                                             */
 int istgcn_gcn_fwd(const float* x, const float* Wc, const float* biasterm, const float* vals,
                    const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
-                   float* z, double* stat_sum, double* stat_sumsq,
+                   const float* add_rows, float* z, double* stat_sum, double* stat_sumsq,
                    int frames, int V, int K, int Cin, int Cout,
-                   int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
+                   int t_in, int t_out, int t_stride, int t_offset, int math, istgcn_stream_t s);
 /* input gradient + adjacency gradient.  dz is formed on the fly from the BatchNorm-backward
  * coefficients: dz = bn_p*((g - bn_m1) - bn_c*(z - bn_mu)) per channel (bn_p = NULL: dz = g).
  *   gin[(f,v)][ci] = sum_k sum_w A_eff[k][v][w] (dz Wc_k^T)[(f,w)][ci]  (+ add_in if not NULL)
@@ -104,7 +108,7 @@ int istgcn_gcn_bwd_x(const float* g, const float* z, const float* bn_p, const fl
                      const int* src_ptr, const int* src_kw, const int* src_id, int nnz,
                      const float* add_in, float* gin, float* dvals,
                      int frames, int V, int K, int Cin, int Cout,
-                     int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
+                     int t_in, int t_out, int t_stride, int t_offset, int math, istgcn_stream_t s);
 /* weight gradient: dWc[K*Cin][Cout] += X'^T dz, dbiasterm[V][Cout] += sum_f dz (both
  * caller-zeroed fp32).                                                                     */
 int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const float* bn_m1,
@@ -113,7 +117,7 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const fl
                      const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
                      float* dWc, float* dbiasterm,
                      int frames, int V, int K, int Cin, int Cout,
-                     int t_in, int t_out, int t_stride, int math, istgcn_stream_t s);
+                     int t_in, int t_out, int t_stride, int t_offset, int math, istgcn_stream_t s);
 
 /* tcgen05 / TMA / TMEM engine of the same graph convolution (forward form, or input-gradient
  * form when the lists are grouped by (k, source joint) and the weight is Wc):
@@ -135,7 +139,7 @@ int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const fl
                   const float* bias_k, const float* colsum, const float* add_rows, float* out,
                   float* in_out,
                   double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
-                  int CinPad, int Cout, int t_in, int t_out, int t_stride, int map_side,
+                  int CinPad, int Cout, int t_in, int t_out, int t_stride, int t_offset, int map_side,
                   istgcn_stream_t s);
 
 /* adjacency gradient on the tcgen05 engine (both operands fed by TMA):
@@ -153,7 +157,7 @@ int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const 
 int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* vals, const int* lptr,
                      const int* lsrc, const int* lid, int nnz, float* dWc, float* dbiasterm,
                      int frames, int V, int K, int Cin, int Cout,
-                     int t_in, int t_out, int t_stride, istgcn_stream_t s);
+                     int t_in, int t_out, int t_stride, int t_offset, istgcn_stream_t s);
 
 /* ---- Inception TCN with 1x1 bottlenecks (net/st_gcn_mstcn_1x1.py:250-266) ---------------
  *   a  = relu((z - mean1)*scale1 + beta1)              (tcn_start: BN + ReLU)
@@ -182,6 +186,27 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
                    float* dbeff, float* dWu, float* dbu, int NM, int T, int V, int C, int bp,
                    int stride, float drop_p, uint64_t drop_seed,
                    const unsigned long long* drop_step, int math, istgcn_stream_t s);
+
+/* ---- full-width temporal convolution (net/st_gcnold.py:160-174: BN -> ReLU -> Conv2d(C, C,
+ * (kt,1), (stride,1), (pad,0)) -> BN -> Dropout; net/st_gcn_mstcn.py: three such convs of 3/9/15
+ * taps scaled by mstcn_importance = one 15-tap conv).  The convolution itself is the sum over
+ * taps of the shifted, strided 1x1 engine above (istgcn_gcn_tc / istgcn_gcn_fwd with K = 1, an
+ * identity adjacency, t_offset = tap - pad and add_rows = the partial sums); these three
+ * element-wise stages sit around it.  rows = N*M*T*V, channels-last.
+ *   bn_relu_apply: a = max((z - mean)*scale + beta, 0)
+ *   bn_back_apply: du = p*((g' - m1) - c*(u - mean)),  g' = go with the dropout mask of
+ *                  (drop_p, drop_seed, drop_step) applied (the tail's convention)
+ *   relu_bn_bwd:   g1 = da where a > 0 else 0;  sg[c] += sum g1,  sgx[c] += sum g1*(z-mean1)*rstd1
+ *                  (caller-zeroed doubles, the inputs of istgcn_bn_bwd_coeffs)                 */
+int istgcn_bn_relu_apply(const float* z, const float* mean, const float* scale, const float* beta,
+                         float* a, long long rows, int C, istgcn_stream_t s);
+int istgcn_bn_back_apply(const float* go, const float* u, const float* p, const float* m1,
+                         const float* c, const float* mean, float* du, long long rows, int C,
+                         float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                         istgcn_stream_t s);
+int istgcn_relu_bn_bwd(const float* da, const float* a, const float* z, const float* mean1,
+                       const float* rstd1, float* g1, double* sg, double* sgx, long long rows, int C,
+                       istgcn_stream_t s);
 
 /* ---- block tail: BN2 -> dropout -> + residual -> ReLU (st_gcn_mstcn_1x1.py:262-266) -----
  * out = relu(BN2(u)*keep/(1-p) + res) where res = NULL (0), the block input (identity,

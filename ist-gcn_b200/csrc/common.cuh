@@ -231,8 +231,12 @@ __device__ __forceinline__ void st4(float* p, const float4& v) {
 
 // Temporal stride of the residual branch (st_gcnold.py:186-193): output frame f = n*t_out + to
 // reads input frame n*t_in + to*stride.  t_out == 0 means "same frames" (the graph convolution).
+// Temporal row map of a strided / shifted 1x1 convolution: frame `to` of the t_out-frame side
+// pairs with frame to*stride + offset of the t_in-frame side (the residual branch uses offset 0;
+// the taps of a temporal convolution use offset = tap - pad).  A frame outside [0, t_in) is the
+// zero padding: map_row returns -1 and the caller reads zeros / skips the store.
 struct FrameMap {
-    int t_in, t_out, stride;
+    int t_in, t_out, stride, offset;
 };
 __device__ __forceinline__ long long map_row(const FrameMap& m, long long row, int V) {
     if (m.t_out == 0) return row;
@@ -240,7 +244,9 @@ __device__ __forceinline__ long long map_row(const FrameMap& m, long long row, i
     const int v = (int)(row - f * V);
     const long long n = f / m.t_out;
     const int to = (int)(f - n * m.t_out);
-    return (n * m.t_in + (long long)to * m.stride) * V + v;
+    const int ti = to * m.stride + m.offset;
+    if (ti < 0 || ti >= m.t_in) return -1;
+    return (n * m.t_in + ti) * V + v;
 }
 
 // Cooperative tile staging with memory-level parallelism: every thread first issues COUNT

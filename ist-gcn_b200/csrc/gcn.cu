@@ -32,16 +32,15 @@ __device__ __forceinline__ void load_x_slice(float* xs, const float* __restrict_
             tid, 0,
             [&](int i) {
                 const int r = i >> 3, c4 = (i & 7) * 4;
-                return (r < valid_rows && ci0 + c4 < Cin)
-                           ? ld4(x + map_row(fm, row0 + r, V) * Cin + ci0 + c4)
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+                const long long src = (r < valid_rows && ci0 + c4 < Cin) ? map_row(fm, row0 + r, V) : -1;
+                return src >= 0 ? ld4(x + src * Cin + ci0 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
             },
             [&](int i, const float4& v) { st4(xs + (i >> 3) * 32 + (i & 7) * 4, v); });
     } else {
         for (int i = tid; i < kTileRows * 32; i += kThreads) {
             const int r = i >> 5, c = i & 31;
-            xs[i] = (r < valid_rows && ci0 + c < Cin) ? x[map_row(fm, row0 + r, V) * Cin + ci0 + c]
-                                                      : 0.f;
+            const long long src = (r < valid_rows && ci0 + c < Cin) ? map_row(fm, row0 + r, V) : -1;
+            xs[i] = src >= 0 ? x[src * Cin + ci0 + c] : 0.f;
         }
     }
 }
@@ -72,7 +71,7 @@ __device__ __forceinline__ void aggregate_partition(float* As, int lda, const fl
 
 // ------------------------------------------------------------------------------------ forward
 struct GcnFwdParams {
-    const float *x, *Wc, *biasterm, *vals;
+    const float *x, *Wc, *biasterm, *vals, *add_rows;
     const int *dst_ptr, *dst_src, *dst_id;
     float* z;
     double *stat_sum, *stat_sumsq;
@@ -155,8 +154,14 @@ __global__ void __launch_bounds__(kThreads) gcn_fwd_kernel(GcnFwdParams p) {
                     const int r = warp_m * 32 + mt * 16 + g + 8 * h;
                     if (r < valid_rows) {
                         const int w = r % V;
-                        const float2 b = *reinterpret_cast<const float2*>(
-                            p.biasterm + (size_t)w * Cout + n0 + cl);
+                        float2 b = make_float2(0.f, 0.f);
+                        if (p.biasterm)
+                            b = *reinterpret_cast<const float2*>(p.biasterm + (size_t)w * Cout + n0 + cl);
+                        if (p.add_rows) {                       // partial sums of a previous tap
+                            const float2 a = *reinterpret_cast<const float2*>(
+                                p.add_rows + (row0 + r) * Cout + n0 + cl);
+                            b.x += a.x; b.y += a.y;
+                        }
                         const float v0 = acc[mt][nt][2 * h] + b.x;
                         const float v1 = acc[mt][nt][2 * h + 1] + b.y;
                         *reinterpret_cast<float2*>(p.z + (row0 + r) * Cout + n0 + cl) =
@@ -327,7 +332,9 @@ __global__ void __launch_bounds__(kThreads) gcn_bwd_x_kernel(GcnBwdXParams p) {
                     const float* grow = Gs + f * V * kLdG + lane;
                     float a = 0.f;
                     for (int j = s_ptr[v]; j < s_ptr[v + 1]; ++j) a = fmaf(s_val[j], grow[s_goff[j]], a);
-                    const long long o = map_row(p.fm, row0 + r, V) * Cin + ci0 + lane;
+                    const long long orow = map_row(p.fm, row0 + r, V);
+                    if (orow < 0) continue;                    // tap falls into the zero padding
+                    const long long o = orow * Cin + ci0 + lane;
                     if (p.add_in) a += p.add_in[o];
                     p.gin[o] = a;
                 }
@@ -514,17 +521,17 @@ using namespace istgcn;
 
 ISTGCN_API int istgcn_gcn_fwd(const float* x, const float* Wc, const float* biasterm,
                               const float* vals, const int* dst_ptr, const int* dst_src,
-                              const int* dst_id, int nnz, float* z, double* stat_sum,
+                              const int* dst_id, int nnz, const float* add_rows, float* z, double* stat_sum,
                               double* stat_sumsq, int frames, int V, int K, int Cin, int Cout,
-                              int t_in, int t_out, int t_stride, int math, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(x && Wc && biasterm && vals && dst_ptr && dst_src && dst_id && z, ISTGCN_E_ARG,
+                              int t_in, int t_out, int t_stride, int t_offset, int math, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(x && Wc && vals && dst_ptr && dst_src && dst_id && z, ISTGCN_E_ARG,
                    "gcn_fwd: null pointer");
     ISTGCN_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), ISTGCN_E_ARG,
                    "gcn_fwd: pass both statistics buffers or neither");
     if (int e = check_gcn_dims("gcn_fwd", frames, V, K, Cin, Cout, nnz)) return e;
     if (frames == 0) return 0;
-    GcnFwdParams p{x, Wc, biasterm, vals, dst_ptr, dst_src, dst_id, z, stat_sum, stat_sumsq,
-                   frames, V, K, Cin, Cout, nnz, 0, {t_in, t_out, t_stride}};
+    GcnFwdParams p{x, Wc, biasterm, vals, add_rows, dst_ptr, dst_src, dst_id, z, stat_sum, stat_sumsq,
+                   frames, V, K, Cin, Cout, nnz, 0, {t_in, t_out, t_stride, t_offset}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     p.tiles = (frames + F - 1) / F;
     cudaStream_t st = (cudaStream_t)s;
@@ -539,7 +546,7 @@ ISTGCN_API int istgcn_gcn_bwd_x(const float* g, const float* z, const float* bn_
                                 const float* x, const float* Wc, const float* vals,
                                 const int* src_ptr, const int* src_kw, const int* src_id, int nnz,
                                 const float* add_in, float* gin, float* dvals, int frames, int V,
-                                int K, int Cin, int Cout, int t_in, int t_out, int t_stride,
+                                int K, int Cin, int Cout, int t_in, int t_out, int t_stride, int t_offset,
                                 int math, istgcn_stream_t s) {
     ISTGCN_REQUIRE(g && x && Wc && vals && src_ptr && src_kw && src_id && (gin || dvals), ISTGCN_E_ARG,
                    "gcn_bwd_x: null pointer");
@@ -548,7 +555,7 @@ ISTGCN_API int istgcn_gcn_bwd_x(const float* g, const float* z, const float* bn_
     if (int e = check_gcn_dims("gcn_bwd_x", frames, V, K, Cin, Cout, nnz)) return e;
     if (frames == 0) return 0;
     GcnBwdXParams pr{g, z, {bn_p, bn_m1, bn_c, bn_mu}, x, Wc, vals, add_in, src_ptr, src_kw, src_id, gin, dvals,
-                     frames, V, K, Cin, Cout, nnz, 0, {t_in, t_out, t_stride}};
+                     frames, V, K, Cin, Cout, nnz, 0, {t_in, t_out, t_stride, t_offset}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     pr.tiles = (frames + F - 1) / F;
     const size_t smem = gcn_bwd_x_smem();
@@ -569,7 +576,7 @@ ISTGCN_API int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_
                                 const float* x, const float* vals,
                                 const int* dst_ptr, const int* dst_src, const int* dst_id, int nnz,
                                 float* dWc, float* dbiasterm, int frames, int V, int K, int Cin,
-                                int Cout, int t_in, int t_out, int t_stride, int math,
+                                int Cout, int t_in, int t_out, int t_stride, int t_offset, int math,
                                 istgcn_stream_t s) {
     ISTGCN_REQUIRE(g && x && vals && dst_ptr && dst_src && dst_id && dWc, ISTGCN_E_ARG,
                    "gcn_bwd_w: null pointer");
@@ -578,7 +585,7 @@ ISTGCN_API int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_
     if (int e = check_gcn_dims("gcn_bwd_w", frames, V, K, Cin, Cout, nnz)) return e;
     if (frames == 0) return 0;
     GcnBwdWParams pr{g, z, {bn_p, bn_m1, bn_c, bn_mu}, x, vals, dst_ptr, dst_src, dst_id, dWc, dbiasterm,
-                     frames, V, K, Cin, Cout, nnz, 0, 0, 0, {t_in, t_out, t_stride}};
+                     frames, V, K, Cin, Cout, nnz, 0, 0, 0, {t_in, t_out, t_stride, t_offset}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     pr.tiles = (frames + F - 1) / F;
     cudaStream_t st = (cudaStream_t)s;

@@ -275,7 +275,7 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ 
                         else tma_store_2d(stage, om, cg, (int)(row0 + ew * 32));
                         bulk_commit();
                     }
-                } else if (ok) {
+                } else if (ok && map_row(p.out_map, row0 + r, V) >= 0) {
                     const long long orow = map_row(p.out_map, row0 + r, V);
                     float* o = p.out + orow * Cout + cg;
                     if ((Cout & 3) == 0) {
@@ -347,8 +347,9 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ 
                         const int r = i >> 3, c4 = (i & 7) * 4;
                         v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                         zv[u] = v[u];
-                        if (r < valid && ci0 + c4 < Cin) {
-                            const long long off = map_row(p.in_map, row0 + r, V) * Cin + ci0 + c4;
+                        const long long src = (r < valid && ci0 + c4 < Cin) ? map_row(p.in_map, row0 + r, V) : -1;
+                        if (src >= 0) {
+                            const long long off = src * Cin + ci0 + c4;
                             v[u] = ld4(p.in + off);
                             if (p.bn.p) zv[u] = ld4(p.in2 + off);
                         }
@@ -373,8 +374,9 @@ gcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ 
                     for (int i = lt; i < kAtomRows * 32; i += 128) {
                         const int r = i >> 5, c = i & 31;
                         float v = 0.f;
-                        if (r < valid && ci0 + c < Cin) {
-                            const long long off = map_row(p.in_map, row0 + r, V) * Cin + ci0 + c;
+                        const long long src = (r < valid && ci0 + c < Cin) ? map_row(p.in_map, row0 + r, V) : -1;
+                        if (src >= 0) {
+                            const long long off = src * Cin + ci0 + c;
                             v = p.in[off];
                             if (p.bn.p)
                                 v = bn_back(v, p.in2[off], p.bn.p[ci0 + c], p.bn.m1[ci0 + c],
@@ -528,7 +530,7 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
                              int nnz, const float* bias_k, const float* colsum, const float* add_rows,
                              float* out,
                              float* in_out, double* stat_sum, double* stat_sumsq, int frames, int V,
-                             int K, int Cin, int CinPad, int Cout, int t_in, int t_out, int t_stride,
+                             int K, int Cin, int CinPad, int Cout, int t_in, int t_out, int t_stride, int t_offset,
                              int map_side, istgcn_stream_t s) {
     ISTGCN_REQUIRE(in && w_rows && vals && lptr && lsrc && lid && out, ISTGCN_E_ARG,
                    "gcn_tc: null pointer");
@@ -548,9 +550,9 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
                    "gcn_tc: pass bias_k and colsum together");
     tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_k, colsum,
                       add_rows, out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout,
-                      nnz, 0, {0, 0, 1}, {0, 0, 1}, 0};
-    if (map_side == 1) p.in_map = {t_in, t_out, t_stride};
-    if (map_side == 2) p.out_map = {t_in, t_out, t_stride};
+                      nnz, 0, {0, 0, 1, 0}, {0, 0, 1, 0}, 0};
+    if (map_side == 1) p.in_map = {t_in, t_out, t_stride, t_offset};
+    if (map_side == 2) p.out_map = {t_in, t_out, t_stride, t_offset};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     p.tiles = (frames + F - 1) / F;
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
@@ -564,7 +566,8 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         if (int e = tc::encode_tile_map(&omap, out, (long long)frames * V, Cout, 32)) return e;
         if (int e = tc::encode_tile_map(&omap_last, out, (long long)frames * V, Cout, last_rows)) return e;
-        p.tma_out = add_rows ? 2 : 1;
+        // statistics must see the accumulated value: the reduce-add path never has it in registers
+        p.tma_out = add_rows ? (stat_sum ? 0 : 2) : 1;
     }
     cudaStream_t st = (cudaStream_t)s;
     if (ncols == 256) return tc::launch_tc<256>(map, omap, omap_last, p, st);

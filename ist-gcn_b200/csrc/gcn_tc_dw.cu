@@ -180,7 +180,8 @@ gcn_tc_dw_kernel(const __grid_constant__ CUtensorMap dzmap, GcnDwParams p) {
                     for (int u = 0; u < 8; ++u) {
                         const int i = lt + u * 128;
                         const int r = i >> 3, c4 = (i & 7) * 4;
-                        v[u] = (r < valid && ci0 + c4 < Cin) ? ld4(p.x + map_row(p.in_map, row0 + r, V) * Cin + ci0 + c4)
+                        const long long src = (r < valid && ci0 + c4 < Cin) ? map_row(p.in_map, row0 + r, V) : -1;
+                        v[u] = src >= 0 ? ld4(p.x + src * Cin + ci0 + c4)
                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
@@ -191,7 +192,8 @@ gcn_tc_dw_kernel(const __grid_constant__ CUtensorMap dzmap, GcnDwParams p) {
                 } else {
                     for (int i = lt; i < kAtomRows * 32; i += 128) {
                         const int r = i >> 5, c = i & 31;
-                        xs[i] = (r < valid && ci0 + c < Cin) ? p.x[map_row(p.in_map, row0 + r, V) * Cin + ci0 + c] : 0.f;
+                        const long long src = (r < valid && ci0 + c < Cin) ? map_row(p.in_map, row0 + r, V) : -1;
+                        xs[i] = src >= 0 ? p.x[src * Cin + ci0 + c] : 0.f;
                     }
                 }
                 __syncwarp();
@@ -262,7 +264,7 @@ using namespace istgcn;
 ISTGCN_API int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* vals, const int* lptr,
                                 const int* lsrc, const int* lid, int nnz, float* dWc,
                                 float* dbiasterm, int frames, int V, int K, int Cin, int Cout,
-                                int t_in, int t_out, int t_stride, istgcn_stream_t s) {
+                                int t_in, int t_out, int t_stride, int t_offset, istgcn_stream_t s) {
     ISTGCN_REQUIRE(dz && x && vals && lptr && lsrc && lid && dWc, ISTGCN_E_ARG, "gcn_tc_dw: null pointer");
     ISTGCN_REQUIRE(V >= 1 && V <= 32 && K >= 1 && K <= 4, ISTGCN_E_SHAPE, "gcn_tc_dw: V=%d K=%d", V, K);
     ISTGCN_REQUIRE(Cout % 32 == 0 && Cout >= 32 && Cout <= 512, ISTGCN_E_SHAPE,
@@ -272,7 +274,7 @@ ISTGCN_API int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* va
     if (frames == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
     tc::GcnDwParams p{x, vals, lptr, lsrc, lid, dWc, frames, V, K, Cin, (Cin + 31) / 32 * 32, Cout, nnz, 0, 0,
-                       {t_in, t_out, t_stride}};
+                       {t_in, t_out, t_stride, t_offset}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     p.tiles = (frames + F - 1) / F;
     const int nchunk = p.CinPad / 32;

@@ -1,0 +1,161 @@
+// Element-wise stages around the full-width temporal convolution of the baseline ST-GCN block
+// (reference: net/st_gcnold.py:160-174, net/st_gcn_msgcn.py, net/st_gcn_mstcn.py):
+//
+//     a  = relu(BN1(z))                         istgcn_bn_relu_apply   (forward)
+//     u  = sum_tap shift_tap(a) * W_tap         kt launches of the strided / shifted 1x1 engine
+//     du = BN2-backward(dropout-mask(go), u)    istgcn_bn_back_apply   (backward)
+//     da = sum_tap shift_tap^T(du) * W_tap^T    kt launches, accumulated
+//     g1 = da * (a > 0), sums for BN1-backward  istgcn_relu_bn_bwd
+//
+// All three are HBM-bound float4 streams over channels-last rows.
+#include "common.cuh"
+
+namespace istgcn {
+
+__global__ void bn_relu_apply_kernel(const float* __restrict__ z, const float* __restrict__ mean,
+                                     const float* __restrict__ scale, const float* __restrict__ beta,
+                                     float* __restrict__ a, long long n4, int C) {
+    const int c4 = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4) * 4;
+        const float4 zv = ld4(z + i * 4);
+        const float4 mu = ld4(mean + c), sc = ld4(scale + c), be = ld4(beta + c);
+        st4(a + i * 4, make_float4(fmaxf(bn_apply(zv.x, mu.x, sc.x, be.x), 0.f),
+                                   fmaxf(bn_apply(zv.y, mu.y, sc.y, be.y), 0.f),
+                                   fmaxf(bn_apply(zv.z, mu.z, sc.z, be.z), 0.f),
+                                   fmaxf(bn_apply(zv.w, mu.w, sc.w, be.w), 0.f)));
+    }
+}
+
+__global__ void bn_back_apply_kernel(const float* __restrict__ go, const float* __restrict__ u,
+                                     const float* __restrict__ p, const float* __restrict__ m1,
+                                     const float* __restrict__ cc, const float* __restrict__ mean,
+                                     float* __restrict__ du, long long n4, int C, float drop_p,
+                                     float keep_scale, uint64_t seed0, const unsigned long long* step) {
+    const uint64_t seed = effective_seed(seed0, step);
+    const int c4 = C >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % c4) * 4;
+        const float4 gv = ld4(go + i * 4), uv = ld4(u + i * 4);
+        const float4 pv = ld4(p + c), mv = ld4(m1 + c), cv = ld4(cc + c), nv = ld4(mean + c);
+        float g[4] = {gv.x, gv.y, gv.z, gv.w};
+        if (drop_p > 0.f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                g[j] = dropout_keep(seed, (uint64_t)(i * 4 + j), drop_p) ? g[j] * keep_scale : 0.f;
+        }
+        st4(du + i * 4, make_float4(bn_back(g[0], uv.x, pv.x, mv.x, cv.x, nv.x),
+                                    bn_back(g[1], uv.y, pv.y, mv.y, cv.y, nv.y),
+                                    bn_back(g[2], uv.z, pv.z, mv.z, cv.z, nv.z),
+                                    bn_back(g[3], uv.w, pv.w, mv.w, cv.w, nv.w)));
+    }
+}
+
+// thread = (row sub-group, 4 channels); per-thread partial sums, one double atomic per channel
+// and CTA at the end
+__global__ void relu_bn_bwd_kernel(const float* __restrict__ da, const float* __restrict__ a,
+                                   const float* __restrict__ z, const float* __restrict__ mean1,
+                                   const float* __restrict__ rstd1, float* __restrict__ g1,
+                                   double* __restrict__ sg, double* __restrict__ sgx, long long rows,
+                                   int C) {
+    __shared__ double red[2][256 * 4];
+    const int c4 = C >> 2;
+    const int rows_per_iter = blockDim.x / c4;
+    const int col = threadIdx.x % c4, rsub = threadIdx.x / c4;
+    const int c = col * 4;
+    double a_g[4] = {0, 0, 0, 0}, a_gx[4] = {0, 0, 0, 0};
+    float mu[4], rs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        mu[j] = mean1[c + j];
+        rs[j] = rstd1[c + j];
+    }
+    if (rsub < rows_per_iter) {
+        for (long long r = (long long)blockIdx.x * rows_per_iter + rsub; r < rows;
+             r += (long long)gridDim.x * rows_per_iter) {
+            const long long off = r * C + c;
+            const float4 dv = ld4(da + off), av = ld4(a + off), zv = ld4(z + off);
+            const float d4[4] = {dv.x, dv.y, dv.z, dv.w}, a4[4] = {av.x, av.y, av.z, av.w},
+                        z4[4] = {zv.x, zv.y, zv.z, zv.w};
+            float g[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                g[j] = a4[j] > 0.f ? d4[j] : 0.f;
+                a_g[j] += g[j];
+                a_gx[j] += g[j] * ((z4[j] - mu[j]) * rs[j]);
+            }
+            st4(g1 + off, make_float4(g[0], g[1], g[2], g[3]));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        red[0][threadIdx.x * 4 + j] = a_g[j];
+        red[1][threadIdx.x * 4 + j] = a_gx[j];
+    }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+        const int cc = ch >> 2, j = ch & 3;
+        double s0 = 0, s1 = 0;
+        for (int k = 0; k < rows_per_iter; ++k) {
+            const int th = k * c4 + cc;
+            s0 += red[0][th * 4 + j];
+            s1 += red[1][th * 4 + j];
+        }
+        atomicAdd(&sg[ch], s0);
+        atomicAdd(&sgx[ch], s1);
+    }
+}
+
+static inline int stream_grid(long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * 16;
+    return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace istgcn
+
+using namespace istgcn;
+
+ISTGCN_API int istgcn_bn_relu_apply(const float* z, const float* mean, const float* scale,
+                                    const float* beta, float* a, long long rows, int C,
+                                    istgcn_stream_t s) {
+    ISTGCN_REQUIRE(z && mean && scale && beta && a, ISTGCN_E_ARG, "bn_relu_apply: null pointer");
+    ISTGCN_REQUIRE(C % 4 == 0, ISTGCN_E_SHAPE, "bn_relu_apply: C=%d not a multiple of 4", C);
+    const long long n4 = rows * C / 4;
+    if (n4 == 0) return 0;
+    bn_relu_apply_kernel<<<stream_grid(n4, 256), 256, 0, (cudaStream_t)s>>>(z, mean, scale, beta, a, n4, C);
+    return finish_launch("bn_relu_apply");
+}
+
+ISTGCN_API int istgcn_bn_back_apply(const float* go, const float* u, const float* p, const float* m1,
+                                    const float* c, const float* mean, float* du, long long rows,
+                                    int C, float drop_p, uint64_t drop_seed,
+                                    const unsigned long long* drop_step, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(go && u && p && m1 && c && mean && du, ISTGCN_E_ARG, "bn_back_apply: null pointer");
+    ISTGCN_REQUIRE(C % 4 == 0, ISTGCN_E_SHAPE, "bn_back_apply: C=%d not a multiple of 4", C);
+    ISTGCN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, ISTGCN_E_ARG, "bn_back_apply: dropout p=%f", drop_p);
+    const long long n4 = rows * C / 4;
+    if (n4 == 0) return 0;
+    bn_back_apply_kernel<<<stream_grid(n4, 256), 256, 0, (cudaStream_t)s>>>(
+        go, u, p, m1, c, mean, du, n4, C, drop_p, 1.f / (1.f - drop_p), drop_seed, drop_step);
+    return finish_launch("bn_back_apply");
+}
+
+ISTGCN_API int istgcn_relu_bn_bwd(const float* da, const float* a, const float* z, const float* mean1,
+                                  const float* rstd1, float* g1, double* sg, double* sgx,
+                                  long long rows, int C, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(da && a && z && mean1 && rstd1 && g1 && sg && sgx, ISTGCN_E_ARG,
+                   "relu_bn_bwd: null pointer");
+    ISTGCN_REQUIRE(C % 4 == 0 && C <= 1024, ISTGCN_E_SHAPE, "relu_bn_bwd: C=%d unsupported", C);
+    if (rows == 0) return 0;
+    const int rows_per_iter = 256 / (C / 4);
+    long long blocks = (rows + rows_per_iter * 8 - 1) / (rows_per_iter * 8);
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    relu_bn_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(da, a, z, mean1, rstd1, g1, sg, sgx,
+                                                                 rows, C);
+    return finish_launch("relu_bn_bwd");
+}

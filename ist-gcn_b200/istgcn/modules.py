@@ -154,6 +154,84 @@ class FusedBlockMixin(object):
         return out
 
 
+def merged_temporal_taps(convs, m_imp, divisor=1.0):
+    """Temporal conv weights (Cout, Cin, kt, 1) of one or several centred branches ->
+    Wtt[kt_max, Cin, Cout] (tap first) and the bias.  Several branches scaled by
+    ``mstcn_importance``, summed and divided by 3 (st_gcn_mstcn.py:244-247) are ONE kt_max-tap
+    convolution."""
+    kt = max(c.weight.shape[2] for c in convs)
+    wtt, bias = 0, 0
+    for i, conv in enumerate(convs):
+        k = conv.weight.shape[2]
+        off = (kt - k) // 2
+        w = conv.weight[:, :, :, 0].permute(2, 1, 0)             # (tap, in, out)
+        if off:
+            w = F.pad(w, (0, 0, 0, 0, off, off))
+        scale = 1 if m_imp is None else m_imp[i]
+        wtt = wtt + w * scale
+        bias = bias + conv.bias * scale
+    if divisor != 1.0:
+        wtt, bias = wtt / divisor, bias / divisor
+    return wtt, bias
+
+
+class FusedWideBlockMixin(object):
+    """Drives ops.STBlockWide for a block with a full-width temporal convolution.  Sub-module
+    names follow the reference: ``gcn``; either ``tcn`` = Sequential(BN, ReLU, Conv2d(kt x 1), BN,
+    Dropout) (st_gcnold.py:160-174) or ``tcn_start`` / ``tcn_1,2,3`` / ``tcn_end``
+    (st_gcn_mstcn.py:185-213); ``residual``."""
+
+    def _init_fused(self, in_channels, out_channels, stride, dropout, residual):
+        FusedBlockMixin._init_fused(self, in_channels, out_channels, stride, dropout, residual)
+
+    _gcn_conv = FusedBlockMixin._gcn_conv
+
+    def _bns(self):
+        if hasattr(self, 'tcn'):
+            return self.tcn[0], self.tcn[3]
+        return self.tcn_start[0], self.tcn_end[0]
+
+    def _block_cfg(self, pattern):
+        bn1, bn2 = self._bns()
+        if self._cfg is None or self._cfg.pattern is not pattern:
+            bnr = ops.BNState(self.residual[1]) if self._res_mode == 2 else None
+            ident = SparsePattern.identity(pattern.V, pattern.flat_idx.device)
+            self._cfg = ops.BlockCfg(pattern, ident, self._io[2], self._res_mode, self._drop_p,
+                                     ops.BNState(bn1), ops.BNState(bn2), bnr, 0)
+        else:
+            self._cfg.bn1, self._cfg.bn2 = ops.BNState(bn1), ops.BNState(bn2)
+            if self._res_mode == 2:
+                self._cfg.bnr = ops.BNState(self.residual[1])
+        return self._cfg
+
+    def forward_cl(self, x, adjs, m_imp, pattern):
+        """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
+        cfg = self._block_cfg(pattern)
+        cfg.training = self.training
+        cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
+        conv = self._gcn_conv()
+        vals, wc, biasterm, w2 = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
+        if hasattr(self, 'tcn'):
+            wtt, bt = merged_temporal_taps([self.tcn[2]], None)
+        else:
+            wtt, bt = merged_temporal_taps([self.tcn_1, self.tcn_2, self.tcn_3], m_imp, 3.0)
+        bn1, bn2 = self._bns()
+        wr = btr = bnr_w = bnr_b = None
+        if self._res_mode == 2:
+            rconv, rbn = self.residual[0], self.residual[1]
+            cout, cin = rconv.weight.shape[0], rconv.weight.shape[1]
+            wr = rconv.weight.view(cout, cin).t()
+            btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout)
+            bnr_w, bnr_b = rbn.weight, rbn.bias
+        out = ops.STBlockWide.apply(x, vals, wc, biasterm, w2, bn1.weight, bn1.bias, wtt, bt,
+                                    bn2.weight, bn2.bias, wr, btr, bnr_w, bnr_b, cfg)
+        if self.training:
+            for bn in (bn1, bn2) + ((self.residual[1],) if self._res_mode == 2 else ()):
+                bn.num_batches_tracked += 1
+        self.last_seed = cfg.seed
+        return out
+
+
 class FusedModelMixin(object):
     """Model.forward / extract_feature shared by every variant (st_gcnold.py:71-120): data_bn
     with the layout change, the block loop, global pooling, the ``fcn`` 1x1 conv."""

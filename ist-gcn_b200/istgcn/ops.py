@@ -67,10 +67,10 @@ def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, C
         W2 = W2.contiguous()
         call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src,
              pat.dst_id, pat.nnz, None if bias_k is None else bias_k.contiguous(), colsum, None, z, None,
-             s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout, 0, 0, 1, 0)
+             s_sum, s_sq, frames, V, K, Cin, W2.shape[1], Cout, 0, 0, 1, 0, 0)
     else:
-        call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
-             s_sum, s_sq, frames, V, K, Cin, Cout, 0, 0, 1, math)
+        call('gcn_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, None, z,
+             s_sum, s_sq, frames, V, K, Cin, Cout, 0, 0, 1, 0, math)
 
 
 class DataBN(Function):
@@ -172,10 +172,10 @@ class STBlock(Function):
                 call('gcn_tc', x, None, None, None, None, None, W2r, cfg.ones, idn.dst_ptr,
                      idn.dst_src, idn.dst_id, V, biasterm_r[0].contiguous(), cfg.ones, None, rres, None,
                      stats[4], stats[5],
-                     NM * Tout, V, 1, Cin, Cin, Cout, T, Tout, s, 1)
+                     NM * Tout, V, 1, Cin, Cin, Cout, T, Tout, s, 0, 1)
             else:
                 call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
-                     rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+                     None, rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0, math)
             mean_r, scale_r, rstd_r = _bn_forward_coeffs(training, stats[4], stats[5], R_out, bnr_w,
                                                          cfg.bnr, Cout, dev)
             bnr_b = bnr_b.contiguous()
@@ -231,19 +231,19 @@ class STBlock(Function):
             # transposed adjacency lists and Wc as the weight; adjacency gradient separately
             dz = torch.empty_like(z)
             call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
-                 pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin, 0, 0, 1, 0)
+                 pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin, 0, 0, 1, 0, 0)
             call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
                  NM * T, V, K, Cin, Cout)
         else:
             call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
-                 pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+                 pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, 0, math)
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
         if use_tc():
             call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc, dbt,
-                 NM * T, V, K, Cin, Cout, 0, 0, 1)
+                 NM * T, V, K, Cin, Cout, 0, 0, 1, 0)
         else:
             call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src,
-                 pat.dst_id, pat.nnz, dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, math)
+                 pat.dst_id, pat.nnz, dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, 0, math)
         dWr = dbtr = dgr = dbr = None
         if cfg.res_mode == 2:
             idn = cfg.ident
@@ -255,17 +255,196 @@ class STBlock(Function):
                 dyr = torch.empty_like(rres)
                 call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
                      idn.t_id, V, None, None, gin, gin, dyr, None, None, NM * Tout, V, 1, Cout, Cout, Cin,
-                     T, Tout, s, 2)
+                     T, Tout, s, 0, 2)
                 call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr, dbtr,
-                     NM * Tout, V, 1, Cin, Cout, T, Tout, s)
+                     NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0)
             else:
                 call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr,
                      idn.src_kw, idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, Cout, T, Tout, s,
-                     math)
+                     0, math)
                 call('gcn_bwd_w', go, rres, pr, m1r, cr, mean_r, x, cfg.ones, idn.dst_ptr, idn.dst_src,
-                     idn.dst_id, V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, math)
+                     idn.dst_id, V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0, math)
         return (gin, dvals, dWc, dbt, None, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr,
                 dbtr, dgr, dbr, None)
+
+
+class STBlockWide(Function):
+    """One baseline ST-GCN block with a FULL-WIDTH temporal convolution: graph conv -> BN -> ReLU
+    -> Conv2d(C, C, (kt,1), (stride,1), (pad,0)) -> BN -> dropout -> + residual -> ReLU
+    (net/st_gcnold.py:148-203; net/st_gcn_msgcn.py with the Inception graph conv;
+    net/st_gcn_mstcn.py with the three 3/9/15-tap branches merged into one 15-tap kernel).
+
+    The temporal convolution is the sum over taps of the strided, shifted 1x1 engine (K = 1,
+    identity adjacency, t_offset = tap - pad); its partial sums accumulate in place.
+    Wtt[kt, C(in), C(out)] is the conv weight with the tap first, bt[C] its bias."""
+
+    @staticmethod
+    def forward(ctx, x, vals, Wc, biasterm, W2, bn1_w, bn1_b, Wtt, bt, bn2_w, bn2_b, Wr, biasterm_r,
+                bnr_w, bnr_b, cfg):
+        x = x.contiguous()
+        NM, T, V, Cin = x.shape
+        C = Wc.shape[1]
+        pat, s, idn = cfg.pattern, cfg.stride, cfg.ident
+        K, kt = pat.K, Wtt.shape[0]
+        pad = (kt - 1) // 2
+        Tout = (T - 1) // s + 1
+        R_in, R_out = NM * T * V, NM * Tout * V
+        dev = x.device
+        training = cfg.training
+        math = math_flag()
+        drop_p = cfg.drop_p if training else 0.0
+        vals, Wc, biasterm = vals.contiguous(), Wc.contiguous(), biasterm.contiguous()
+        Wtt, bt = Wtt.contiguous(), bt.contiguous()
+        if cfg.ones is None or cfg.ones.device != dev:
+            cfg.ones = torch.ones(V, device=dev, dtype=torch.float32)
+        stats = torch.zeros(6, C, device=dev, dtype=torch.float64) if training else [None] * 6
+
+        z = torch.empty(NM, T, V, C, device=dev, dtype=torch.float32)
+        _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K, Cin, C, math)
+        mean1, scale1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w, cfg.bn1,
+                                                  C, dev)
+        bn1_b, bn2_b = bn1_b.contiguous(), bn2_b.contiguous()
+        a = torch.empty_like(z)
+        call('bn_relu_apply', z, mean1, scale1, bn1_b, a, i64(R_in), C)
+        u = torch.empty(NM, Tout, V, C, device=dev, dtype=torch.float32)
+        if use_tc():
+            Wrows = Wtt.detach().transpose(1, 2).contiguous()         # [kt][C(out)][C(in)]
+            bt_k = bt.detach().view(1, C)
+        else:
+            bt_vc = bt.detach().unsqueeze(0).expand(V, C).contiguous()
+        for tap in range(kt):
+            first, last = tap == 0, tap == kt - 1
+            ssum, ssq = (stats[2], stats[3]) if last else (None, None)
+            if use_tc():
+                call('gcn_tc', a, None, None, None, None, None, Wrows[tap], cfg.ones, idn.dst_ptr,
+                     idn.dst_src, idn.dst_id, V, bt_k if first else None, cfg.ones if first else None,
+                     None if first else u, u, None, ssum, ssq, NM * Tout, V, 1, C, C, C, T, Tout, s,
+                     tap - pad, 1)
+            else:
+                call('gcn_fwd', a, Wtt[tap], bt_vc if first else None, cfg.ones, idn.dst_ptr,
+                     idn.dst_src, idn.dst_id, V, None if first else u, u, ssum, ssq, NM * Tout, V, 1,
+                     C, C, T, Tout, s, tap - pad, math)
+        mean2, scale2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w, cfg.bn2,
+                                                  C, dev)
+        rres = scale_r = mean_r = rstd_r = None
+        res = None
+        if cfg.res_mode == 1:
+            res = x
+        elif cfg.res_mode == 2:
+            Wr, biasterm_r = Wr.contiguous(), biasterm_r.contiguous()
+            rres = torch.empty(NM, Tout, V, C, device=dev, dtype=torch.float32)
+            if use_tc():
+                W2r = Wr.t().contiguous()
+                call('gcn_tc', x, None, None, None, None, None, W2r, cfg.ones, idn.dst_ptr,
+                     idn.dst_src, idn.dst_id, V, biasterm_r[0].contiguous(), cfg.ones, None, rres, None,
+                     stats[4], stats[5], NM * Tout, V, 1, Cin, Cin, C, T, Tout, s, 0, 1)
+            else:
+                call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
+                     None, rres, stats[4], stats[5], NM * Tout, V, 1, Cin, C, T, Tout, s, 0, math)
+            mean_r, scale_r, rstd_r = _bn_forward_coeffs(training, stats[4], stats[5], R_out, bnr_w,
+                                                         cfg.bnr, C, dev)
+            bnr_b = bnr_b.contiguous()
+            res = rres
+        out = torch.empty(NM, Tout, V, C, device=dev, dtype=torch.float32)
+        call('block_tail_fwd', u, mean2, scale2, bn2_b, res, mean_r, scale_r,
+             bnr_b if cfg.res_mode == 2 else None, out, i64(R_out), C, float(drop_p),
+             u64(cfg.seed), step_counter(dev))
+
+        ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
+        ctx.dims = (NM, T, Tout, V, Cin, C)
+        if training:
+            ctx.save_for_backward(x, vals, Wc, z, a, u, out, rres, mean1, rstd1, mean2, rstd2, mean_r,
+                                  rstd_r, Wtt, Wr, bn1_w, bn2_w, bnr_w)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        if not ctx.training:
+            raise RuntimeError('istgcn: backward through eval-mode BatchNorm is not supported')
+        (x, vals, Wc, z, a, u, out, rres, mean1, rstd1, mean2, rstd2, mean_r, rstd_r, Wtt, Wr, bn1_w,
+         bn2_w, bnr_w) = ctx.saved_tensors
+        cfg, math, drop_p, seed = ctx.cfg, ctx.math, ctx.drop_p, ctx.seed
+        NM, T, Tout, V, Cin, C = ctx.dims
+        pat, s, idn = cfg.pattern, cfg.stride, cfg.ident
+        K, kt = pat.K, Wtt.shape[0]
+        pad = (kt - 1) // 2
+        R_in, R_out = NM * T * V, NM * Tout * V
+        dev = x.device
+        gout = gout.contiguous()
+        sums = torch.zeros(6, C, device=dev, dtype=torch.float64)
+        go = torch.empty_like(gout)
+        call('block_tail_bwd', gout, out, u, mean2, rstd2, rres, mean_r, rstd_r, go, sums[0], sums[1],
+             sums[2] if rres is not None else None, sums[3] if rres is not None else None,
+             i64(R_out), C, float(drop_p), u64(seed), step_counter(dev))
+        p2, m12, c2, dg2, db2 = _coeffs(5, C, dev)
+        call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2, C)
+        du = torch.empty_like(u)
+        call('bn_back_apply', go, u, p2, m12, c2, mean2, du, i64(R_out), C, float(drop_p), u64(seed),
+             step_counter(dev))
+        # gradient w.r.t. a = relu(BN1(z)): transposed taps, accumulated; weight / bias gradients
+        da = torch.zeros(NM, T, V, C, device=dev, dtype=torch.float32)
+        dWtt, dbt_vc = torch.zeros_like(Wtt), torch.zeros(V, C, device=dev)
+        for tap in range(kt):
+            off = tap - pad
+            if use_tc():
+                if s == 1:      # pure shift: read du at frame t - off, whole tiles leave through TMA
+                    call('gcn_tc', du, None, None, None, None, None, Wtt[tap], cfg.ones, idn.t_ptr,
+                         idn.t_src, idn.t_id, V, None, None, None if tap == 0 else da, da, None, None,
+                         None, NM * T, V, 1, C, C, C, T, T, 1, -off, 1)
+                else:
+                    call('gcn_tc', du, None, None, None, None, None, Wtt[tap], cfg.ones, idn.t_ptr,
+                         idn.t_src, idn.t_id, V, None, None, da, da, None, None, None, NM * Tout, V, 1,
+                         C, C, C, T, Tout, s, off, 2)
+                call('gcn_tc_dw', du, a, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWtt[tap],
+                     dbt_vc if tap == 0 else None, NM * Tout, V, 1, C, C, T, Tout, s, off)
+            else:
+                call('gcn_bwd_x', du, None, None, None, None, None, a, Wtt[tap], cfg.ones, idn.src_ptr,
+                     idn.src_kw, idn.src_id, V, da, da, None, NM * Tout, V, 1, C, C, T, Tout, s, off,
+                     math)
+                call('gcn_bwd_w', du, None, None, None, None, None, a, cfg.ones, idn.dst_ptr,
+                     idn.dst_src, idn.dst_id, V, dWtt[tap], dbt_vc if tap == 0 else None, NM * Tout, V,
+                     1, C, C, T, Tout, s, off, math)
+        g1 = torch.empty_like(z)
+        call('relu_bn_bwd', da, a, z, mean1, rstd1, g1, sums[4], sums[5], i64(R_in), C)
+        p1, m11, c1, dg1, db1 = _coeffs(5, C, dev)
+        call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, C)
+        gin = torch.empty_like(x)
+        dvals = torch.zeros_like(vals)
+        add_in = go if cfg.res_mode == 1 else None
+        dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, C, device=dev)
+        if use_tc():
+            dz = torch.empty_like(z)
+            call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
+                 pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, C, C, Cin, 0, 0, 1, 0, 0)
+            call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
+                 NM * T, V, K, Cin, C)
+            call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc, dbt,
+                 NM * T, V, K, Cin, C, 0, 0, 1, 0)
+        else:
+            call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
+                 pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, C, 0, 0, 1, 0, math)
+            call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src,
+                 pat.dst_id, pat.nnz, dWc, dbt, NM * T, V, K, Cin, C, 0, 0, 1, 0, math)
+        dWr = dbtr = dgr = dbr = None
+        if cfg.res_mode == 2:
+            pr, m1r, cr, dgr, dbr = _coeffs(5, C, dev)
+            call('bn_bwd_coeffs', sums[2], sums[3], f64(R_out), bnr_w, rstd_r, pr, m1r, cr, dgr, dbr, C)
+            dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, C, device=dev)
+            if use_tc():
+                dyr = torch.empty_like(rres)
+                call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
+                     idn.t_id, V, None, None, gin, gin, dyr, None, None, NM * Tout, V, 1, C, C, Cin,
+                     T, Tout, s, 0, 2)
+                call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr, dbtr,
+                     NM * Tout, V, 1, Cin, C, T, Tout, s, 0)
+            else:
+                call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr,
+                     idn.src_kw, idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, C, T, Tout, s,
+                     0, math)
+                call('gcn_bwd_w', go, rres, pr, m1r, cr, mean_r, x, cfg.ones, idn.dst_ptr, idn.dst_src,
+                     idn.dst_id, V, dWr, dbtr, NM * Tout, V, 1, Cin, C, T, Tout, s, 0, math)
+        return (gin, dvals, dWc, dbt, None, dg1, db1, dWtt, dbt_vc.sum(0), dg2, db2, dWr, dbtr, dgr,
+                dbr, None)
 
 
 class GraphConv(Function):
@@ -294,10 +473,10 @@ class GraphConv(Function):
         gz = gz.contiguous()
         gin, dvals = torch.empty_like(x), torch.zeros_like(vals)
         call('gcn_bwd_x', gz, None, None, None, None, None, x, Wc, vals, pat.src_ptr, pat.src_kw, pat.src_id,
-             pat.nnz, None, gin, dvals, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
+             pat.nnz, None, gin, dvals, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, 0, math)
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=x.device)
         call('gcn_bwd_w', gz, None, None, None, None, None, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
-             pat.nnz, dWc, dbt, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, math)
+             pat.nnz, dWc, dbt, NM * T, V, pat.K, Cin, Cout, 0, 0, 1, 0, math)
         return gin, dvals, dWc, dbt, None, None
 
 

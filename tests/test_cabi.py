@@ -65,9 +65,19 @@ def test_state_dict_layouts_match_oracle():
     """Key names, order and shapes of the drop-in models == the reference layouts that the
     oracle state (strict-loaded into the reference by make_golden.py) encodes."""
     import net.ist_gcn
+    import net.st_gcn
+    import net.st_gcn_msgcn
+    import net.st_gcn_mstcn
     import net.st_gcn_mstcn_1x1
+    import net.st_gcnold
     from oracle import model_ref
-    cases = [(net.ist_gcn.Model, 'ist_gcn', dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
+    assert net.st_gcnold.Model is net.st_gcn.Model
+    cases = [(net.st_gcn.Model, 'st_gcn', dict(layout='ntu-rgb+d', strategy='spatial'), 60),
+             (net.st_gcn.Model, 'st_gcn', dict(layout='openpose', strategy='uniform'), 400),
+             (net.st_gcn_msgcn.Model, 'st_gcn_msgcn',
+              dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
+             (net.st_gcn_mstcn.Model, 'st_gcn_mstcn', dict(layout='ntu-rgb+d', strategy='spatial'), 60),
+             (net.ist_gcn.Model, 'ist_gcn', dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
              (net.ist_gcn.Model, 'ist_gcn', dict(layout='openpose_sym', strategy='spatial_3_sym'), 400),
              (net.st_gcn_mstcn_1x1.Model, 'st_gcn_mstcn_1x1',
               dict(layout='ntu-rgb+d_sym', strategy='spatial_sym'), 60)]
@@ -82,6 +92,10 @@ def test_state_dict_layouts_match_oracle():
         m.load_state_dict(st, strict=True)
         m2 = cls(3, ncls, g_args, False)
         assert not any(k.startswith('edge_importance') for k in m2.state_dict())
+    import net.st_gcn_twostream
+    two = net.st_gcn_twostream.Model(3, 60, dict(layout='ntu-rgb+d', strategy='spatial'), True)
+    one = list(net.st_gcn.Model(3, 60, dict(layout='ntu-rgb+d', strategy='spatial'), True).state_dict())
+    assert list(two.state_dict()) == ['origin_stream.' + k for k in one] + ['motion_stream.' + k for k in one]
     n_params = sum(p.numel() for p in net.ist_gcn.Model(
         3, 60, dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), True).parameters())
     assert n_params == 1100789

@@ -277,18 +277,18 @@ def _load_case(name):
 
 
 @pytest.mark.parametrize('math', ['3xtf32', 'tf32'])
-@pytest.mark.parametrize('name', ['ist_gcn', 'ist_gcn_kinetics', 'st_gcn_mstcn_1x1'])
+@pytest.mark.parametrize('name', ['ist_gcn', 'ist_gcn_kinetics', 'st_gcn_mstcn_1x1', 'st_gcn',
+                                  'st_gcn_msgcn', 'st_gcn_mstcn'])
 def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
     """Logits, loss and EVERY parameter gradient of a training step vs the fixture generated
     from the reference's own modules and vs the live oracle."""
-    import net.ist_gcn
-    import net.st_gcn_mstcn_1x1
+    import importlib
     from oracle import model_ref
     mg, g_args, num_class, shape, state, x, label = _load_case(name)
     arch = name.replace('_kinetics', '')
     fix = np.load(os.path.join(golden_dir, 'model_%s.npz' % name))
     assert mg.state_digest(state) == str(fix['state_sha256'])
-    cls = net.ist_gcn.Model if arch == 'ist_gcn' else net.st_gcn_mstcn_1x1.Model
+    cls = importlib.import_module('net.' + arch).Model
     model = cls(shape[1], num_class, g_args, True)
     assert list(model.state_dict().keys()) == list(state.keys())
     model.load_state_dict(state, strict=True)
@@ -346,6 +346,34 @@ def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
     assert not report(errs, 1.0), report(errs, 1.0)
     cos = dot / (n1 ** 0.5 * n2 ** 0.5)
     assert cos > (0.9999 if math == '3xtf32' else 0.98), cos
+
+
+@pytest.mark.parametrize('math', ['3xtf32', 'tf32'])
+def test_twostream_vs_oracle(env, math):
+    """net.st_gcn_twostream: joint stream + motion stream (temporal second difference), logits
+    summed (st_gcn_twostream.py:19-28), eval and training mode vs the oracle."""
+    import net.st_gcn_twostream
+    from oracle import model_ref
+    mg, g_args, num_class, shape, state, x, label = _load_case('st_gcn')
+    other = model_ref.perturb_state(state, seed=5)
+    both = {}
+    both.update({'origin_stream.' + k: v for k, v in state.items()})
+    both.update({'motion_stream.' + k: v for k, v in other.items()})
+    model = net.st_gcn_twostream.Model(shape[1], num_class, g_args, True)
+    model.load_state_dict(both, strict=True)
+    dev = torch.device('cuda')
+    model = model.to(dev)
+    old = env.set_math(math)
+    try:
+        model.eval()
+        with torch.no_grad():
+            ev = model(x.to(dev))
+        model.train()
+        tr = model(x.to(dev))
+    finally:
+        env.set_math(old)
+    assert rel(ev, model_ref.twostream_forward(both, x, 'st_gcn', training=False)) < TOL[math]
+    assert rel(tr, model_ref.twostream_forward(both, x, 'st_gcn', training=True)) < TOL[math]
 
 
 def _oracle_grads(state, x, label, arch, dtype):

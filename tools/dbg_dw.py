@@ -16,7 +16,7 @@ for (Cin, Cout, frames) in [(64, 64, 10), (64, 64, 5), (128, 128, 7), (256, 256,
     x = torch.randn(frames * V, Cin, device=dev)
     dz = torch.randn(frames * V, Cout, device=dev)
     dW = torch.zeros(K * Cin, Cout, device=dev); db = torch.zeros(V, Cout, device=dev)
-    call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dW, db, frames, V, K, Cin, Cout)
+    call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dW, db, frames, V, K, Cin, Cout, 0, 0, 1, 0)
     torch.cuda.synchronize()
     xp = torch.einsum('fvc,kvw->fwkc', x.view(frames, V, Cin).double().cpu(), A.double())      # X'[f,w,k,ci]
     ref = torch.einsum('fwkc,fwo->kco', xp, dz.view(frames, V, Cout).double().cpu()).reshape(K * Cin, Cout)

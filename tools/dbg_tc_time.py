@@ -19,7 +19,7 @@ def run(A, Cin, Cout, frames, tag):
     bias = torch.randn(K, Cout, device=dev); colsum = A.sum(1).contiguous().to(dev); z = torch.empty(frames * V, Cout, device=dev)
     st = torch.zeros(2, Cout, device=dev, dtype=torch.float64)
     def f():
-        call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, bias, colsum, None, z, None, st[0], st[1], frames, V, K, Cin, Cin, Cout, 0, 0, 1, 0)
+        call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, bias, colsum, None, z, None, st[0], st[1], frames, V, K, Cin, Cin, Cout, 0, 0, 1, 0, 0)
     for _ in range(3): f()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
