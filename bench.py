@@ -149,11 +149,24 @@ def algorithmic_bytes(kernel, batch, shape):
     return per_launch
 
 
-def build_model(workload, device, dropout=0.5):
-    import net.ist_gcn
+ARCHS = ('ist_gcn', 'st_gcn_mstcn_1x1', 'st_gcn', 'st_gcn_msgcn', 'st_gcn_mstcn')
+
+
+def graph_args_for(workload, arch):
+    """The symmetric 4-partition graph for the Inception-GCN variants, the reference's default
+    3-partition 'spatial' graph of the same skeleton for the single-adjacency ones."""
+    g = dict(WORKLOADS[workload]['graph_args'])
+    if arch not in ('ist_gcn', 'st_gcn_msgcn'):
+        g = dict(layout=g['layout'].replace('_sym', ''), strategy='spatial')
+    return g
+
+
+def build_model(workload, device, dropout=0.5, arch='ist_gcn'):
+    import importlib
     from istgcn import trainer
     w = WORKLOADS[workload]
-    model = net.ist_gcn.Model(w['shape'][0], w['num_class'], w['graph_args'], True, dropout=dropout)
+    cls = importlib.import_module('net.' + arch).Model
+    model = cls(w['shape'][0], w['num_class'], graph_args_for(workload, arch), True, dropout=dropout)
     model.apply(trainer.weights_init)
     return model.to(device)
 
@@ -174,7 +187,7 @@ def run_istgcn(args):
     istgcn.set_math(args.math)
     w = WORKLOADS[args.workload]
     torch.manual_seed(0)
-    model = build_model(args.workload, dev)
+    model = build_model(args.workload, dev, arch=args.arch)
     dp.broadcast_state(model)
     tr = trainer.Trainer(model, base_lr=0.01, use_graph=not args.no_graph)
     torch.manual_seed(1000 + rank)
@@ -230,8 +243,9 @@ def run_istgcn(args):
     per_kernel = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in timing.items()}
     top = max(per_kernel, key=per_kernel.get)
     peak, peak_src = measured_peaks()
-    alg = algorithmic_bytes(top, B, w['shape'])
-    if top == 'gcn_tc':                  # the same entry point serves forward and input gradient
+    # the per-launch byte model below describes the IST-GCN block table only
+    alg = algorithmic_bytes(top, B, w['shape']) if args.arch == 'ist_gcn' else []
+    if alg and top == 'gcn_tc':          # the same entry point serves forward and input gradient
         alg = alg + algorithmic_bytes('gcn_tc_bwd', B, w['shape'])
     n_launch = len(timing[top])
     alg_total = sum(alg) * prof_steps if alg else None
@@ -281,12 +295,13 @@ def run_istgcn(args):
         fwd = world * B * args.steps / (e0.elapsed_time(e1) / 1e3)
 
     line = {
-        'metric': 'ist_gcn_train_clips_per_s', 'value': value, 'unit': 'clips/s',
+        'metric': '%s_train_clips_per_s' % args.arch, 'value': value, 'unit': 'clips/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
         'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'tf32' if args.math == 'tf32' else 'fp32(3xtf32)',
         'data': 'synthetic',
-        'config': {'workload': w['name'], 'clips_per_gpu': B, 'global_batch': B * world,
+        'config': {'workload': w['name'].replace('IST-GCN', args.arch) if args.arch != 'ist_gcn' else w['name'],
+                   'clips_per_gpu': B, 'global_batch': B * world,
                    'dropout': 0.5, 'optimizer': 'SGD(momentum .9, nesterov, wd 1e-4)',
                    'parallelism': 'dp%d' % world, 'activations': 'fp32 channels-last',
                    'cuda_graph': not args.no_graph,
@@ -313,9 +328,10 @@ def cpu_reference(args, steps, warmup):
     w = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    g = Graph(**w['graph_args'])
+    g = Graph(**graph_args_for(args.workload, args.arch))
     torch.manual_seed(0)
-    state = model_ref.make_state('ist_gcn', w['shape'][0], w['num_class'], g.A, g.A2, g.A3, seed=0)
+    state = model_ref.make_state(args.arch, w['shape'][0], w['num_class'], g.A, getattr(g, 'A2', None),
+                                 getattr(g, 'A3', None), seed=0)
     names = [k for k, v in state.items() if v.is_floating_point() and 'running' not in k
              and k not in ('A', 'A2', 'A3') and '.gcn.branch.bn.' not in k]
     for k in names:
@@ -327,7 +343,7 @@ def cpu_reference(args, steps, warmup):
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        out = model_ref.forward(state, x, 'ist_gcn', training=True, dropout=0.5)
+        out = model_ref.forward(state, x, args.arch, training=True, dropout=0.5)
         loss = F.cross_entropy(out, y)
         grads = torch.autograd.grad(loss, [state[k] for k in names], allow_unused=True)
         with torch.no_grad():
@@ -350,7 +366,7 @@ def run_reference(args):
     w = WORKLOADS[args.workload]
     steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
     base = cpu_reference(args, steps, warmup)
-    line = {'impl': 'reference', 'metric': 'ist_gcn_train_clips_per_s', 'value': base['value'],
+    line = {'impl': 'reference', 'metric': '%s_train_clips_per_s' % args.arch, 'value': base['value'],
             'unit': 'clips/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
             'ms_per_step': base['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
@@ -369,6 +385,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='istgcn', choices=['istgcn', 'reference'])
     ap.add_argument('--workload', default='ntu', choices=sorted(WORKLOADS))
+    ap.add_argument('--arch', default='ist_gcn', choices=ARCHS,
+                    help='network variant (the headline metric is quoted on ist_gcn)')
     ap.add_argument('--batch', type=int, default=64, help='clips per GPU')
     ap.add_argument('--math', default='tf32', choices=['tf32', '3xtf32'])
     ap.add_argument('--cpu-batch', type=int, default=4, help='clips per CPU-baseline step')
