@@ -11,17 +11,34 @@
 //               [32 ci x 32 c] (SWIZZLE_128B, K-major for both operands)
 //   warp 1      MMA issuer: M=128, N=K*32, K=8 per instruction; accumulator = G for one
 //               32-channel slice of ci and all K partitions, double buffered in TMEM
-//   warps 4-7   epilogue: tcgen05.ld (thread = row), 32-long dot products against the
-//               transposed x slice in shared memory, shared-memory atomics per non-zero
-//   warps 8-11  loaders: x slice -> shared memory, transposed ([ci][row], pitch 129)
+//   warps 4-7   epilogue: tcgen05.ld (thread = row), 32-long dot products against the x slice
+//               in shared memory (128-bit reads, four independent partial sums), shared-memory
+//               atomics per non-zero
+//   warps 8-11  loaders: x slice -> shared memory, [row][32 ci] with a 36-float pitch
 #include "tc_common.cuh"
 
 namespace istgcn {
 namespace tc {
 
+#ifndef ISTGCN_DA_PROF
+#define ISTGCN_DA_PROF 0      // 1: per-role clock64 accounting of CTA 0 (tools/dbg_da_time.py)
+#endif
+#if ISTGCN_DA_PROF
+__device__ unsigned long long g_prof_da[32];
+#define DPROF_DECL long long prof[32] = {0}
+#define DPROF_T0() long long _t0 = clock64()
+#define DPROF_ADD(i) do { long long _t1 = clock64(); prof[i] += _t1 - _t0; _t0 = _t1; } while (0)
+#define DPROF_OUT(lo, hi) do { if (blockIdx.x == 0) for (int _i = lo; _i <= hi; ++_i) g_prof_da[_i] += prof[_i]; } while (0)
+#else
+#define DPROF_DECL
+#define DPROF_T0()
+#define DPROF_ADD(i)
+#define DPROF_OUT(lo, hi)
+#endif
+
 constexpr int kThreadsDA = 384;
 constexpr int kStagesDA = 4;
-constexpr int kXT = 129;                       // pitch of the transposed x slice
+constexpr int kXP = 36;                        // row pitch of the x slice (floats)
 
 struct GcnDaParams {
     const float* x;                            // [rows][Cin]
@@ -35,7 +52,7 @@ struct SmemDA {
     static constexpr int stage_bytes = 2 * kAtomBytes;               // dz atom + weight atom
     static constexpr int ring_off = 0;
     static constexpr int xt_off = ring_off + kStagesDA * stage_bytes;
-    static constexpr int list_off = xt_off + 2 * 32 * kXT * 4;
+    static constexpr int list_off = xt_off + 2 * kAtomRows * kXP * 4;
     static constexpr int dv_off = list_off + kMaxNnz * 8 + (kMaxKV + 4) * 4;
     static constexpr int bar_off = dv_off + kMaxNnz * 4;
     static constexpr int kNumBars = 2 * kStagesDA + 4 + 4;
@@ -90,12 +107,15 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
     if (warp == 0) {
         if (lane == 0) {
             uint32_t it = 0;
+            DPROF_DECL; DPROF_T0();
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int row0 = tile * F * V;
                 for (int ch = 0; ch < nchunk; ++ch)
                     for (int ca = 0; ca < natom; ++ca, ++it) {
                         const int s = it % kStagesDA;
+                        DPROF_ADD(1);
                         mbar_wait(&empty[s], ((it / kStagesDA) & 1) ^ 1);
+                        DPROF_ADD(0);
                         uint8_t* dst = ring + s * L::stage_bytes;
                         mbar_arrive_expect_tx(&full[s], kAtomBytes + K * 32 * 128);
                         tma_load_2d(dst, &dzmap, &full[s], ca * 32, row0);
@@ -104,20 +124,26 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                                         k * Cin + ch * 32);
                     }
             }
+            DPROF_ADD(1); DPROF_OUT(0, 1);
         }
     } else if (warp == 1) {
         if (lane == 0) {
             const uint32_t idesc = make_idesc(128, NG, false, false);
             uint32_t it = 0, cit = 0;
+            DPROF_DECL; DPROF_T0();
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
                 for (int ch = 0; ch < nchunk; ++ch, ++cit) {
                     const int buf = cit & 1;
+                    DPROF_ADD(4);
                     mbar_wait(&t_empty[buf], ((cit >> 1) & 1) ^ 1);
+                    DPROF_ADD(2);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + buf * 128;
                     for (int ca = 0; ca < natom; ++ca, ++it) {
                         const int s = it % kStagesDA;
+                        DPROF_ADD(4);
                         mbar_wait(&full[s], (it / kStagesDA) & 1);
+                        DPROF_ADD(3);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(ring + s * L::stage_bytes);
                         const uint32_t b_addr = a_addr + kAtomBytes;
@@ -130,12 +156,14 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                     }
                     tc_commit(&t_full[buf]);
                 }
+            DPROF_ADD(4); DPROF_OUT(2, 4);
         }
     } else if (warp >= 4 && warp < 8) {
         // ---- epilogue: G rows from TMEM, dots against the transposed x slice
         const int ew = warp - 4;
         const int r = ew * 32 + lane;
         uint32_t cit = 0;
+        DPROF_DECL; DPROF_T0();
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int f0 = tile * F;
             const int valid = min(F, p.frames - f0) * V;
@@ -143,21 +171,28 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
             const int fr = r / V, w = r - fr * V;
             for (int ch = 0; ch < nchunk; ++ch, ++cit) {
                 const int buf = cit & 1;
+                DPROF_ADD(7);
                 mbar_wait(&t_full[buf], (cit >> 1) & 1);
+                DPROF_ADD(5);
                 mbar_wait(&x_full[buf], (cit >> 1) & 1);
+                DPROF_ADD(6);
                 tc_fence_after();
-                const float* xt = XT + buf * 32 * kXT + fr * V;
+                const float* xt = XT + buf * kAtomRows * kXP + fr * V * kXP;
                 for (int k = 0; k < K; ++k) {
                     float g[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 128 + k * 32, g);
                     if (ok) {
                         for (int j = s_ptr[k * V + w]; j < s_ptr[k * V + w + 1]; ++j) {
                             const int2 e = s_ent[j];
-                            const float* xr = xt + e.x;
-                            float acc = 0.f;
+                            const float* xr = xt + e.x * kXP;
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-                            for (int ci = 0; ci < 32; ++ci) acc = fmaf(g[ci], xr[ci * kXT], acc);
-                            atomicAdd(&s_dv[e.y], acc);
+                            for (int c4 = 0; c4 < 32; c4 += 4) {
+                                const float4 xv = *reinterpret_cast<const float4*>(xr + c4);
+                                a0 = fmaf(g[c4], xv.x, a0); a1 = fmaf(g[c4 + 1], xv.y, a1);
+                                a2 = fmaf(g[c4 + 2], xv.z, a2); a3 = fmaf(g[c4 + 3], xv.w, a3);
+                            }
+                            atomicAdd(&s_dv[e.y], (a0 + a1) + (a2 + a3));
                         }
                     }
                 }
@@ -166,18 +201,23 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                 if (lane == 0) { mbar_arrive(&t_empty[buf]); mbar_arrive(&x_empty[buf]); }
             }
         }
+        DPROF_ADD(7);
+        if (tid == 128) DPROF_OUT(5, 7);
     } else if (warp >= 8) {
         // ---- loaders: x slice [rows][32 ci] -> XT[ci][row]
         const int lt = tid - 8 * 32;
         uint32_t cit = 0;
+        DPROF_DECL; DPROF_T0();
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
             const int f0 = tile * F;
             const int valid = min(F, p.frames - f0) * V;
             const long long row0 = (long long)f0 * V;
             for (int ch = 0; ch < nchunk; ++ch, ++cit) {
                 const int buf = cit & 1;
+                DPROF_ADD(9);
                 mbar_wait(&x_empty[buf], ((cit >> 1) & 1) ^ 1);
-                float* xt = XT + buf * 32 * kXT;
+                DPROF_ADD(8);
+                float* xt = XT + buf * kAtomRows * kXP;
                 const int ci0 = ch * 32;
                 if ((Cin & 3) == 0) {
                     float4 v[8];
@@ -192,21 +232,20 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                     for (int u = 0; u < 8; ++u) {
                         const int i = lt + u * 128;
                         const int rr = i >> 3, c4 = (i & 7) * 4;
-                        xt[(c4 + 0) * kXT + rr] = v[u].x;
-                        xt[(c4 + 1) * kXT + rr] = v[u].y;
-                        xt[(c4 + 2) * kXT + rr] = v[u].z;
-                        xt[(c4 + 3) * kXT + rr] = v[u].w;
+                        st4(xt + rr * kXP + c4, v[u]);
                     }
                 } else {
                     for (int i = lt; i < kAtomRows * 32; i += 128) {
                         const int rr = i >> 5, c = i & 31;
-                        xt[c * kXT + rr] = (rr < valid && ci0 + c < Cin) ? p.x[(row0 + rr) * Cin + ci0 + c] : 0.f;
+                        xt[rr * kXP + c] = (rr < valid && ci0 + c < Cin) ? p.x[(row0 + rr) * Cin + ci0 + c] : 0.f;
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&x_full[buf]);
             }
         }
+        DPROF_ADD(9);
+        if (tid == 256) DPROF_OUT(8, 9);
     }
 
     tc_fence_before();
@@ -222,6 +261,16 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
 }  // namespace istgcn
 
 using namespace istgcn;
+
+#if ISTGCN_DA_PROF
+extern "C" int istgcn_debug_prof_da(unsigned long long* out) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, tc::g_prof_da, sizeof(unsigned long long) * 32);
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(tc::g_prof_da, z, sizeof(z));
+    return 0;
+}
+#endif
 
 // dvals[id] += sum_{f,ci} x[(f,v)][ci] * (dz Wc_k^T)[(f,w)][ci] over the non-zeros (k,v,w).
 // dz [frames*V][Cout] and Wc [K*Cin][Cout] row-major, 16-byte aligned, Cout % 32 == 0.

@@ -576,7 +576,7 @@ struct TcnBwdDownParams {
 };
 
 template <int NT, bool PRECISE>
-__global__ void __launch_bounds__(kThreads) tcn_bwd_down_kernel(TcnBwdDownParams p) {
+__global__ void __launch_bounds__(kThreads, 2) tcn_bwd_down_kernel(TcnBwdDownParams p) {
     constexpr int BP = NT * 8;
     constexpr int LDD = BP + 4;                 // dh1s as A (g-indexed), Wds as B^T (g-indexed)
     constexpr int LDA = 40;                     // a-tile as A^T (t-indexed)

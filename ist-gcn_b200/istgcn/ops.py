@@ -223,9 +223,12 @@ class STBlock(Function):
              float(drop_p), u64(seed), step_counter(dev), math)
         p1, m11, c1, dg1, db1 = _coeffs(5, Cout, dev)
         call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
-        gin = torch.empty_like(x)
+        # identity residual: the block-input gradient starts as `go` and the graph-conv input
+        # gradient is accumulated onto it in place (TMA reduce-add on the tcgen05 engine); every
+        # other reader of `go` has already run on this stream
+        gin = go if cfg.res_mode == 1 else torch.empty_like(x)
         dvals = torch.zeros_like(vals)
-        add_in = go if cfg.res_mode == 1 else None
+        add_in = gin if cfg.res_mode == 1 else None
         if use_tc():
             # input gradient on the tcgen05 engine: the forward kernel run on dz with the
             # transposed adjacency lists and Wc as the weight; adjacency gradient separately
@@ -408,9 +411,12 @@ class STBlockWide(Function):
         call('relu_bn_bwd', da, a, z, mean1, rstd1, g1, sums[4], sums[5], i64(R_in), C)
         p1, m11, c1, dg1, db1 = _coeffs(5, C, dev)
         call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, C)
-        gin = torch.empty_like(x)
+        # identity residual: the block-input gradient starts as `go` and the graph-conv input
+        # gradient is accumulated onto it in place (TMA reduce-add on the tcgen05 engine); every
+        # other reader of `go` has already run on this stream
+        gin = go if cfg.res_mode == 1 else torch.empty_like(x)
         dvals = torch.zeros_like(vals)
-        add_in = go if cfg.res_mode == 1 else None
+        add_in = gin if cfg.res_mode == 1 else None
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, C, device=dev)
         if use_tc():
             dz = torch.empty_like(z)
