@@ -1,0 +1,50 @@
+"""Drop-in for the reference ``net.st_gcn_mstcn_1x1_deep`` (net/st_gcn_mstcn_1x1_deep.py:13-269):
+the 13-block depth variant of ``net.st_gcn_mstcn_1x1`` (one more block per channel width).
+
+Same constructor, same sub-module names and registration order (=> same state_dict), same
+``forward(x)`` on (N, C, T, V, M); every block runs as fused sm_100a kernels."""
+import torch
+import torch.nn as nn
+
+from istgcn.modules import FusedModelMixin
+from net.utils.graph import Graph
+from net.st_gcn_mstcn_1x1 import st_gcn
+
+
+class Model(FusedModelMixin, nn.Module):
+    r"""Model(in_channels, num_class, graph_args, edge_importance_weighting, **kwargs)
+    (N, in_channels, T, V, M) -> (N, num_class)."""
+
+    def __init__(self, in_channels, num_class, graph_args, edge_importance_weighting, **kwargs):
+        super().__init__()
+        self.graph = Graph(**graph_args)
+        A = torch.tensor(self.graph.A, dtype=torch.float32, requires_grad=False)
+        self.register_buffer('A', A)
+        spatial_kernel_size = A.size(0)
+        temporal_kernel_size = 9
+        kernel_size = (temporal_kernel_size, spatial_kernel_size)
+        self.data_bn = nn.BatchNorm1d(in_channels * A.size(1))
+        kwargs0 = {k: v for k, v in kwargs.items() if k != 'dropout'}
+        self.st_gcn_networks = nn.ModuleList((
+            st_gcn(in_channels, 64, kernel_size, 1, residual=False, **kwargs0),
+            st_gcn(64, 64, kernel_size, 1, **kwargs),
+            st_gcn(64, 64, kernel_size, 1, **kwargs),
+            st_gcn(64, 64, kernel_size, 1, **kwargs),
+            st_gcn(64, 64, kernel_size, 1, **kwargs),
+            st_gcn(64, 128, kernel_size, 2, **kwargs),
+            st_gcn(128, 128, kernel_size, 1, **kwargs),
+            st_gcn(128, 128, kernel_size, 1, **kwargs),
+            st_gcn(128, 128, kernel_size, 1, **kwargs),
+            st_gcn(128, 256, kernel_size, 2, **kwargs),
+            st_gcn(256, 256, kernel_size, 1, **kwargs),
+            st_gcn(256, 256, kernel_size, 1, **kwargs),
+            st_gcn(256, 256, kernel_size, 1, **kwargs),
+        ))
+        if edge_importance_weighting:
+            self.edge_importance = nn.ParameterList([
+                nn.Parameter(torch.ones(self.A.size())) for _ in self.st_gcn_networks])
+        else:
+            self.edge_importance = [1] * len(self.st_gcn_networks)
+        self.mstcn_importance = nn.ParameterList([
+            nn.Parameter(torch.ones(3)) for _ in self.st_gcn_networks])
+        self.fcn = nn.Conv2d(256, num_class, kernel_size=1)

@@ -33,6 +33,11 @@ TEN = ((None, 64, 1, False), (64, 64, 1, True), (64, 64, 1, True), (64, 64, 1, T
 SEVEN = ((None, 64, 1, False), (64, 64, 1, True), (64, 64, 1, True), (64, 128, 2, True),
          (128, 128, 1, True), (128, 256, 2, True), (256, 256, 1, True))
 
+THIRTEEN = ((None, 64, 1, False), (64, 64, 1, True), (64, 64, 1, True), (64, 64, 1, True),
+            (64, 64, 1, True), (64, 128, 2, True), (128, 128, 1, True), (128, 128, 1, True),
+            (128, 128, 1, True), (128, 256, 2, True), (256, 256, 1, True), (256, 256, 1, True),
+            (256, 256, 1, True))
+
 # arch -> (graph conv kind, temporal kind, block table, has the unused per-block nn.Linear)
 ARCHS = {
     'st_gcn': ('single', 'plain', TEN, True),                 # net/st_gcnold.py
@@ -40,6 +45,10 @@ ARCHS = {
     'st_gcn_mstcn': ('single', 'incept_full', SEVEN, False),  # net/st_gcn_mstcn.py
     'st_gcn_mstcn_1x1': ('single', 'incept_1x1', TEN, False),  # net/st_gcn_mstcn_1x1.py
     'ist_gcn': ('inception', 'incept_1x1', TEN, False),       # composite, see module docstring
+    # depth variants: same blocks, different block lists
+    'st_gcn_mstcn_1x1_deep': ('single', 'incept_1x1', THIRTEEN, False),   # net/st_gcn_mstcn_1x1_deep.py:49-63
+    'st_gcn_deep_msgcn': ('inception', 'plain', THIRTEEN, False),         # net/st_gcn_deep_msgcn.py:60-77
+    'st_gcn_msgcn_new': ('inception', 'plain', SEVEN, False),             # net/st_gcn_msgcn_new.py:60-73
 }
 
 

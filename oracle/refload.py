@@ -60,7 +60,9 @@ def build_reference_model(arch, in_channels, num_class, graph_args, edge_importa
     import torch.nn as nn
     import torch.nn.functional as F
     table = {'st_gcn': 'net.st_gcnold', 'st_gcn_msgcn': 'net.st_gcn_msgcn',
-             'st_gcn_mstcn': 'net.st_gcn_mstcn', 'st_gcn_mstcn_1x1': 'net.st_gcn_mstcn_1x1'}
+             'st_gcn_mstcn': 'net.st_gcn_mstcn', 'st_gcn_mstcn_1x1': 'net.st_gcn_mstcn_1x1',
+             'st_gcn_mstcn_1x1_deep': 'net.st_gcn_mstcn_1x1_deep',
+             'st_gcn_deep_msgcn': 'net.st_gcn_deep_msgcn', 'st_gcn_msgcn_new': 'net.st_gcn_msgcn_new'}
     if arch in table:
         return load(table[arch]).Model(in_channels, num_class, graph_args,
                                        edge_importance_weighting, **kwargs)

@@ -44,6 +44,10 @@ MODEL_CASES = {
     'ist_gcn': (dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60, (2, 3, 24, 25, 2)),
     'ist_gcn_kinetics': (dict(layout='openpose_sym', strategy='spatial_3_sym'), 400,
                          (2, 3, 20, 18, 2)),
+    'st_gcn_mstcn_1x1_deep': (dict(layout='ntu-rgb+d_sym', strategy='spatial_sym'), 60,
+                              (2, 3, 16, 25, 2)),
+    'st_gcn_deep_msgcn': (dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60, (2, 3, 16, 25, 2)),
+    'st_gcn_msgcn_new': (dict(layout='openpose_sym', strategy='spatial_3_sym'), 60, (2, 3, 16, 18, 2)),
 }
 
 
@@ -80,16 +84,20 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     graph_mod = refload.load('net.utils.graph')
+    only = set(sys.argv[1:])            # optional: regenerate only the named model cases
     out = {}
-    for layout, strategy in GRAPH_CASES:
+    for layout, strategy in ([] if only else GRAPH_CASES):
         g = graph_mod.Graph(layout=layout, strategy=strategy)
         for name in ('A', 'A2', 'A3'):
             if hasattr(g, name):
                 out['%s|%s|%s' % (layout, strategy, name)] = np.ascontiguousarray(getattr(g, name))
-    np.savez_compressed(os.path.join(HERE, 'graphs.npz'), **out)
-    print('graphs.npz', len(out), 'arrays')
+    if not only:
+        np.savez_compressed(os.path.join(HERE, 'graphs.npz'), **out)
+        print('graphs.npz', len(out), 'arrays')
 
     for name, (g_args, num_class, shape) in MODEL_CASES.items():
+        if only and name not in only:
+            continue
         arch = name.replace('_kinetics', '')
         graph = graph_mod.Graph(**g_args)
         state = case_state(name, graph)

@@ -64,6 +64,7 @@ def test_no_cpu_fallback(lib_path):
 def test_state_dict_layouts_match_oracle():
     """Key names, order and shapes of the drop-in models == the reference layouts that the
     oracle state (strict-loaded into the reference by make_golden.py) encodes."""
+    import importlib
     import net.ist_gcn
     import net.st_gcn
     import net.st_gcn_msgcn
@@ -77,6 +78,12 @@ def test_state_dict_layouts_match_oracle():
              (net.st_gcn_msgcn.Model, 'st_gcn_msgcn',
               dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
              (net.st_gcn_mstcn.Model, 'st_gcn_mstcn', dict(layout='ntu-rgb+d', strategy='spatial'), 60),
+             (importlib.import_module('net.st_gcn_mstcn_1x1_deep').Model, 'st_gcn_mstcn_1x1_deep',
+              dict(layout='ntu-rgb+d_sym', strategy='spatial_sym'), 60),
+             (importlib.import_module('net.st_gcn_deep_msgcn').Model, 'st_gcn_deep_msgcn',
+              dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
+             (importlib.import_module('net.st_gcn_msgcn_new').Model, 'st_gcn_msgcn_new',
+              dict(layout='openpose_sym', strategy='spatial_3_sym'), 400),
              (net.ist_gcn.Model, 'ist_gcn', dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
              (net.ist_gcn.Model, 'ist_gcn', dict(layout='openpose_sym', strategy='spatial_3_sym'), 400),
              (net.st_gcn_mstcn_1x1.Model, 'st_gcn_mstcn_1x1',
