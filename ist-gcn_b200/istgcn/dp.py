@@ -31,6 +31,7 @@ class GradBuckets(object):
     def __init__(self, named_params, bucket_bytes=2 << 20, group=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         params = [(n, p) for n, p in named_params if p.requires_grad and not is_unused(n)]
         self.skipped = [n for n, p in named_params if p.requires_grad and is_unused(n)]
         self.buckets = []                       # list of dicts: flat, params, pending

@@ -111,3 +111,61 @@ class Trainer(object):
     def evaluate(self, x):
         self.model.eval()
         return self.model(x)
+
+    # ------------------------------------------------------------------ epoch driver
+    def train_epoch(self, loader, epoch=0, step=None, device=None):
+        """One pass of recognition.py:185-310 over ``loader`` (yields (data, label)): step LR
+        schedule, pinned non-blocking H2D, one ``step`` per batch.  The loss is read back once per
+        epoch, not once per iteration (the reference's per-iteration ``.item()`` is a host sync).
+        Returns the mean loss."""
+        device = device or next(self.model.parameters()).device
+        self.set_lr(self.base_lr * (0.1 ** sum(1 for s in (step or []) if epoch >= s)))
+        total, count = None, 0
+        for data, label in loader:
+            data = data.float().to(device, non_blocking=True)
+            label = label.long().to(device, non_blocking=True)
+            if self._static is not None and self._static[0].shape != data.shape:
+                self.invalidate_graph()             # ragged last batch: re-capture for its shape
+            loss = self.step(data, label).detach()
+            total = loss.clone() if total is None else total + loss
+            count += 1
+        return float(total.item()) / max(count, 1) if count else float('nan')
+
+    @torch.no_grad()
+    def test_epoch(self, loader, topk=(1, 5), device=None):
+        """recognition.py:312-345 + show_topk (:178-183): mean loss and top-k accuracies (%)."""
+        device = device or next(self.model.parameters()).device
+        self.model.eval()
+        results, labels, losses = [], [], []
+        for data, label in loader:
+            data = data.float().to(device, non_blocking=True)
+            label = label.long().to(device, non_blocking=True)
+            out = self.model(data)
+            losses.append(F.cross_entropy(out, label))
+            results.append(out)
+            labels.append(label)
+        result, label = torch.cat(results), torch.cat(labels)
+        rank = result.argsort(dim=1)
+        acc = {k: 100.0 * (rank[:, -k:] == label[:, None]).any(dim=1).float().mean().item() for k in topk}
+        return torch.stack(losses).mean().item(), acc
+
+    def fit(self, train_loader, num_epoch, step=None, start_epoch=0, save_interval=10, eval_interval=5,
+            test_loader=None, work_dir=None, log=print):
+        """processor/processor.py:159-226 (train phase): per epoch train, save
+        ``epoch{N}_model.pt`` every ``save_interval`` epochs and at the end, evaluate every
+        ``eval_interval`` epochs and at the end.  Rank 0 writes the files."""
+        import os
+        from . import checkpoint
+        history = []
+        for epoch in range(start_epoch, num_epoch):
+            log('Training epoch: {}'.format(epoch))
+            rec = {'epoch': epoch, 'train_loss': self.train_epoch(train_loader, epoch, step)}
+            last = epoch + 1 == num_epoch
+            if work_dir and self.buckets.rank == 0 and ((epoch + 1) % save_interval == 0 or last):
+                os.makedirs(work_dir, exist_ok=True)
+                checkpoint.save_model(self.model, os.path.join(work_dir, 'epoch{}_model.pt'.format(epoch + 1)))
+            if test_loader is not None and ((epoch + 1) % eval_interval == 0 or last):
+                log('Eval epoch: {}'.format(epoch))
+                rec['val_loss'], rec['acc'] = self.test_epoch(test_loader)
+            history.append(rec)
+        return history
