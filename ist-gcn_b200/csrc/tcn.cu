@@ -114,7 +114,7 @@ struct TcnUpParams {
     int NM, T, Tout, V, C, bp, stride, TT, tiles_per_sample;
 };
 
-constexpr int kUpRows = 256;   // output rows (frames*V) of one temporal tile
+constexpr int kUpRows = 128;   // output rows (frames*V) of one temporal tile
 
 template <int NT, bool PRECISE>
 __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
@@ -267,7 +267,7 @@ struct TcnBwdUpParams {
 };
 
 template <int NT, bool PRECISE>
-__global__ void __launch_bounds__(kThreads) tcn_bwd_up_kernel(TcnBwdUpParams p) {
+__global__ void __launch_bounds__(kThreads, 4) tcn_bwd_up_kernel(TcnBwdUpParams p) {
     constexpr int BP = NT * 8;
     constexpr int LDT = BP == 8 ? 8 : 24;       // h2s as A^T (t-indexed rows)
     constexpr int MAXCH = 8;                    // C <= 256 -> at most 8 column chunks of 32
@@ -576,7 +576,7 @@ struct TcnBwdDownParams {
 };
 
 template <int NT, bool PRECISE>
-__global__ void __launch_bounds__(kThreads, 2) tcn_bwd_down_kernel(TcnBwdDownParams p) {
+__global__ void __launch_bounds__(kThreads, 3) tcn_bwd_down_kernel(TcnBwdDownParams p) {
     constexpr int BP = NT * 8;
     constexpr int LDD = BP + 4;                 // dh1s as A (g-indexed), Wds as B^T (g-indexed)
     constexpr int LDA = 40;                     // a-tile as A^T (t-indexed)
@@ -772,7 +772,7 @@ ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* mean1, const float* s
         const int TI = (p.TT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)TI * V * ld_g(bp) + kUpRows * ld_g(bp) +
                                              kTaps * bp * ld_t(bp) + bp * (C + 8) + 4 * C);
-        const int grid = grid_for((long long)NM * p.tiles_per_sample, 2);
+        const int grid = grid_for((long long)NM * p.tiles_per_sample, 4);
 #define LAUNCH_UP(NT, PC)                                            \
     set_smem(tcn_up_kernel<NT, PC>, smem);                           \
     tcn_up_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
@@ -809,7 +809,7 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
                          (long long)NM * Tout * V, C, bp, drop_p, 1.f / (1.f - drop_p), drop_seed,
                          drop_step};
         const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * ld_t(bp) + 8 + bp * (C + 4) + C + bp);
-        const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 3);
+        const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 4);
 #define LAUNCH_BU(NT, PC)                                            \
     set_smem(tcn_bwd_up_kernel<NT, PC>, smem);                       \
     tcn_bwd_up_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
@@ -826,7 +826,7 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
         const int TO = (p.TT - 1 + 2 * kHalf) / stride + 2;
         const size_t smem = sizeof(float) * ((size_t)TO * V * ld_g(bp) + kUpRows * ld_t(bp) + 8 +
                                              kTaps * bp * ld_g(bp) + bp + 2) + kUpRows * sizeof(int2);
-        const int grid = grid_for((long long)NM * p.tiles_per_sample, 2);
+        const int grid = grid_for((long long)NM * p.tiles_per_sample, 4);
 #define LAUNCH_BT(NT, PC)                                            \
     set_smem(tcn_bwd_t_kernel<NT, PC>, smem);                        \
     tcn_bwd_t_kernel<NT, PC><<<grid, kThreads, smem, st>>>(p)
