@@ -11,7 +11,10 @@
 //               [32 ci x 32 c] (SWIZZLE_128B, K-major for both operands)
 //   warp 1      MMA issuer: M=128, N=K*32, K=8 per instruction; accumulator = G for one
 //               32-channel slice of ci and all K partitions, double buffered in TMEM
-//   warps 4-7   epilogue: tcgen05.ld (thread = row), 32-long dot products against the x slice
+//   warps 4-7, 12-23  epilogue, four teams of four warps; team t takes every fourth entry of
+//               each (k, w) list (the list lengths are skewed, max 12 vs mean 2.4, and a warp
+//               runs max-over-lanes iterations):
+//               tcgen05.ld (thread = row), 32-long dot products against the x slice
 //               in shared memory (128-bit reads, four independent partial sums), shared-memory
 //               atomics per non-zero
 //   warps 8-11  loaders: x slice -> shared memory, [row][32 ci] with a 36-float pitch
@@ -36,7 +39,8 @@ __device__ unsigned long long g_prof_da[32];
 #define DPROF_OUT(lo, hi)
 #endif
 
-constexpr int kThreadsDA = 384;
+constexpr int kTeamsDA = 4;                // epilogue warp teams (4 warps each)
+constexpr int kThreadsDA = (12 + 4 * (kTeamsDA - 1)) * 32;   // TMA, MMA, 2 idle, team 0, loaders, teams 1..
 constexpr int kStagesDA = 4;
 constexpr int kXP = 36;                        // row pitch of the x slice (floats)
 
@@ -92,8 +96,8 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
     if (tid == 0) {
         for (int i = 0; i < kStagesDA; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4);
-            mbar_init(&x_full[i], 4); mbar_init(&x_empty[i], 4);
+            mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * kTeamsDA);
+            mbar_init(&x_full[i], 4); mbar_init(&x_empty[i], 4 * kTeamsDA);
         }
         fence_barrier_init();
     }
@@ -158,9 +162,11 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                 }
             DPROF_ADD(4); DPROF_OUT(2, 4);
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ---- epilogue: G rows from TMEM, dots against the transposed x slice
-        const int ew = warp - 4;
+    } else if ((warp >= 4 && warp < 8) || warp >= 12) {
+        // ---- epilogue: G rows from TMEM, dots against the x slice; team t takes the entries
+        // beg + t, beg + t + kTeamsDA, ... of every (k, w) list
+        const int ew = warp & 3;
+        const int team = warp >= 12 ? 1 + ((warp - 12) >> 2) : 0;
         const int r = ew * 32 + lane;
         uint32_t cit = 0;
         DPROF_DECL; DPROF_T0();
@@ -182,7 +188,8 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                     float g[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + buf * 128 + k * 32, g);
                     if (ok) {
-                        for (int j = s_ptr[k * V + w]; j < s_ptr[k * V + w + 1]; ++j) {
+                        for (int j = s_ptr[k * V + w] + ((team + k) % kTeamsDA); j < s_ptr[k * V + w + 1];
+                             j += kTeamsDA) {
                             const int2 e = s_ent[j];
                             const float* xr = xt + e.x * kXP;
                             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -203,7 +210,7 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
         }
         DPROF_ADD(7);
         if (tid == 128) DPROF_OUT(5, 7);
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 12) {
         // ---- loaders: x slice [rows][32 ci] -> XT[ci][row]
         const int lt = tid - 8 * 32;
         uint32_t cit = 0;

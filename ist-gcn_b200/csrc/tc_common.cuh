@@ -248,7 +248,8 @@ __device__ __forceinline__ void aggregate_joint(float* __restrict__ A, const flo
         st4(A + (SW32 ? atom_index32(f * V + w, c4) : atom_index(f * V + w, c4)), acc[f]);
 }
 
-// dispatch on the number of frames per tile: 5 (V=25), 7 (V=18), 8 (V<=16), ...
+// dispatch on the number of frames: 5 (V=25), 7 (V=18), 8 (V<=16) per tile, or the share of one
+// aggregator team (a team working on frames [f0, f0+n) passes xs + f0*fstride and w + f0*V)
 template <bool SW32 = false>
 __device__ __forceinline__ void aggregate_joint_any(int F, float* __restrict__ A,
                                                     const float* __restrict__ xs,
@@ -259,6 +260,9 @@ __device__ __forceinline__ void aggregate_joint_any(int F, float* __restrict__ A
         case 7: aggregate_joint<7, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
         case 8: aggregate_joint<8, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
         case 6: aggregate_joint<6, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        case 3: aggregate_joint<3, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        case 2: aggregate_joint<2, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
+        case 1: aggregate_joint<1, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
         default: aggregate_joint<4, SW32>(A, xs, s_ent, beg, end, fstride, V, w, c4); break;
     }
 }
