@@ -198,6 +198,15 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
  *                  (drop_p, drop_seed, drop_step) applied (the tail's convention)
  *   relu_bn_bwd:   g1 = da where a > 0 else 0;  sg[c] += sum g1,  sgx[c] += sum g1*(z-mean1)*rstd1
  *                  (caller-zeroed doubles, the inputs of istgcn_bn_bwd_coeffs)                 */
+/* The same convolution as ONE tcgen05 implicit GEMM (csrc/tconv_tc.cu): both operands by TMA, tap
+ * `tap` = the activation box shifted by dir*(tap - pad) frames, out-of-range frames read as zeros.
+ *   out[(n,to,v)][co] = sum_tap sum_ci in[(n, to*stride + dir*(tap-pad), v)][ci] * w_rows[tap*Cout+co][ci]
+ *                       + bias[co]
+ * dir = +1: forward; dir = -1 (stride 1 only) with the transposed weights: input gradient.
+ * Needs Cin, Cout multiples of 32, Tout a multiple of floor(128/V); stat_* as in istgcn_gcn_tc. */
+int istgcn_tconv_tc(const float* in, const float* w_rows, const float* bias, float* out,
+                    double* stat_sum, double* stat_sumsq, int NM, int T, int Tout, int V, int Cin,
+                    int Cout, int kt, int stride, int dir, istgcn_stream_t s);
 int istgcn_bn_relu_apply(const float* z, const float* mean, const float* scale, const float* beta,
                          float* a, long long rows, int C, istgcn_stream_t s);
 int istgcn_bn_back_apply(const float* go, const float* u, const float* p, const float* m1,

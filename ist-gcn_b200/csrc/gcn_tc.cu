@@ -463,8 +463,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                   CUtensorMapFloatOOBfill);
 
-int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows,
-                    bool atom32) {
+static EncodeTiledFn encode_fn() {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void* sym = nullptr;
@@ -472,10 +471,17 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
         cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q);
         if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !sym) {
             set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
-            return ISTGCN_E_ARCH;
+            return nullptr;
         }
         fn = reinterpret_cast<EncodeTiledFn>(sym);
     }
+    return fn;
+}
+
+int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long long cols, int box_rows,
+                    bool atom32) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return ISTGCN_E_ARCH;
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
     cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
@@ -487,6 +493,28 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for [%lld x %lld] box %d", (int)r, rows, cols,
                   box_rows);
+        return ISTGCN_E_ARG;
+    }
+    return 0;
+}
+
+// Channels-last activation [NM][T][V][C] as a 4-D tensor (C, V, T, NM): box = 32 channels x V
+// joints x `frames` frames taken every `t_stride`-th frame (SWIZZLE_128B; out-of-range frames
+// read as zeros = the temporal padding).
+int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V, int C, int frames,
+                      int t_stride) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return ISTGCN_E_ARCH;
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)V, (cuuint64_t)T, (cuuint64_t)NM};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)V * C * 4, (cuuint64_t)T * V * C * 4};
+    cuuint32_t box[4] = {32u, (cuuint32_t)V, (cuuint32_t)((frames - 1) * t_stride + 1), 1u};
+    cuuint32_t estr[4] = {1u, 1u, (cuuint32_t)t_stride, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for frames map [%d x %d x %d x %d]", (int)r, NM, T,
+                  V, C);
         return ISTGCN_E_ARG;
     }
     return 0;

@@ -90,6 +90,16 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // every committed bulk store is complete (writes performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// 4-D tile load (coordinates fastest first), completes on `bar`
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6}], [%2];" ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {   // one warp
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -271,6 +281,9 @@ __device__ __forceinline__ void aggregate_joint_any(int F, float* __restrict__ A
 // 2-D fp32 row-major matrix [rows][cols] -> tiles of [box_rows][32 floats], SWIZZLE_128B.
 int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long long cols,
                     int box_rows, bool atom32 = false);
+// 4-D (C, V, T, NM) view of a channels-last activation: box of 32 channels x V x frames (strided)
+int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V, int C, int frames,
+                      int t_stride);
 
 }  // namespace tc
 }  // namespace istgcn

@@ -18,7 +18,7 @@ SYMBOLS = (
     'istgcn_bn_finalize', 'istgcn_bn_eval_coeffs', 'istgcn_bn_bwd_coeffs',
     'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
-    'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_relu_bn_bwd',
+    'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_relu_bn_bwd', 'istgcn_tconv_tc',
     'istgcn_block_tail_fwd', 'istgcn_block_tail_bwd', 'istgcn_dropout_mask',
     'istgcn_pool_fwd', 'istgcn_pool_bwd',
 )

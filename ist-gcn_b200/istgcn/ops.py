@@ -271,6 +271,12 @@ class STBlock(Function):
                 dbtr, dgr, dbr, None)
 
 
+def _tconv_fused_ok(C, Tout, V):
+    """Shapes the tcgen05 temporal-convolution kernel takes (csrc/tconv_tc.cu)."""
+    F = min(8, 128 // V)
+    return C % 32 == 0 and Tout % F == 0 and F * V > 96
+
+
 class STBlockWide(Function):
     """One baseline ST-GCN block with a FULL-WIDTH temporal convolution: graph conv -> BN -> ReLU
     -> Conv2d(C, C, (kt,1), (stride,1), (pad,0)) -> BN -> dropout -> + residual -> ReLU
@@ -310,12 +316,16 @@ class STBlockWide(Function):
         a = torch.empty_like(z)
         call('bn_relu_apply', z, mean1, scale1, bn1_b, a, i64(R_in), C)
         u = torch.empty(NM, Tout, V, C, device=dev, dtype=torch.float32)
+        fused = use_tc() and _tconv_fused_ok(C, Tout, V)
         if use_tc():
             Wrows = Wtt.detach().transpose(1, 2).contiguous()         # [kt][C(out)][C(in)]
             bt_k = bt.detach().view(1, C)
         else:
             bt_vc = bt.detach().unsqueeze(0).expand(V, C).contiguous()
-        for tap in range(kt):
+        if fused:       # one implicit GEMM: taps = shifted TMA boxes of the activation
+            call('tconv_tc', a, Wrows, bt.detach(), u, stats[2], stats[3], NM, T, Tout, V, C, C, kt,
+                 s, 1)
+        for tap in range(0 if fused else kt):
             first, last = tap == 0, tap == kt - 1
             ssum, ssq = (stats[2], stats[3]) if last else (None, None)
             if use_tc():
@@ -387,10 +397,15 @@ class STBlockWide(Function):
         # gradient w.r.t. a = relu(BN1(z)): transposed taps, accumulated; weight / bias gradients
         da = torch.zeros(NM, T, V, C, device=dev, dtype=torch.float32)
         dWtt, dbt_vc = torch.zeros_like(Wtt), torch.zeros(V, C, device=dev)
+        fused_dx = use_tc() and s == 1 and _tconv_fused_ok(C, T, V)
+        if fused_dx:    # transposed convolution = the same implicit GEMM with mirrored taps
+            call('tconv_tc', du, Wtt, None, da, None, None, NM, T, T, V, C, C, kt, 1, -1)
         for tap in range(kt):
             off = tap - pad
             if use_tc():
-                if s == 1:      # pure shift: read du at frame t - off, whole tiles leave through TMA
+                if fused_dx:
+                    pass
+                elif s == 1:      # pure shift: read du at frame t - off, whole tiles leave through TMA
                     call('gcn_tc', du, None, None, None, None, None, Wtt[tap], cfg.ones, idn.t_ptr,
                          idn.t_src, idn.t_id, V, None, None, None if tap == 0 else da, da, None, None,
                          None, NM * T, V, 1, C, C, C, T, T, 1, -off, 1)

@@ -377,6 +377,78 @@ def test_twostream_vs_oracle(env, math):
     assert rel(tr, model_ref.twostream_forward(both, x, 'st_gcn', training=True)) < TOL[math]
 
 
+@pytest.mark.parametrize('shape', [(3, 20, 25, 64, 9, 1, 1), (3, 20, 25, 64, 9, 2, 1),
+                                   (2, 40, 25, 128, 15, 1, 1), (2, 10, 25, 256, 9, 1, 1),
+                                   (3, 14, 18, 64, 9, 1, 1), (3, 20, 25, 64, 9, 1, -1),
+                                   (2, 10, 25, 256, 15, 1, -1)])
+def test_tconv_tc_vs_conv2d(env, shape):
+    """The tcgen05 implicit-GEMM temporal convolution (csrc/tconv_tc.cu) vs F.conv2d in fp64:
+    forward with stride 1 / 2 (outputs and BatchNorm sums) and the stride-1 input gradient."""
+    from istgcn._lib import call
+    NM, T, V, C, kt, s, direction = shape
+    dev = torch.device('cuda')
+    gen = torch.Generator().manual_seed(3)
+    Tout, pad = (T - 1) // s + 1, (kt - 1) // 2
+    w = (torch.randn(C, C, kt, 1, generator=gen) * 0.05).to(dev)            # (co, ci, kt, 1)
+    if direction == 1:
+        b = torch.randn(C, generator=gen).to(dev)
+        x = torch.randn(NM, T, V, C, generator=gen).to(dev)
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), b.double(), stride=(s, 1),
+                       padding=(pad, 0)).permute(0, 2, 3, 1)
+        wrows = w[:, :, :, 0].permute(2, 0, 1).contiguous().view(kt * C, C)   # [tap][co][ci]
+        out = torch.empty(NM, Tout, V, C, device=dev)
+        st = torch.zeros(2, C, device=dev, dtype=torch.float64)
+        call('tconv_tc', x, wrows, b, out, st[0], st[1], NM, T, Tout, V, C, C, kt, s, 1)
+        assert rel(out, ref) < 2e-3
+        assert rel(st[0], ref.sum((0, 1, 2)), 1e-3 * ref.abs().sum().item()) < 2e-3
+        assert rel(st[1], ref.pow(2).sum((0, 1, 2))) < 2e-3
+    else:
+        du = torch.randn(NM, T, V, C, generator=gen).to(dev)
+        a = torch.randn(NM, T, V, C, generator=gen).to(dev).double().requires_grad_(True)
+        F.conv2d(a.permute(0, 3, 1, 2), w.double(), None, padding=(pad, 0)).permute(0, 2, 3, 1) \
+            .backward(du.double())
+        wt = w[:, :, :, 0].permute(2, 1, 0).contiguous().view(kt * C, C)      # [tap][ci][co]
+        da = torch.empty(NM, T, V, C, device=dev)
+        call('tconv_tc', du, wt, None, da, None, None, NM, T, T, V, C, C, kt, 1, -1)
+        assert rel(da, a.grad) < 2e-3
+
+
+@pytest.mark.parametrize('arch', ['st_gcn', 'st_gcn_mstcn'])
+def test_fused_temporal_conv_model_vs_oracle(env, arch):
+    """T = 20 makes every block's Tout a multiple of the 5-frame tile, so the full-width variants
+    take the fused tcgen05 temporal convolution (forward everywhere, input gradient in the
+    stride-1 blocks): logits, loss and gradients vs the fp64 oracle, 'tf32' bounds."""
+    import importlib
+    from oracle import model_ref
+    mg, g_args, num_class, shape, state, _, label = _load_case(arch)
+    x = torch.randn(shape[0], shape[1], 20, shape[3], shape[4], generator=torch.Generator().manual_seed(5))
+    model = importlib.import_module('net.' + arch).Model(shape[1], num_class, g_args, True)
+    model.load_state_dict(state, strict=True)
+    dev = torch.device('cuda')
+    model = model.to(dev).train()
+    from istgcn import _lib
+    old = env.set_math('tf32')
+    try:
+        _lib.timing = {}
+        logits = model(x.to(dev))
+        F.cross_entropy(logits, label.to(dev)).backward()
+        used, _lib.timing = _lib.timing, None
+    finally:
+        env.set_math(old)
+    assert 'tconv_tc' in used and len(used['tconv_tc']) >= len(model.st_gcn_networks)
+    ref = model_ref.forward({k: v.double() if v.is_floating_point() else v for k, v in state.items()},
+                            x.double(), arch, training=True)
+    assert rel(logits, ref) < TOL['tf32']
+    g64 = _oracle_grads(state, x, label, arch, torch.float64)
+    dot = n1 = n2 = 0.0
+    for k, prm in model.named_parameters():
+        if k not in g64:
+            continue
+        mine = prm.grad.detach().cpu().double()
+        dot += (mine * g64[k]).sum().item(); n1 += mine.pow(2).sum().item(); n2 += g64[k].pow(2).sum().item()
+    assert dot / (n1 ** 0.5 * n2 ** 0.5) > 0.98
+
+
 def _oracle_grads(state, x, label, arch, dtype):
     from oracle import model_ref
     lv = {k: (v.detach().clone().to(dtype).requires_grad_(True)
