@@ -207,6 +207,13 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
 int istgcn_tconv_tc(const float* in, const float* w_rows, const float* bias, float* out,
                     double* stat_sum, double* stat_sumsq, int NM, int T, int Tout, int V, int Cin,
                     int Cout, int kt, int stride, int dir, istgcn_stream_t s);
+/* Weight gradient of the same convolution on the tcgen05 engine (csrc/tconv_dw_tc.cu):
+ *   dW[tap*Cin + ci][co] += sum_{n,to,v} a[(n, to*stride + tap - pad, v)][ci] * du[(n,to,v)][co]
+ *   dbias_vc[v][co]      += sum_{n,to} du[(n,to,v)][co]                       (may be NULL)
+ * a [NM][T][V][Cin], du [NM][Tout][V][Cout]; outputs caller-zeroed.  Cin, Cout multiples of 32,
+ * Cout <= 128 or a multiple of 128.                                                           */
+int istgcn_tconv_dw_tc(const float* a, const float* du, float* dW, float* dbias_vc, int NM, int T,
+                       int Tout, int V, int Cin, int Cout, int kt, int stride, istgcn_stream_t s);
 int istgcn_bn_relu_apply(const float* z, const float* mean, const float* scale, const float* beta,
                          float* a, long long rows, int C, istgcn_stream_t s);
 int istgcn_bn_back_apply(const float* go, const float* u, const float* p, const float* m1,

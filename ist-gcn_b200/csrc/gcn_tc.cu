@@ -502,7 +502,7 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
 // joints x `frames` frames taken every `t_stride`-th frame (SWIZZLE_128B; out-of-range frames
 // read as zeros = the temporal padding).
 int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V, int C, int frames,
-                      int t_stride) {
+                      int t_stride, bool atom32) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return ISTGCN_E_ARCH;
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)V, (cuuint64_t)T, (cuuint64_t)NM};
@@ -510,7 +510,8 @@ int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V,
     cuuint32_t box[4] = {32u, (cuuint32_t)V, (cuuint32_t)((frames - 1) * t_stride + 1), 1u};
     cuuint32_t estr[4] = {1u, 1u, (cuuint32_t)t_stride, 1u};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d) for frames map [%d x %d x %d x %d]", (int)r, NM, T,

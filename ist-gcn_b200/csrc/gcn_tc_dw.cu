@@ -254,6 +254,16 @@ __global__ void frame_colsum_kernel(const float* __restrict__ in, float* __restr
     }
 }
 
+int launch_frame_colsum(const float* in, float* out, int frames, int n, cudaStream_t st) {
+    int slabs = (num_sms() * 4 * 256) / (n / 4 > 0 ? n / 4 : 1);
+    if (slabs < 1) slabs = 1;
+    if (slabs > frames) slabs = frames;
+    const int fpc = (frames + slabs - 1) / slabs;
+    dim3 grid((n / 4 + 255) / 256, (frames + fpc - 1) / fpc);
+    frame_colsum_kernel<<<grid, 256, 0, st>>>(in, out, frames, n, fpc);
+    return finish_launch("frame_colsum");
+}
+
 }  // namespace tc
 }  // namespace istgcn
 
@@ -289,15 +299,7 @@ ISTGCN_API int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* va
     if (nx > p.tiles) nx = p.tiles;
     tc::gcn_tc_dw_kernel<<<dim3(nx, groups), tc::kThreadsDW, tc::SmemDW::total, st>>>(dzmap, p);
     if (int e = finish_launch("gcn_tc_dw")) return e;
-    if (dbiasterm) {
-        const int n = V * Cout;
-        int slabs = (num_sms() * 4 * 256) / (n / 4 > 0 ? n / 4 : 1);
-        if (slabs < 1) slabs = 1;
-        if (slabs > frames) slabs = frames;
-        const int fpc = (frames + slabs - 1) / slabs;
-        dim3 grid((n / 4 + 255) / 256, (frames + fpc - 1) / fpc);
-        tc::frame_colsum_kernel<<<grid, 256, 0, st>>>(dz, dbiasterm, frames, n, fpc);
-        if (int e = finish_launch("frame_colsum")) return e;
-    }
+    if (dbiasterm)
+        if (int e = tc::launch_frame_colsum(dz, dbiasterm, frames, V * Cout, st)) return e;
     return 0;
 }

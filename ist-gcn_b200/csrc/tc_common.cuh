@@ -283,7 +283,9 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
                     int box_rows, bool atom32 = false);
 // 4-D (C, V, T, NM) view of a channels-last activation: box of 32 channels x V x frames (strided)
 int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V, int C, int frames,
-                      int t_stride);
+                      int t_stride, bool atom32 = false);
+// out[j] += sum_f in[f][j], j < n (gcn_tc_dw.cu)
+int launch_frame_colsum(const float* in, float* out, int frames, int n, cudaStream_t st);
 
 }  // namespace tc
 }  // namespace istgcn

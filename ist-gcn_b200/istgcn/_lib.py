@@ -19,6 +19,7 @@ SYMBOLS = (
     'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
     'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_relu_bn_bwd', 'istgcn_tconv_tc',
+    'istgcn_tconv_dw_tc',
     'istgcn_block_tail_fwd', 'istgcn_block_tail_bwd', 'istgcn_dropout_mask',
     'istgcn_pool_fwd', 'istgcn_pool_bwd',
 )
@@ -67,7 +68,7 @@ def _conv(a):
 
 # kernels launched per C-ABI call (tcn_fwd = down + up, tcn_bwd = up + temporal + down,
 # pool_fwd = kernel behind a memset) -- used for the ``gpu_launches`` count of bench.py
-KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2}
+KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2, 'tconv_dw_tc': 2}
 launch_count = 0          # kernels launched through this binding since import
 timing = None             # set to a dict by bench.py: name -> list of (start_event, end_event)
 

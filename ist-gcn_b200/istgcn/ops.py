@@ -400,6 +400,9 @@ class STBlockWide(Function):
         fused_dx = use_tc() and s == 1 and _tconv_fused_ok(C, T, V)
         if fused_dx:    # transposed convolution = the same implicit GEMM with mirrored taps
             call('tconv_tc', du, Wtt, None, da, None, None, NM, T, T, V, C, C, kt, 1, -1)
+        fused_dw = use_tc() and C % 32 == 0 and (C <= 128 or C % 128 == 0)
+        if fused_dw:    # all taps of the weight gradient in one kernel (accumulators in TMEM)
+            call('tconv_dw_tc', a, du, dWtt, dbt_vc, NM, T, Tout, V, C, C, kt, s)
         for tap in range(kt):
             off = tap - pad
             if use_tc():
@@ -413,8 +416,9 @@ class STBlockWide(Function):
                     call('gcn_tc', du, None, None, None, None, None, Wtt[tap], cfg.ones, idn.t_ptr,
                          idn.t_src, idn.t_id, V, None, None, da, da, None, None, None, NM * Tout, V, 1,
                          C, C, C, T, Tout, s, off, 2)
-                call('gcn_tc_dw', du, a, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWtt[tap],
-                     dbt_vc if tap == 0 else None, NM * Tout, V, 1, C, C, T, Tout, s, off)
+                if not fused_dw:
+                    call('gcn_tc_dw', du, a, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWtt[tap],
+                         dbt_vc if tap == 0 else None, NM * Tout, V, 1, C, C, T, Tout, s, off)
             else:
                 call('gcn_bwd_x', du, None, None, None, None, None, a, Wtt[tap], cfg.ones, idn.src_ptr,
                      idn.src_kw, idn.src_id, V, da, da, None, NM * Tout, V, 1, C, C, T, Tout, s, off,

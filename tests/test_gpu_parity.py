@@ -413,6 +413,30 @@ def test_tconv_tc_vs_conv2d(env, shape):
         assert rel(da, a.grad) < 2e-3
 
 
+@pytest.mark.parametrize('shape', [(3, 20, 25, 64, 9, 1), (3, 21, 25, 64, 9, 2), (2, 13, 25, 128, 15, 1),
+                                   (2, 10, 25, 256, 9, 1), (3, 14, 18, 64, 9, 1)])
+def test_tconv_dw_tc_vs_conv2d(env, shape):
+    """Weight / bias gradient of the temporal convolution on the tcgen05 engine
+    (csrc/tconv_dw_tc.cu) vs autograd of F.conv2d in fp64, incl. stride 2 with an odd T and
+    clip lengths that are not a multiple of the K-tile."""
+    from istgcn._lib import call
+    NM, T, V, C, kt, s = shape
+    dev = torch.device('cuda')
+    gen = torch.Generator().manual_seed(4)
+    Tout, pad = (T - 1) // s + 1, (kt - 1) // 2
+    a = torch.randn(NM, T, V, C, generator=gen).to(dev)
+    du = torch.randn(NM, Tout, V, C, generator=gen).to(dev)
+    w = torch.zeros(C, C, kt, 1, device=dev, dtype=torch.float64, requires_grad=True)
+    F.conv2d(a.permute(0, 3, 1, 2).double(), w, None, stride=(s, 1), padding=(pad, 0)) \
+        .permute(0, 2, 3, 1).backward(du.double())
+    ref = w.grad[:, :, :, 0].permute(2, 1, 0).contiguous()                 # [tap][ci][co]
+    dW = torch.zeros(kt, C, C, device=dev)
+    db = torch.zeros(V, C, device=dev)
+    call('tconv_dw_tc', a, du, dW, db, NM, T, Tout, V, C, C, kt, s)
+    assert rel(dW, ref) < 2e-3
+    assert rel(db, du.double().sum((0, 1))) < 1e-5
+
+
 @pytest.mark.parametrize('arch', ['st_gcn', 'st_gcn_mstcn'])
 def test_fused_temporal_conv_model_vs_oracle(env, arch):
     """T = 20 makes every block's Tout a multiple of the 5-frame tile, so the full-width variants
@@ -436,6 +460,7 @@ def test_fused_temporal_conv_model_vs_oracle(env, arch):
     finally:
         env.set_math(old)
     assert 'tconv_tc' in used and len(used['tconv_tc']) >= len(model.st_gcn_networks)
+    assert len(used.get('tconv_dw_tc', [])) == len(model.st_gcn_networks)
     ref = model_ref.forward({k: v.double() if v.is_floating_point() else v for k, v in state.items()},
                             x.double(), arch, training=True)
     assert rel(logits, ref) < TOL['tf32']

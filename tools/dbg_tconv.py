@@ -39,6 +39,37 @@ check(2, 10, 25, 256, 9, 1, 1)
 check(3, 14, 18, 64, 9, 1, 1)
 check(3, 20, 25, 64, 9, 1, -1)
 check(2, 10, 25, 256, 15, 1, -1)
+def check_dw(NM, T, V, C, kt, s):
+    Tout = (T - 1) // s + 1
+    pad = (kt - 1) // 2
+    a = torch.randn(NM, T, V, C, device=dev); du = torch.randn(NM, Tout, V, C, device=dev)
+    w = torch.zeros(C, C, kt, 1, device=dev, dtype=torch.float64, requires_grad=True)
+    y = F.conv2d(a.permute(0, 3, 1, 2).double(), w, None, stride=(s, 1), padding=(pad, 0)).permute(0, 2, 3, 1)
+    y.backward(du.double())
+    ref = w.grad[:, :, :, 0].permute(2, 1, 0).contiguous()       # [tap][ci][co]
+    dW = torch.zeros(kt, C, C, device=dev); db = torch.zeros(V, C, device=dev)
+    call('tconv_dw_tc', a, du, dW, db, NM, T, Tout, V, C, C, kt, s)
+    torch.cuda.synchronize()
+    err = ((dW.double() - ref).abs().max() / ref.abs().max()).item()
+    berr = ((db.double() - du.double().sum((0, 1))).abs().max() / du.double().sum((0, 1)).abs().max()).item()
+    print('dW  NM %d T %d V %d C %d kt %d s %d: err %.2e bias err %.2e' % (NM, T, V, C, kt, s, err, berr))
+check_dw(3, 20, 25, 64, 9, 1)
+check_dw(3, 21, 25, 64, 9, 2)
+check_dw(2, 13, 25, 128, 15, 1)
+check_dw(2, 10, 25, 256, 9, 1)
+check_dw(3, 14, 18, 64, 9, 1)
+for C, T in [(64, 300), (128, 150), (256, 75)]:
+    NM, V, kt = 128, 25, 9
+    a = torch.randn(NM, T, V, C, device=dev); du = torch.randn(NM, T, V, C, device=dev)
+    dW = torch.zeros(kt, C, C, device=dev)
+    f = lambda: call('tconv_dw_tc', a, du, dW, None, NM, T, T, V, C, C, kt, 1)
+    for _ in range(3): f()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(10): f()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print('dW C %3d T %3d: %.3f ms  %.1f TFLOP/s' % (C, T, ms, 2.0 * NM * T * V * C * C * kt / ms / 1e9))
 # timing at bench shapes
 for C, T in [(64, 300), (128, 150), (256, 75)]:
     NM, V, kt = 128, 25, 9
