@@ -4,9 +4,11 @@
 //
 //     OUT[(n,to,v)][co] = sum_tap sum_ci IN[(n, to*stride + dir*(tap - pad), v)][ci] * W[tap][co][ci]
 //
-// dir = +1 is the forward convolution; dir = -1 with the transposed weights is the input gradient
-// of a stride-1 convolution.  Both operands come straight from TMA: the activation is a 4-D tensor
-// (C, V, T, NM), a tile is F = floor(128/V) whole frames of one clip, and tap `tap` of that tile
+// dir = +1 is the forward convolution; dir = -1 with the transposed weights is the input gradient.
+// For stride 2 the input gradient splits by the parity q of the input frame ti = 2j + q: only the
+// taps with q + pad - tap even reach it, from output frame j + (q + pad - tap)/2 -- two launches
+// of the same kernel with a tap table, whose tiles leave through a frame-strided 4-D TMA store.
+// Both operands come straight from TMA: the activation is a 4-D tensor (C, V, T, NM), a tile is F = floor(128/V) whole frames of one clip, and tap `tap` of that tile
 // is simply the same box shifted by `tap - pad` frames -- frames outside [0, T) are out of bounds
 // for the tensor map and read as zeros, which IS the temporal zero padding.  A temporal stride is
 // the tensor map's element stride in the T dimension.
@@ -28,7 +30,10 @@ struct TconvParams {
     const float* bias;            // [Cout] or NULL
     float* out;                   // [NM*Tout*V][Cout]
     double *stat_sum, *stat_sumsq;
-    int NM, T, Tout, V, Cin, Cout, kt, stride, dir, tiles, tiles_per_clip;
+    int NM, V, Cin, Cout, tiles, tiles_per_clip;
+    int in_step;                  // input frame of a tile's first output frame = to0 * in_step + tap_off
+    int ntaps, tap_w[16], tap_off[16];   // weight block and frame offset of every contributing tap
+    int out4d, out_q, out_step;   // 4-D strided store: output frame = out_q + out_step * to
 };
 
 template <int NCOLS>
@@ -50,7 +55,7 @@ template <int NCOLS>
 __global__ void __launch_bounds__(kThreadsTV, 1)
 tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap wmap,
                 const __grid_constant__ CUtensorMap omap, const __grid_constant__ CUtensorMap omap_last,
-                TconvParams p) {
+                const __grid_constant__ CUtensorMap omap4, TconvParams p) {
     using L = SmemTV<NCOLS>;
     constexpr int kStages = L::kStages;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -69,7 +74,6 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     const int V = p.V, Cout = p.Cout;
     const int F = (kAtomRows / V) > 8 ? 8 : (kAtomRows / V);
     const int nchunk = p.Cin / 32;
-    const int pad = (p.kt - 1) / 2;
     const int n0 = blockIdx.y * NCOLS;
     const uint32_t a_bytes = (uint32_t)(F * V) * 128u;
 
@@ -86,7 +90,7 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&amap); tma_prefetch_desc(&wmap);
-        tma_prefetch_desc(&omap); tma_prefetch_desc(&omap_last);
+        tma_prefetch_desc(&omap); tma_prefetch_desc(&omap_last); tma_prefetch_desc(&omap4);
     }
     if (warp == 1) tmem_alloc(tmem_slot, 2 * NCOLS);
     fence_proxy_async();
@@ -101,15 +105,15 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int n = tile / p.tiles_per_clip;
                 const int to0 = (tile - n * p.tiles_per_clip) * F;
-                for (int tap = 0; tap < p.kt; ++tap) {
-                    const int t_first = to0 * p.stride + p.dir * (tap - pad);
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    const int t_first = to0 * p.in_step + p.tap_off[tap];
                     for (int ch = 0; ch < nchunk; ++ch, ++it) {
                         const int s = it % kStages;
                         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
                         uint8_t* dst = ring + s * L::stage_bytes;
                         mbar_arrive_expect_tx(&full[s], a_bytes + L::kBAtomBytes);
                         tma_load_4d(dst, &amap, &full[s], ch * 32, 0, t_first, n);
-                        tma_load_2d(dst + kAtomBytes, &wmap, &full[s], ch * 32, tap * Cout + n0);
+                        tma_load_2d(dst + kAtomBytes, &wmap, &full[s], ch * 32, p.tap_w[tap] * Cout + n0);
                     }
                 }
             }
@@ -123,7 +127,7 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                 mbar_wait(&t_empty[buf], ((tcount >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + buf * NCOLS;
-                const int nst = p.kt * nchunk;
+                const int nst = p.ntaps * nchunk;
                 for (int st = 0; st < nst; ++st, ++it) {
                     const int s = it % kStages;
                     mbar_wait(&full[s], (it / kStages) & 1);
@@ -148,6 +152,8 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
         for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
             const int buf = tcount & 1;
             const long long row0 = (long long)tile * F * V;      // tiles never straddle clips
+            const int cn = tile / p.tiles_per_clip;
+            const int ct = p.out_q + p.out_step * (tile - cn * p.tiles_per_clip) * F;
             const bool ok = r < F * V;
             mbar_wait(&t_full[buf], (tcount >> 1) & 1);
             tc_fence_after();
@@ -160,17 +166,32 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                     const float4 bv = *reinterpret_cast<const float4*>(s_bias + c0 + j);
                     v[j] += bv.x; v[j + 1] += bv.y; v[j + 2] += bv.z; v[j + 3] += bv.w;
                 }
-                if (lane == 0) bulk_wait_read();
-                __syncwarp();
+                if (p.out4d) {
+                    // the four warps' staging areas are one [128 rows][128 B] SWIZZLE_128B tile:
+                    // one frame-strided 4-D store per 32 columns, issued by warp 4
+                    if (ew == 0 && lane == 0) bulk_wait_read();
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                } else {
+                    if (lane == 0) bulk_wait_read();
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
                         make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 fence_proxy_async();
-                __syncwarp();
-                if (lane == 0 && cg < Cout) {
-                    tma_store_2d(stage, om, cg, (int)(row0 + ew * 32));
-                    bulk_commit();
+                if (p.out4d) {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (ew == 0 && lane == 0 && cg < Cout) {
+                        tma_store_4d(smem + L::out_off, &omap4, cg, 0, ct, cn);
+                        bulk_commit();
+                    }
+                } else {
+                    __syncwarp();
+                    if (lane == 0 && cg < Cout) {
+                        tma_store_2d(stage, om, cg, (int)(row0 + ew * 32));
+                        bulk_commit();
+                    }
                 }
                 if (p.stat_sum) {
                     float q[32];
@@ -210,7 +231,8 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
 
 template <int NCOLS>
 static int launch_tv(const CUtensorMap& amap, const CUtensorMap& wmap, const CUtensorMap& omap,
-                     const CUtensorMap& omap_last, const TconvParams& p, cudaStream_t s) {
+                     const CUtensorMap& omap_last, const CUtensorMap& omap4, const TconvParams& p,
+                     cudaStream_t s) {
     using L = SmemTV<NCOLS>;
     auto kern = tconv_tc_kernel<NCOLS>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total);
@@ -218,7 +240,7 @@ static int launch_tv(const CUtensorMap& amap, const CUtensorMap& wmap, const CUt
     int nx = num_sms() / ny;
     if (nx < 1) nx = 1;
     if (nx > p.tiles) nx = p.tiles;
-    kern<<<dim3(nx, ny), kThreadsTV, L::total, s>>>(amap, wmap, omap, omap_last, p);
+    kern<<<dim3(nx, ny), kThreadsTV, L::total, s>>>(amap, wmap, omap, omap_last, omap4, p);
     return finish_launch("tconv_tc");
 }
 
@@ -231,8 +253,10 @@ using namespace istgcn;
 //   in     [NM][T][V][Cin]      channels-last activation (dir=+1) or output gradient (dir=-1)
 //   w_rows [kt*Cout][Cin]       per tap: rows = output channel, columns = input channel
 //   out    [NM][Tout][V][Cout]
-// Requirements: Cin % 32 == 0, Cout % 32 == 0, Tout % floor(128/V) == 0, floor(128/V)*V > 96;
-// dir = -1 needs stride == 1 (then Tout == T).
+// Requirements: Cin % 32 == 0, Cout % 32 == 0, floor(128/V)*V > 96; the output frame count must
+// be a multiple of floor(128/V) except for dir = -1 with stride 2 (4-D stores clip ragged ends).
+// dir = -1: `in` is the output gradient [NM][Tout][V][Cin], `out` the input gradient
+// [NM][T][V][Cout], w_rows the transposed weights [kt*Cout][Cin] (rows = conv input channel).
 ISTGCN_API int istgcn_tconv_tc(const float* in, const float* w_rows, const float* bias, float* out,
                                double* stat_sum, double* stat_sumsq, int NM, int T, int Tout, int V,
                                int Cin, int Cout, int kt, int stride, int dir, istgcn_stream_t s) {
@@ -243,29 +267,63 @@ ISTGCN_API int istgcn_tconv_tc(const float* in, const float* w_rows, const float
                    "tconv_tc: V=%d kt=%d unsupported", V, kt);
     ISTGCN_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && Cout <= 1024,
                    ISTGCN_E_SHAPE, "tconv_tc: Cin=%d Cout=%d must be multiples of 32", Cin, Cout);
-    ISTGCN_REQUIRE(dir == 1 || (dir == -1 && stride == 1), ISTGCN_E_ARG,
-                   "tconv_tc: dir=%d stride=%d unsupported", dir, stride);
+    ISTGCN_REQUIRE(dir == 1 || dir == -1, ISTGCN_E_ARG, "tconv_tc: dir=%d unsupported", dir);
     ISTGCN_REQUIRE(stride >= 1 && Tout == (T - 1) / stride + 1, ISTGCN_E_SHAPE,
                    "tconv_tc: Tout=%d does not match T=%d stride=%d", Tout, T, stride);
+    ISTGCN_REQUIRE(dir == 1 || stride <= 2, ISTGCN_E_SHAPE, "tconv_tc: dir=-1 needs stride 1 or 2");
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
-    ISTGCN_REQUIRE(Tout % F == 0 && F * V > 96, ISTGCN_E_SHAPE,
-                   "tconv_tc: Tout=%d must be a multiple of %d frames per tile (V=%d)", Tout, F, V);
+    ISTGCN_REQUIRE(F * V > 96, ISTGCN_E_SHAPE, "tconv_tc: V=%d unsupported", V);
     ISTGCN_REQUIRE(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w_rows) |
                      reinterpret_cast<uintptr_t>(out)) & 15) == 0,
                    ISTGCN_E_ARG, "tconv_tc: pointers must be 16-byte aligned");
     if ((long long)NM * Tout == 0) return 0;
-    tc::TconvParams p{bias, out, stat_sum, stat_sumsq, NM, T, Tout, V, Cin, Cout, kt, stride, dir, 0, 0};
-    p.tiles_per_clip = Tout / F;
-    p.tiles = NM * p.tiles_per_clip;
+    const int pad = (kt - 1) / 2;
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
-    CUtensorMap amap, wmap, omap, omap_last;
-    if (int e = tc::encode_frames_map(&amap, in, NM, T, V, Cin, F, stride)) return e;
+    cudaStream_t st = (cudaStream_t)s;
+    // frames on the input side / output side of this launch
+    const int T_in = dir == 1 ? T : Tout, T_out = dir == 1 ? Tout : T;
+    CUtensorMap amap, wmap, omap, omap_last, omap4;
     if (int e = tc::encode_tile_map(&wmap, w_rows, (long long)kt * Cout, Cin, ncols)) return e;
-    const long long rows = (long long)NM * Tout * V;
+    const long long rows = (long long)NM * T_out * V;
     if (int e = tc::encode_tile_map(&omap, out, rows, Cout, 32)) return e;
     if (int e = tc::encode_tile_map(&omap_last, out, rows, Cout, F * V - 96)) return e;
-    cudaStream_t st = (cudaStream_t)s;
-    if (ncols == 256) return tc::launch_tv<256>(amap, wmap, omap, omap_last, p, st);
-    if (ncols == 128) return tc::launch_tv<128>(amap, wmap, omap, omap_last, p, st);
-    return tc::launch_tv<64>(amap, wmap, omap, omap_last, p, st);
+    const bool strided_dx = dir == -1 && stride == 2;
+    if (int e = tc::encode_frames_map(&amap, in, NM, T_in, V, Cin, F, dir == 1 ? stride : 1)) return e;
+    if (int e = tc::encode_frames_map(&omap4, out, NM, T_out, V, Cout, F, strided_dx ? 2 : 1)) return e;
+    for (int q = 0; q < (strided_dx ? 2 : 1); ++q) {
+        tc::TconvParams p{};
+        p.bias = bias; p.out = out; p.stat_sum = stat_sum; p.stat_sumsq = stat_sumsq;
+        p.NM = NM; p.V = V; p.Cin = Cin; p.Cout = Cout;
+        int frames_out = T_out;                       // output frames handled by this launch
+        if (dir == 1) {
+            p.in_step = stride;
+            for (int tap = 0; tap < kt; ++tap) { p.tap_w[p.ntaps] = tap; p.tap_off[p.ntaps++] = tap - pad; }
+        } else if (!strided_dx) {
+            p.in_step = 1;
+            for (int tap = 0; tap < kt; ++tap) { p.tap_w[p.ntaps] = tap; p.tap_off[p.ntaps++] = pad - tap; }
+        } else {                                      // input frames ti = 2j + q
+            p.in_step = 1;
+            for (int tap = 0; tap < kt; ++tap)
+                if (((q + pad - tap) & 1) == 0) {
+                    p.tap_w[p.ntaps] = tap;
+                    p.tap_off[p.ntaps++] = (q + pad - tap) / 2;
+                }
+            p.out4d = 1; p.out_q = q; p.out_step = 2;
+            frames_out = (T_out - q + 1) / 2;
+        }
+        if (frames_out <= 0 || p.ntaps == 0) continue;
+        if (!p.out4d) {
+            ISTGCN_REQUIRE(frames_out % F == 0, ISTGCN_E_SHAPE,
+                           "tconv_tc: %d output frames must be a multiple of %d frames per tile (V=%d)",
+                           frames_out, F, V);
+        }
+        p.tiles_per_clip = (frames_out + F - 1) / F;
+        p.tiles = NM * p.tiles_per_clip;
+        int e;
+        if (ncols == 256) e = tc::launch_tv<256>(amap, wmap, omap, omap_last, omap4, p, st);
+        else if (ncols == 128) e = tc::launch_tv<128>(amap, wmap, omap, omap_last, omap4, p, st);
+        else e = tc::launch_tv<64>(amap, wmap, omap, omap_last, omap4, p, st);
+        if (e) return e;
+    }
+    return 0;
 }

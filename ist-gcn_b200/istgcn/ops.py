@@ -397,9 +397,11 @@ class STBlockWide(Function):
         # gradient w.r.t. a = relu(BN1(z)): transposed taps, accumulated; weight / bias gradients
         da = torch.zeros(NM, T, V, C, device=dev, dtype=torch.float32)
         dWtt, dbt_vc = torch.zeros_like(Wtt), torch.zeros(V, C, device=dev)
-        fused_dx = use_tc() and s == 1 and _tconv_fused_ok(C, T, V)
-        if fused_dx:    # transposed convolution = the same implicit GEMM with mirrored taps
-            call('tconv_tc', du, Wtt, None, da, None, None, NM, T, T, V, C, C, kt, 1, -1)
+        # transposed convolution = the same implicit GEMM with mirrored taps (stride 2: one launch
+        # per input-frame parity inside the entry point)
+        fused_dx = use_tc() and _tconv_fused_ok(C, T if s == 1 else 128 // V, V) and s <= 2
+        if fused_dx:
+            call('tconv_tc', du, Wtt, None, da, None, None, NM, T, Tout, V, C, C, kt, s, -1)
         fused_dw = use_tc() and C % 32 == 0 and (C <= 128 or C % 128 == 0)
         if fused_dw:    # all taps of the weight gradient in one kernel (accumulators in TMEM)
             call('tconv_dw_tc', a, du, dWtt, dbt_vc, NM, T, Tout, V, C, C, kt, s)

@@ -380,10 +380,12 @@ def test_twostream_vs_oracle(env, math):
 @pytest.mark.parametrize('shape', [(3, 20, 25, 64, 9, 1, 1), (3, 20, 25, 64, 9, 2, 1),
                                    (2, 40, 25, 128, 15, 1, 1), (2, 10, 25, 256, 9, 1, 1),
                                    (3, 14, 18, 64, 9, 1, 1), (3, 20, 25, 64, 9, 1, -1),
-                                   (2, 10, 25, 256, 15, 1, -1)])
+                                   (2, 10, 25, 256, 15, 1, -1), (3, 20, 25, 64, 9, 2, -1),
+                                   (2, 23, 25, 128, 15, 2, -1), (2, 14, 18, 64, 9, 2, -1)])
 def test_tconv_tc_vs_conv2d(env, shape):
     """The tcgen05 implicit-GEMM temporal convolution (csrc/tconv_tc.cu) vs F.conv2d in fp64:
-    forward with stride 1 / 2 (outputs and BatchNorm sums) and the stride-1 input gradient."""
+    forward with stride 1 / 2 (outputs and BatchNorm sums) and the input gradient (stride 1; stride 2
+    = one launch per input-frame parity with frame-strided TMA stores, ragged clip ends)."""
     from istgcn._lib import call
     NM, T, V, C, kt, s, direction = shape
     dev = torch.device('cuda')
@@ -403,13 +405,13 @@ def test_tconv_tc_vs_conv2d(env, shape):
         assert rel(st[0], ref.sum((0, 1, 2)), 1e-3 * ref.abs().sum().item()) < 2e-3
         assert rel(st[1], ref.pow(2).sum((0, 1, 2))) < 2e-3
     else:
-        du = torch.randn(NM, T, V, C, generator=gen).to(dev)
+        du = torch.randn(NM, Tout, V, C, generator=gen).to(dev)
         a = torch.randn(NM, T, V, C, generator=gen).to(dev).double().requires_grad_(True)
-        F.conv2d(a.permute(0, 3, 1, 2), w.double(), None, padding=(pad, 0)).permute(0, 2, 3, 1) \
-            .backward(du.double())
+        F.conv2d(a.permute(0, 3, 1, 2), w.double(), None, stride=(s, 1), padding=(pad, 0)) \
+            .permute(0, 2, 3, 1).backward(du.double())
         wt = w[:, :, :, 0].permute(2, 1, 0).contiguous().view(kt * C, C)      # [tap][ci][co]
-        da = torch.empty(NM, T, V, C, device=dev)
-        call('tconv_tc', du, wt, None, da, None, None, NM, T, T, V, C, C, kt, 1, -1)
+        da = torch.full((NM, T, V, C), float('nan'), device=dev)             # every element is written
+        call('tconv_tc', du, wt, None, da, None, None, NM, T, Tout, V, C, C, kt, s, -1)
         assert rel(da, a.grad) < 2e-3
 
 

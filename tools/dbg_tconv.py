@@ -22,16 +22,16 @@ def check(NM, T, V, C, kt, s, dir_):
         serr = ((st[0] - ref.sum((0, 1, 2))).abs().max() / ref.sum((0, 1, 2)).abs().max()).item()
         print('fwd NM %d T %d V %d C %d kt %d s %d: err %.2e stat err %.2e' % (NM, T, V, C, kt, s, err, serr))
     else:
-        du = torch.randn(NM, T, V, C, device=dev)
+        du = torch.randn(NM, Tout, V, C, device=dev)
         a = torch.randn(NM, T, V, C, device=dev, dtype=torch.float64, requires_grad=True)
-        y = F.conv2d(a.permute(0, 3, 1, 2), w.double(), None, stride=(1, 1), padding=(pad, 0)).permute(0, 2, 3, 1)
+        y = F.conv2d(a.permute(0, 3, 1, 2), w.double(), None, stride=(s, 1), padding=(pad, 0)).permute(0, 2, 3, 1)
         y.backward(du.double())
         wt = w[:, :, :, 0].permute(2, 1, 0).contiguous().view(kt * C, C)        # [tap][ci][co]
-        da = torch.empty(NM, T, V, C, device=dev)
-        call('tconv_tc', du, wt, None, da, None, None, NM, T, T, V, C, C, kt, 1, -1)
+        da = torch.full((NM, T, V, C), float('nan'), device=dev)
+        call('tconv_tc', du, wt, None, da, None, None, NM, T, Tout, V, C, C, kt, s, -1)
         torch.cuda.synchronize()
         err = ((da.double() - a.grad).abs().max() / a.grad.abs().max()).item()
-        print('dx  NM %d T %d V %d C %d kt %d: err %.2e' % (NM, T, V, C, kt, err))
+        print('dx  NM %d T %d V %d C %d kt %d s %d: err %.2e' % (NM, T, V, C, kt, s, err))
 check(3, 20, 25, 64, 9, 1, 1)
 check(3, 20, 25, 64, 9, 2, 1)
 check(2, 40, 25, 128, 15, 1, 1)
@@ -39,6 +39,9 @@ check(2, 10, 25, 256, 9, 1, 1)
 check(3, 14, 18, 64, 9, 1, 1)
 check(3, 20, 25, 64, 9, 1, -1)
 check(2, 10, 25, 256, 15, 1, -1)
+check(3, 20, 25, 64, 9, 2, -1)
+check(2, 23, 25, 128, 15, 2, -1)
+check(2, 14, 18, 64, 9, 2, -1)
 def check_dw(NM, T, V, C, kt, s):
     Tout = (T - 1) // s + 1
     pad = (kt - 1) // 2
