@@ -716,6 +716,116 @@ __global__ void __launch_bounds__(kThreads, 3) tcn_bwd_down_kernel(TcnBwdDownPar
     }
 }
 
+// The same stage as a plain streaming kernel on the CUDA cores.  The contraction of this stage
+// runs over the bp <= 16 bottleneck channels only, so there is nothing for a tensor core to do:
+// thread = (row sub-group, CH channels), one vector of z in / one vector of g1 out per row, the
+// weight-gradient and BatchNorm sums stay in registers over the thread's rows and are flushed
+// once per CTA (CH = 4 for bp = 8, 2 for bp = 16: CH*bp accumulators must stay in registers).
+// Exact fp32 (serves both math modes); HBM-bound like the block-tail kernels.
+template <int BP, int CH>
+__global__ void __launch_bounds__(256) tcn_bwd_down_stream_kernel(TcnBwdDownParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int C = p.C, cgn = C / CH;            // channel groups = threads per row
+    float* Wt = smem;                           // [BP][C]  (Wd transposed: conflict-free reads)
+    float* red = Wt + BP * C;                   // [256][2*CH] reduction scratch
+    const int tid = threadIdx.x;
+    const int rows_per_iter = 256 / cgn;
+    const int col = tid % cgn, rsub = tid / cgn, c = col * CH;
+    for (int i = tid; i < C * BP; i += 256) Wt[(i % BP) * C + (i / BP)] = p.Wd[i];
+    __syncthreads();
+    float mu[CH], sc[CH], be[CH], rs[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        mu[i] = p.mean1[c + i]; sc[i] = p.scale1[c + i]; be[i] = p.beta1[c + i]; rs[i] = p.rstd1[c + i];
+    }
+    float accw[CH][BP];
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+#pragma unroll
+        for (int j = 0; j < BP; ++j) accw[i][j] = 0.f;
+    float sg[CH], sgx[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) sg[i] = sgx[i] = 0.f;
+    if (rsub < rows_per_iter) {
+        for (long long r = (long long)blockIdx.x * rows_per_iter + rsub; r < p.rows;
+             r += (long long)gridDim.x * rows_per_iter) {
+            float z4[CH];
+            if (CH == 4) {
+                const float4 zv = ld4(p.z + r * C + c);
+                z4[0] = zv.x; z4[1] = zv.y; z4[CH - 2] = zv.z; z4[CH - 1] = zv.w;
+            } else {
+                const float2 zv = *reinterpret_cast<const float2*>(p.z + r * C + c);
+                z4[0] = zv.x; z4[1] = zv.y;
+            }
+            float dh[BP];
+#pragma unroll
+            for (int j = 0; j < BP; j += 4) {
+                const float4 d = ld4(p.dh1 + r * BP + j);
+                dh[j] = d.x; dh[j + 1] = d.y; dh[j + 2] = d.z; dh[j + 3] = d.w;
+            }
+            float a4[CH], da[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                a4[i] = fmaxf(bn_apply(z4[i], mu[i], sc[i], be[i]), 0.f);
+                da[i] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < BP; ++j) {
+#pragma unroll
+                for (int i = 0; i < CH; ++i) da[i] = fmaf(dh[j], Wt[j * C + c + i], da[i]);
+            }
+            float g[CH];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                g[i] = a4[i] > 0.f ? da[i] : 0.f;
+                sg[i] += g[i];
+                sgx[i] += g[i] * (z4[i] - mu[i]) * rs[i];
+#pragma unroll
+                for (int j = 0; j < BP; ++j) accw[i][j] = fmaf(a4[i], dh[j], accw[i][j]);
+            }
+            if (CH == 4)
+                st4(p.g1 + r * C + c, make_float4(g[0], g[1], g[CH - 2], g[CH - 1]));
+            else
+                *reinterpret_cast<float2*>(p.g1 + r * C + c) = make_float2(g[0], g[1]);
+        }
+    }
+    // ---- CTA reduction over the row sub-groups, then one atomic per output and CTA
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        red[tid * 2 * CH + i] = sg[i];
+        red[tid * 2 * CH + CH + i] = sgx[i];
+    }
+    __syncthreads();
+    for (int ch = tid; ch < C; ch += 256) {
+        const int cc = ch / CH, i = ch % CH;
+        double s0 = 0.0, s1 = 0.0;
+        for (int k = 0; k < rows_per_iter; ++k) {
+            s0 += red[(k * cgn + cc) * 2 * CH + i];
+            s1 += red[(k * cgn + cc) * 2 * CH + CH + i];
+        }
+        atomicAdd(&p.sg1[ch], s0);
+        atomicAdd(&p.sg1x[ch], s1);
+    }
+    // dWd two bottleneck columns at a time through the same scratch
+#pragma unroll
+    for (int j0 = 0; j0 < BP; j0 += 2) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            red[tid * 2 * CH + i * 2] = accw[i][j0];
+            red[tid * 2 * CH + i * 2 + 1] = accw[i][j0 + 1];
+        }
+        __syncthreads();
+        for (int o = tid; o < C * 2; o += 256) {
+            const int ch = o >> 1, jj = o & 1;
+            const int cc = ch / CH, i = ch % CH;
+            float s0 = 0.f;
+            for (int k = 0; k < rows_per_iter; ++k) s0 += red[(k * cgn + cc) * 2 * CH + i * 2 + jj];
+            atomicAdd(&p.dWd[(size_t)ch * BP + j0 + jj], s0);
+        }
+    }
+}
+
 static int grid_for(long long tiles, int per_sm) {
     long long n = (long long)num_sms() * per_sm;
     if (n > tiles) n = tiles;
@@ -838,6 +948,24 @@ ISTGCN_API int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, 
     {
         TcnBwdDownParams p{dh1_ws, z, scale1, beta1, mean1, rstd1, Wd, g1, dWd, sg1, sg1x,
                            (long long)NM * T * V, C, bp};
+        const int cgn = C / (bp == 8 ? 4 : 2);
+        // streaming CUDA-core version: wins for bp = 8 (0.18 vs 0.23 ms at C = 64); at bp = 16 the
+        // 2*C*bp FMAs per row make it instruction-bound and the mma.sync kernel below is faster
+        if (bp == 8 && C % 4 == 0 && cgn <= 256 && 256 % cgn == 0) {
+            const size_t sm = sizeof(float) * ((size_t)bp * C + 256 * 8);
+            const int rpi = 256 / cgn;
+            long long blocks = (p.rows + rpi * 8 - 1) / (rpi * 8);
+            const long long cap = (long long)num_sms() * 4;
+            if (blocks > cap) blocks = cap;
+            if (bp == 8) {
+                set_smem(tcn_bwd_down_stream_kernel<8, 4>, sm);
+                tcn_bwd_down_stream_kernel<8, 4><<<(int)blocks, 256, sm, st>>>(p);
+            } else {
+                set_smem(tcn_bwd_down_stream_kernel<16, 2>, sm);
+                tcn_bwd_down_stream_kernel<16, 2><<<(int)blocks, 256, sm, st>>>(p);
+            }
+            return finish_launch("tcn_bwd_down");
+        }
         const size_t smem = sizeof(float) * (kTileRows * 36 + kTileRows * 40 + kTileRows * ld_g(bp) +
                                              C * ld_g(bp) + 2 * C);
         const int grid = grid_for((p.rows + kTileRows - 1) / kTileRows, 3);
