@@ -34,6 +34,7 @@ struct TconvParams {
     int in_step;                  // input frame of a tile's first output frame = to0 * in_step + tap_off
     int ntaps, tap_w[16], tap_off[16];   // weight block and frame offset of every contributing tap
     int out4d, out_q, out_step;   // 4-D strided store: output frame = out_q + out_step * to
+    int frames_out;               // output frames per clip handled by this launch
 };
 
 template <int NCOLS>
@@ -153,8 +154,9 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
             const int buf = tcount & 1;
             const long long row0 = (long long)tile * F * V;      // tiles never straddle clips
             const int cn = tile / p.tiles_per_clip;
-            const int ct = p.out_q + p.out_step * (tile - cn * p.tiles_per_clip) * F;
-            const bool ok = r < F * V;
+            const int cto = (tile - cn * p.tiles_per_clip) * F;
+            const int ct = p.out_q + p.out_step * cto;
+            const bool ok = r < min(F, p.frames_out - cto) * V;     // ragged clip end: bias-only rows
             mbar_wait(&t_full[buf], (tcount >> 1) & 1);
             tc_fence_after();
             for (int c0 = 0; c0 < NCOLS; c0 += 32) {
@@ -253,8 +255,8 @@ using namespace istgcn;
 //   in     [NM][T][V][Cin]      channels-last activation (dir=+1) or output gradient (dir=-1)
 //   w_rows [kt*Cout][Cin]       per tap: rows = output channel, columns = input channel
 //   out    [NM][Tout][V][Cout]
-// Requirements: Cin % 32 == 0, Cout % 32 == 0, floor(128/V)*V > 96; the output frame count must
-// be a multiple of floor(128/V) except for dir = -1 with stride 2 (4-D stores clip ragged ends).
+// Requirements: Cin % 32 == 0, Cout % 32 == 0, floor(128/V)*V > 96.  Clips whose output frame
+// count is not a multiple of floor(128/V) leave through 4-D stores that clip the ragged end.
 // dir = -1: `in` is the output gradient [NM][Tout][V][Cin], `out` the input gradient
 // [NM][T][V][Cout], w_rows the transposed weights [kt*Cout][Cin] (rows = conv input channel).
 ISTGCN_API int istgcn_tconv_tc(const float* in, const float* w_rows, const float* bias, float* out,
@@ -312,11 +314,10 @@ ISTGCN_API int istgcn_tconv_tc(const float* in, const float* w_rows, const float
             frames_out = (T_out - q + 1) / 2;
         }
         if (frames_out <= 0 || p.ntaps == 0) continue;
-        if (!p.out4d) {
-            ISTGCN_REQUIRE(frames_out % F == 0, ISTGCN_E_SHAPE,
-                           "tconv_tc: %d output frames must be a multiple of %d frames per tile (V=%d)",
-                           frames_out, F, V);
+        if (!p.out4d && frames_out % F != 0) {        // ragged clips: the 4-D store clips the tail
+            p.out4d = 1; p.out_q = 0; p.out_step = 1;
         }
+        p.frames_out = frames_out;
         p.tiles_per_clip = (frames_out + F - 1) / F;
         p.tiles = NM * p.tiles_per_clip;
         int e;

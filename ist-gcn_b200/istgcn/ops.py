@@ -271,10 +271,10 @@ class STBlock(Function):
                 dbtr, dgr, dbr, None)
 
 
-def _tconv_fused_ok(C, Tout, V):
+def _tconv_fused_ok(C, V):
     """Shapes the tcgen05 temporal-convolution kernel takes (csrc/tconv_tc.cu)."""
     F = min(8, 128 // V)
-    return C % 32 == 0 and Tout % F == 0 and F * V > 96
+    return C % 32 == 0 and F * V > 96
 
 
 class STBlockWide(Function):
@@ -316,7 +316,7 @@ class STBlockWide(Function):
         a = torch.empty_like(z)
         call('bn_relu_apply', z, mean1, scale1, bn1_b, a, i64(R_in), C)
         u = torch.empty(NM, Tout, V, C, device=dev, dtype=torch.float32)
-        fused = use_tc() and _tconv_fused_ok(C, Tout, V)
+        fused = use_tc() and _tconv_fused_ok(C, V)
         if use_tc():
             Wrows = Wtt.detach().transpose(1, 2).contiguous()         # [kt][C(out)][C(in)]
             bt_k = bt.detach().view(1, C)
@@ -399,7 +399,7 @@ class STBlockWide(Function):
         dWtt, dbt_vc = torch.zeros_like(Wtt), torch.zeros(V, C, device=dev)
         # transposed convolution = the same implicit GEMM with mirrored taps (stride 2: one launch
         # per input-frame parity inside the entry point)
-        fused_dx = use_tc() and _tconv_fused_ok(C, T if s == 1 else 128 // V, V) and s <= 2
+        fused_dx = use_tc() and _tconv_fused_ok(C, V) and s <= 2
         if fused_dx:
             call('tconv_tc', du, Wtt, None, da, None, None, NM, T, Tout, V, C, C, kt, s, -1)
         fused_dw = use_tc() and C % 32 == 0 and (C <= 128 or C % 128 == 0)

@@ -381,7 +381,9 @@ def test_twostream_vs_oracle(env, math):
                                    (2, 40, 25, 128, 15, 1, 1), (2, 10, 25, 256, 9, 1, 1),
                                    (3, 14, 18, 64, 9, 1, 1), (3, 20, 25, 64, 9, 1, -1),
                                    (2, 10, 25, 256, 15, 1, -1), (3, 20, 25, 64, 9, 2, -1),
-                                   (2, 23, 25, 128, 15, 2, -1), (2, 14, 18, 64, 9, 2, -1)])
+                                   (2, 23, 25, 128, 15, 2, -1), (2, 14, 18, 64, 9, 2, -1),
+                                   (3, 23, 25, 64, 9, 1, 1), (2, 24, 18, 128, 9, 2, 1),
+                                   (3, 17, 25, 64, 15, 1, -1)])
 def test_tconv_tc_vs_conv2d(env, shape):
     """The tcgen05 implicit-GEMM temporal convolution (csrc/tconv_tc.cu) vs F.conv2d in fp64:
     forward with stride 1 / 2 (outputs and BatchNorm sums) and the input gradient (stride 1; stride 2
