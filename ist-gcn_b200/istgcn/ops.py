@@ -120,6 +120,12 @@ class BlockCfg(object):
         self.seed = 0
 
 
+def _tconv_fused_ok(C, V):
+    """Shapes the tcgen05 temporal-convolution kernel takes (csrc/tconv_tc.cu)."""
+    F = min(8, 128 // V)
+    return C % 32 == 0 and F * V > 96
+
+
 class STBlock(Function):
     """One IST-GCN block: graph conv -> BN -> ReLU -> 1x1 -> {3,9,15}x1 -> 1x1 -> BN -> dropout
     -> + residual -> ReLU  (net/st_gcn_mstcn_1x1.py:250-266 with tgcn.py:76-89 or
@@ -167,7 +173,11 @@ class STBlock(Function):
                 cfg.ones = torch.ones(V, device=dev, dtype=torch.float32)
             Wr, biasterm_r = Wr.contiguous(), biasterm_r.contiguous()
             rres = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-            if use_tc():     # strided 1x1 conv = K=1 / identity-adjacency case of the tcgen05 engine
+            if use_tc() and _tconv_fused_ok(Cin, V) and Cout % 32 == 0:
+                # strided 1x1 conv = the one-tap case of the TMA-fed temporal convolution
+                call('tconv_tc', x, Wr.t().contiguous(), biasterm_r[0].contiguous(), rres, stats[4],
+                     stats[5], NM, T, Tout, V, Cin, Cout, 1, s, 1)
+            elif use_tc():   # K=1 / identity-adjacency case of the graph-conv engine
                 W2r = Wr.t().contiguous()                      # (Cout, Cin): rows n, cols ci
                 call('gcn_tc', x, None, None, None, None, None, W2r, cfg.ones, idn.dst_ptr,
                      idn.dst_src, idn.dst_id, V, biasterm_r[0].contiguous(), cfg.ones, None, rres, None,
@@ -259,8 +269,11 @@ class STBlock(Function):
                 call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
                      idn.t_id, V, None, None, gin, gin, dyr, None, None, NM * Tout, V, 1, Cout, Cout, Cin,
                      T, Tout, s, 0, 2)
-                call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr, dbtr,
-                     NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0)
+                if Cin % 32 == 0 and (Cout <= 128 or Cout % 128 == 0):
+                    call('tconv_dw_tc', x, dyr, dWr, dbtr, NM, T, Tout, V, Cin, Cout, 1, s)
+                else:
+                    call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr,
+                         dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0)
             else:
                 call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr,
                      idn.src_kw, idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, Cout, T, Tout, s,
@@ -269,12 +282,6 @@ class STBlock(Function):
                      idn.dst_id, V, dWr, dbtr, NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0, math)
         return (gin, dvals, dWc, dbt, None, dg1, db1, dWd, dbd, dWeff, dbeff, dWu, dbu, dg2, db2, dWr,
                 dbtr, dgr, dbr, None)
-
-
-def _tconv_fused_ok(C, V):
-    """Shapes the tcgen05 temporal-convolution kernel takes (csrc/tconv_tc.cu)."""
-    F = min(8, 128 // V)
-    return C % 32 == 0 and F * V > 96
 
 
 class STBlockWide(Function):
@@ -346,7 +353,10 @@ class STBlockWide(Function):
         elif cfg.res_mode == 2:
             Wr, biasterm_r = Wr.contiguous(), biasterm_r.contiguous()
             rres = torch.empty(NM, Tout, V, C, device=dev, dtype=torch.float32)
-            if use_tc():
+            if use_tc() and _tconv_fused_ok(Cin, V) and C % 32 == 0:
+                call('tconv_tc', x, Wr.t().contiguous(), biasterm_r[0].contiguous(), rres, stats[4],
+                     stats[5], NM, T, Tout, V, Cin, C, 1, s, 1)
+            elif use_tc():
                 W2r = Wr.t().contiguous()
                 call('gcn_tc', x, None, None, None, None, None, W2r, cfg.ones, idn.dst_ptr,
                      idn.dst_src, idn.dst_id, V, biasterm_r[0].contiguous(), cfg.ones, None, rres, None,
@@ -462,8 +472,11 @@ class STBlockWide(Function):
                 call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
                      idn.t_id, V, None, None, gin, gin, dyr, None, None, NM * Tout, V, 1, C, C, Cin,
                      T, Tout, s, 0, 2)
-                call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr, dbtr,
-                     NM * Tout, V, 1, Cin, C, T, Tout, s, 0)
+                if Cin % 32 == 0 and (C <= 128 or C % 128 == 0):
+                    call('tconv_dw_tc', x, dyr, dWr, dbtr, NM, T, Tout, V, Cin, C, 1, s)
+                else:
+                    call('gcn_tc_dw', dyr, x, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V, dWr,
+                         dbtr, NM * Tout, V, 1, Cin, C, T, Tout, s, 0)
             else:
                 call('gcn_bwd_x', go, rres, pr, m1r, cr, mean_r, x, Wr, cfg.ones, idn.src_ptr,
                      idn.src_kw, idn.src_id, V, gin, gin, None, NM * Tout, V, 1, Cin, C, T, Tout, s,

@@ -464,7 +464,7 @@ def test_fused_temporal_conv_model_vs_oracle(env, arch):
     finally:
         env.set_math(old)
     assert 'tconv_tc' in used and len(used['tconv_tc']) >= len(model.st_gcn_networks)
-    assert len(used.get('tconv_dw_tc', [])) == len(model.st_gcn_networks)
+    assert len(used.get('tconv_dw_tc', [])) >= len(model.st_gcn_networks)      # + strided residual convs
     ref = model_ref.forward({k: v.double() if v.is_floating_point() else v for k, v in state.items()},
                             x.double(), arch, training=True)
     assert rel(logits, ref) < TOL['tf32']
