@@ -20,6 +20,8 @@
 // Input gradient:   IN = dz (formed on load), lists grouped by (k,v) (transposed adjacency),
 //                   W = Wc (K*Cin, Cout), epilogue adds the residual gradient.
 // Every mbarrier wait is bounded (trap on timeout) so a pipeline bug cannot hang the device.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace istgcn {
@@ -577,6 +579,15 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
     if (frames == 0) return 0;
     ISTGCN_REQUIRE((bias_k == nullptr) == (colsum == nullptr), ISTGCN_E_ARG,
                    "gcn_tc: pass bias_k and colsum together");
+    // second-generation engine (aggregation on the tensor core, gcn_tc2.cu) whenever the input can
+    // be fed by TMA as it lies in HBM; ISTGCN_GCN_TC_V1=1 keeps the first-generation kernel
+    static const bool force_v1 = getenv("ISTGCN_GCN_TC_V1") != nullptr;
+    if (!force_v1 && bn_p == nullptr && in_out == nullptr && map_side == 0 && CinPad == Cin &&
+        (add_rows == nullptr || (add_rows == out && stat_sum == nullptr)) &&
+        tc::gcn_tc2_eligible(V, K, Cin, Cout, in, out))
+        return tc::launch_gcn_tc2(in, w_rows, vals, lptr, lsrc, lid, bias_k, colsum, out,
+                                  add_rows != nullptr, stat_sum, stat_sumsq, frames, V, K, Cin, Cout,
+                                  (cudaStream_t)s);
     tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_k, colsum,
                       add_rows, out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout,
                       nnz, 0, {0, 0, 1, 0}, {0, 0, 1, 0}, 0};

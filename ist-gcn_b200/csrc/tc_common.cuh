@@ -16,6 +16,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of the (converged) warp: the way to issue single-thread instructions (TMA, tcgen05.mma,
+// tcgen05.commit) from warp-uniform control flow.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -291,6 +303,12 @@ int encode_tile_map(CUtensorMap* map, const float* base, long long rows, long lo
 // 4-D (C, V, T, NM) view of a channels-last activation: box of 32 channels x V x frames (strided)
 int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V, int C, int frames,
                       int t_stride, bool atom32 = false);
+// second-generation graph-convolution engine (gcn_tc2.cu)
+bool gcn_tc2_eligible(int V, int K, int Cin, int Cout, const float* in, const float* out);
+int launch_gcn_tc2(const float* in, const float* w_rows, const float* vals, const int* lptr,
+                   const int* lsrc, const int* lid, const float* bias_k, const float* colsum, float* out,
+                   int reduce, double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
+                   int Cout, cudaStream_t st);
 // out[j] += sum_f in[f][j], j < n (gcn_tc_dw.cu)
 int launch_frame_colsum(const float* in, float* out, int frames, int n, cudaStream_t st);
 
