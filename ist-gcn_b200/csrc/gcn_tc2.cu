@@ -123,7 +123,7 @@ struct GcnTc2Params {
     const int *lptr, *lsrc, *lid;
     const float *bias_k, *colsum;
     double *stat_sum, *stat_sumsq;
-    int frames, V, K, Cin, Cout, tiles, reduce, variant;
+    int frames, V, K, Cin, Cout, tiles, reduce;
 };
 
 template <int NCOLS>
@@ -310,6 +310,9 @@ gcn_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
         const int ew = warp - 4;
         const int w = lane;
         uint8_t* stage = smem + L::stage_off + ew * 4096;      // [32 rows][128 B], SWIZZLE_128B
+        double acc_s[NCOLS / 32], acc_q[NCOLS / 32];          // this warp's column sums (lane = column)
+#pragma unroll
+        for (int i = 0; i < NCOLS / 32; ++i) acc_s[i] = acc_q[i] = 0.0;
         float cs[4] = {0.f, 0.f, 0.f, 0.f};
         if (p.bias_k && w < V)
             for (int k = 0; k < K; ++k) cs[k] = p.colsum[k * V + w];
@@ -317,9 +320,9 @@ gcn_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             const uint32_t buf = t % ND2, use = t / ND2;
             const int frame = (blockIdx.x + t * gridDim.x) * kFr2 + ew;
             const bool fok = frame < p.frames;
-            const bool ok = fok && w < V;
             mbar_wait(&t_full[buf], use & 1);
             tc_fence_after();
+#pragma unroll
             for (int c0 = 0; c0 < NCOLS; c0 += 32) {
                 if (c0 >= Cout) break;
                 float v[32];
@@ -349,17 +352,19 @@ gcn_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                     else tma_store_2d(stage, &omap, c0, frame * V);
                     bulk_commit();
                 }
-                if (p.stat_sum) {
-                    float q[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        v[j] = ok ? v[j] : 0.f;
-                        q[j] = v[j] * v[j];
+                if (p.stat_sum && fok) {
+                    // column sums straight from the staging tile: lane c adds column c of the V
+                    // valid rows (one conflict-free wavefront per row; the TMA store reads the
+                    // tile concurrently), then joins the warp's double accumulators
+                    float a = 0.f, q = 0.f;
+                    const int cj = lane >> 2, ce = (lane & 3) * 4;
+                    for (int r = 0; r < V; ++r) {
+                        const float x = *reinterpret_cast<const float*>(stage + r * 128 + ((cj ^ (r & 7)) << 4) + ce);
+                        a += x;
+                        q = fmaf(x, x, q);
                     }
-                    const float csum = warp_column_sums(v, lane);
-                    const float cq = warp_column_sums(q, lane);
-                    atomicAdd(&s_sum[c0 + lane], (double)csum);
-                    atomicAdd(&s_sq[c0 + lane], (double)cq);
+                    acc_s[c0 / 32] += (double)a;
+                    acc_q[c0 / 32] += (double)q;
                 }
             }
             tc_fence_before();
@@ -367,6 +372,13 @@ gcn_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
         if (lane == 0) bulk_wait_all();
+        if (p.stat_sum) {
+#pragma unroll
+            for (int i = 0; i < NCOLS / 32; ++i) {
+                atomicAdd(&s_sum[i * 32 + lane], acc_s[i]);
+                atomicAdd(&s_sq[i * 32 + lane], acc_q[i]);
+            }
+        }
     }
 
     // ---- teardown
@@ -442,8 +454,7 @@ int launch_gcn_tc2(const float* in, const float* w_rows, const float* vals, cons
                    int reduce, double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
                    int Cout, cudaStream_t st) {
     GcnTc2Params p{vals, lptr, lsrc, lid, bias_k, colsum, stat_sum, stat_sumsq, frames, V, K, Cin, Cout,
-                   (frames + kFr2 - 1) / kFr2, reduce, 0};
-    if (const char* v = getenv("ISTGCN_TC2_VARIANT")) p.variant = atoi(v);
+                   (frames + kFr2 - 1) / kFr2, reduce};
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
     CUtensorMap xmap, wmap, omap;
     if (int e = encode_frame_slices(&xmap, in, frames, V, Cin)) return e;

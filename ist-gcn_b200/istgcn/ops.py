@@ -11,6 +11,8 @@ the mirrored chain.  Parameter regrouping (A*importance, merged temporal taps, w
 transposes) is done with tiny differentiable torch ops *outside* the Function, so autograd
 maps the kernel's gradients back onto the reference's parameter tensors.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -118,6 +120,13 @@ class BlockCfg(object):
         self.ones = None
         self.training = True
         self.seed = 0
+
+
+def _gcn_tc2_ok(cin, cout):
+    """Channel counts the TMA-fed graph-convolution engine takes (csrc/gcn_tc2.cu:
+    gcn_tc2_eligible); everything else stays on the first-generation kernel."""
+    return cin % 32 == 0 and cout % 32 == 0 and 32 <= cout <= 256 and \
+        os.environ.get('ISTGCN_GCN_TC_V1') is None
 
 
 def _tconv_fused_ok(C, V):
@@ -243,8 +252,17 @@ class STBlock(Function):
             # input gradient on the tcgen05 engine: the forward kernel run on dz with the
             # transposed adjacency lists and Wc as the weight; adjacency gradient separately
             dz = torch.empty_like(z)
-            call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
-                 pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin, 0, 0, 1, 0, 0)
+            if _gcn_tc2_ok(Cout, Cin):
+                # second-generation engine (csrc/gcn_tc2.cu): its input arrives by TMA, so dz
+                # (BatchNorm backward of g1) is materialised by the element-wise kernel first
+                call('bn_back_apply', g1, z, p1, m11, c1, mean1, dz, i64(R_in), Cout, 0.0, u64(0), None)
+                call('gcn_tc', dz, None, None, None, None, None, Wc, vals, pat.t_ptr, pat.t_src,
+                     pat.t_id, pat.nnz, None, None, add_in, gin, None, None, None, NM * T, V, K, Cout,
+                     Cout, Cin, 0, 0, 1, 0, 0)
+            else:
+                call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
+                     pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin,
+                     0, 0, 1, 0, 0)
             call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
                  NM * T, V, K, Cin, Cout)
         else:
@@ -451,8 +469,15 @@ class STBlockWide(Function):
         dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, C, device=dev)
         if use_tc():
             dz = torch.empty_like(z)
-            call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
-                 pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, C, C, Cin, 0, 0, 1, 0, 0)
+            if _gcn_tc2_ok(C, Cin):
+                call('bn_back_apply', g1, z, p1, m11, c1, mean1, dz, i64(R_in), C, 0.0, u64(0), None)
+                call('gcn_tc', dz, None, None, None, None, None, Wc, vals, pat.t_ptr, pat.t_src,
+                     pat.t_id, pat.nnz, None, None, add_in, gin, None, None, None, NM * T, V, K, C, C,
+                     Cin, 0, 0, 1, 0, 0)
+            else:
+                call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
+                     pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, C, C, Cin, 0, 0, 1,
+                     0, 0)
             call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
                  NM * T, V, K, Cin, C)
             call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc, dbt,
