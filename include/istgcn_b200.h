@@ -142,6 +142,26 @@ int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const fl
                   int CinPad, int Cout, int t_in, int t_out, int t_stride, int t_offset, int map_side,
                   istgcn_stream_t s);
 
+/* ---- first block (in_channels <= 4: net/st_gcnold.py:46 `st_gcn(in_channels, 64, ...)`, the
+ * graph convolution of tgcn.py:76-89 on a 3-channel input) on CUDA cores in full fp32
+ * (csrc/gcn_small.cu): 12 B in / 256 B out per row, so no tensor-core slice padding.
+ *   gcn_small_fwd: out[(f,w)][n] = sum_{k,c} X'_k[(f,w)][c] * Wc[k*Cin+c][n] + biasterm[w][n]
+ *                  (+ BatchNorm sums).  Wc [K*Cin][Cout], Cout = 64 or 128; lists by (k, dest w).
+ *   gcn_small_bwd: the whole backward behind dz = p*((g1 - m1) - c*(z - mu)) in ONE kernel:
+ *                  dx [frames*V][Cin] (written); dvals, dWc [K*Cin][64], dbt [V][64] accumulated
+ *                  (caller-zeroed; dvals / dbt may be NULL).  (tptr, tsrc, tid) = lists grouped by
+ *                  (k, source v) with tsrc = destination w.  Cout = 64.                        */
+int istgcn_gcn_small_fwd(const float* x, const float* Wc, const float* biasterm, const float* vals,
+                         const int* lptr, const int* lsrc, const int* lid, int nnz, float* out,
+                         double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
+                         int Cout, istgcn_stream_t s);
+int istgcn_gcn_small_bwd(const float* g1, const float* z, const float* bn_p, const float* bn_m1,
+                         const float* bn_c, const float* bn_mu, const float* x, const float* Wc,
+                         const float* vals, const int* lptr, const int* lsrc, const int* lid,
+                         const int* tptr, const int* tsrc, const int* tid, int nnz, float* dx,
+                         float* dvals, float* dWc, float* dbt, int frames, int V, int K, int Cin,
+                         int Cout, istgcn_stream_t s);
+
 /* adjacency gradient on the tcgen05 engine (both operands fed by TMA):
  *   dvals[id] += sum_{f,ci} x[(f,v)][ci] * (dz Wc_k^T)[(f,w)][ci]   over the non-zeros (k,v,w)
  * dz [frames*V][Cout] (gradient w.r.t. the graph-conv output), Wc [K*Cin][Cout]; lists grouped

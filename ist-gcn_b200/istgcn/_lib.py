@@ -17,6 +17,7 @@ SYMBOLS = (
     'istgcn_data_bn_stats', 'istgcn_data_bn_apply', 'istgcn_data_bn_bwd',
     'istgcn_bn_finalize', 'istgcn_bn_eval_coeffs', 'istgcn_bn_bwd_coeffs',
     'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
+    'istgcn_gcn_small_fwd', 'istgcn_gcn_small_bwd',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
     'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_relu_bn_bwd', 'istgcn_tconv_tc',
     'istgcn_tconv_dw_tc',

@@ -144,6 +144,56 @@ def test_graph_conv_op(env, math, layout, strategy, cin, cout, nm, t):
         assert rel(mine.grad * union.to(dev), theirs.grad * union) < tol
 
 
+# ----------------------------------------------------------------------------- first block
+@pytest.mark.parametrize('layout,strategy,cin,nm,t', [
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 3, 2, 9),       # 18 frames: two full tiles + a ragged one
+    ('ntu-rgb+d', 'spatial', 3, 1, 8),                 # K = 3
+    ('openpose_sym', 'spatial_3_sym', 2, 3, 5),        # V = 18
+    ('ntu-rgb+d_sym', 'spatial_sym', 4, 1, 3),         # Cin = 4 (generic instantiation)
+])
+def test_first_block_kernels_vs_fp64(env, layout, strategy, cin, nm, t):
+    """csrc/gcn_small.cu (Cin <= 4, full fp32 on CUDA cores): forward + BatchNorm sums, and the
+    one-kernel backward (dx, dvals, dWc, dbt behind the BatchNorm-backward transform) against an
+    fp64 evaluation of tgcn.py:76-89 -- 1e-5 relative whatever the math mode."""
+    from istgcn._lib import call
+    from istgcn.sparse import SparsePattern
+    from net.utils.graph import Graph
+    dev = torch.device('cuda')
+    g = Graph(layout, strategy)
+    A = sum(torch.tensor(getattr(g, n), dtype=torch.float64) for n in ('A', 'A2', 'A3') if hasattr(g, n))
+    K, V, cout, frames = A.shape[0], A.shape[1], 64, nm * t
+    gen = torch.Generator().manual_seed(7 + cin)
+    A = A * (1 + 0.3 * torch.randn(A.shape, generator=gen, dtype=torch.float64)) * (A != 0)
+    pat = SparsePattern((A != 0).numpy(), dev)
+    vals = A.reshape(-1)[pat.flat_idx.cpu()].float().to(dev)
+    A = torch.zeros(K * V * V, dtype=torch.float64).index_put_((pat.flat_idx.cpu(),), vals.cpu().double()).view(K, V, V)
+    x = torch.randn(frames, V, cin, generator=gen)
+    Wc = torch.randn(K * cin, cout, generator=gen) * 0.3
+    bt = torch.randn(V, cout, generator=gen)
+    x64, A64, W64 = (v.double().requires_grad_(True) for v in (x, A, Wc))
+    ref = torch.einsum('fvc,kvw,kcn->fwn', x64, A64, W64.view(K, cin, cout)) + bt.double()
+    out = torch.full((frames, V, cout), float('nan'), device=dev)
+    st = torch.zeros(2, cout, device=dev, dtype=torch.float64)
+    call('gcn_small_fwd', x.to(dev), Wc.to(dev), bt.to(dev), vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
+         pat.nnz, out, st[0], st[1], frames, V, K, cin, cout)
+    assert rel(out, ref) < 1e-5
+    assert rel(st[0], ref.sum((0, 1))) < 1e-5 and rel(st[1], (ref * ref).sum((0, 1))) < 1e-5
+    g1 = torch.randn(frames, V, cout, generator=gen)
+    z = torch.randn(frames, V, cout, generator=gen)
+    p, m1, c, mu = (torch.randn(cout, generator=gen) * s + o for s, o in ((0.2, 1.0), (0.1, 0), (0.1, 0), (0.5, 0)))
+    dz = (p * ((g1 - m1) - c * (z - mu))).double()
+    ref.backward(dz)
+    dx = torch.full((frames, V, cin), float('nan'), device=dev)
+    dvals, dWc, dbt = torch.zeros_like(vals), torch.zeros(K * cin, cout, device=dev), torch.zeros(V, cout, device=dev)
+    call('gcn_small_bwd', g1.to(dev), z.to(dev), p.to(dev), m1.to(dev), c.to(dev), mu.to(dev), x.to(dev),
+         Wc.to(dev), vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.t_ptr, pat.t_src, pat.t_id, pat.nnz,
+         dx, dvals, dWc, dbt, frames, V, K, cin, cout)
+    assert rel(dx, x64.grad) < 1e-5
+    assert rel(dWc, W64.grad) < 1e-5
+    assert rel(dbt, dz.sum(0)) < 1e-5
+    assert rel(dvals, A64.grad.reshape(-1)[pat.flat_idx.cpu()]) < 1e-5
+
+
 # ----------------------------------------------------------------------------- data_bn
 def test_data_bn_layout_and_stats(env):
     from istgcn import ops
