@@ -42,57 +42,6 @@ constexpr int kXStage = kFr2 * kSlotRows * 128;        // one 32-channel slice o
 constexpr int kAdjCol = 0;                             // TMEM: adjacency [0, 128)
 constexpr int kD1Col = 128;                            //       D1 [128, 128 + 128*ND1)
 
-__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
-                                            int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
-        "%4, %5}], [%2];" ::"r"(smem_u32(smem_dst)),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 consecutive 32-bit columns
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
-                                               uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// the same with a disable-output-lane mask (bit i of word q set: lane 32q+i is NOT written)
-__device__ __forceinline__ void tc_mma_tf32_ts_masked(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b,
-                                                      uint32_t idesc, uint32_t accumulate, uint32_t m0,
-                                                      uint32_t m1, uint32_t m2, uint32_t m3) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
-        : "memory");
-}
-// registers -> TMEM: this warp's 32 lanes x 32 consecutive columns
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
-        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
-        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
-        "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
-        "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])),
-        "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
-        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])),
-        "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])),
-        "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])),
-        "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
-        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])),
-        "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
-        "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
-        : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
 template <int NCOLS>
 struct Cfg2 {
     static constexpr int WU = NCOLS > 128 ? 128 : NCOLS;          // weight rows per TMA box
@@ -400,7 +349,7 @@ gcn_tc2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 
 // 3-D (C, V, frames) view of a channels-last activation: box = 32 channels x V joints x 1 frame,
 // 32-byte-atom 128B swizzle (the MN-major TF32 operand layout)
-static int encode_frame_slices(CUtensorMap* map, const float* base, long long frames, int V, int C) {
+int encode_frame_slices(CUtensorMap* map, const float* base, long long frames, int V, int C) {
     typedef CUresult (*Fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                            const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                            CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

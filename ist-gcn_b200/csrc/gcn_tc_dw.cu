@@ -20,6 +20,8 @@
 //   warps 2-3,16-17  loaders: x slice -> smem
 //   warps 4-7     final epilogue: TMEM -> fp32 atomics into dWc
 //   warps 8-15    aggregators: x slice -> the 4 (K) X' atoms of the row block (double buffered)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace istgcn {
@@ -283,6 +285,16 @@ ISTGCN_API int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* va
     ISTGCN_REQUIRE(nnz >= 0 && nnz <= kMaxNnz, ISTGCN_E_SHAPE, "gcn_tc_dw: nnz=%d", nnz);
     if (frames == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
+    // second-generation kernel (aggregation on the tensor core, gcn_tc_dw2.cu) for plain frame maps
+    static const bool force_v1 = getenv("ISTGCN_GCN_TC_V1") != nullptr;
+    if (!force_v1 && t_out == 0 && tc::gcn_tc_dw2_eligible(V, K, Cin, Cout) &&
+        ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(x)) & 15) == 0) {
+        if (int e = tc::launch_gcn_tc_dw2(dz, x, vals, lptr, lsrc, lid, dWc, frames, V, K, Cin, Cout, st))
+            return e;
+        if (dbiasterm)
+            if (int e = tc::launch_frame_colsum(dz, dbiasterm, frames, V * Cout, st)) return e;
+        return 0;
+    }
     tc::GcnDwParams p{x, vals, lptr, lsrc, lid, dWc, frames, V, K, Cin, (Cin + 31) / 32 * 32, Cout, nnz, 0, 0,
                        {t_in, t_out, t_stride, t_offset}};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
