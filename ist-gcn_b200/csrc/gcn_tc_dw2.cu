@@ -172,18 +172,19 @@ gcn_tc_dw2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
                 mbar_wait(d1_empty, (s & 1) ^ 1);           // converters have read slice s-1
                 tc_fence_after();
                 if (elect_one()) {
+                    // partition -> frame -> K-step: long same-accumulator runs (see gcn_tc2.cu)
+                    for (int k = 0; k < K; ++k)
 #pragma unroll
-                    for (int f = 0; f < kDwFr; ++f) {
-                        const uint32_t b_addr = xs0 + xs * kDwXStage + f * (kDwSlot * 128);
-                        const uint32_t m0 = f == 0 ? 0u : ~0u, m1 = f == 1 ? 0u : ~0u,
-                                       m2 = f == 2 ? 0u : ~0u, m3 = f == 3 ? 0u : ~0u;
-                        for (int k = 0; k < K; ++k)
+                        for (int f = 0; f < kDwFr; ++f) {
+                            const uint32_t b_addr = xs0 + xs * kDwXStage + f * (kDwSlot * 128);
+                            const uint32_t m0 = f == 0 ? 0u : ~0u, m1 = f == 1 ? 0u : ~0u,
+                                           m2 = f == 2 ? 0u : ~0u, m3 = f == 3 ? 0u : ~0u;
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks)
                                 tc_mma_tf32_ts_masked(d1 + k * 32, adj + k * 32 + ks * 8,
                                                       make_desc(b_addr + ks * 1024, 4096, 512, 1), idesc1,
                                                       ks ? 1u : 0u, m0, m1, m2, m3);
-                    }
+                        }
                     tc_commit(&x_empty[xs]);
                     tc_commit(d1_full);
                 }
