@@ -109,17 +109,15 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            DPROF_DECL; DPROF_T0();
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                const int row0 = tile * F * V;
-                for (int ch = 0; ch < nchunk; ++ch)
-                    for (int ca = 0; ca < natom; ++ca, ++it) {
-                        const int s = it % kStagesDA;
-                        DPROF_ADD(1);
-                        mbar_wait(&empty[s], ((it / kStagesDA) & 1) ^ 1);
-                        DPROF_ADD(0);
+        // TMA producer (warp-convergent loop, elected issue: see gcn_tc2.cu)
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int row0 = tile * F * V;
+            for (int ch = 0; ch < nchunk; ++ch)
+                for (int ca = 0; ca < natom; ++ca, ++it) {
+                    const int s = it % kStagesDA;
+                    mbar_wait(&empty[s], ((it / kStagesDA) & 1) ^ 1);
+                    if (elect_one()) {
                         uint8_t* dst = ring + s * L::stage_bytes;
                         mbar_arrive_expect_tx(&full[s], kAtomBytes + K * 32 * 128);
                         tma_load_2d(dst, &dzmap, &full[s], ca * 32, row0);
@@ -127,28 +125,24 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                             tma_load_2d(dst + kAtomBytes + k * 32 * 128, &wmap, &full[s], ca * 32,
                                         k * Cin + ch * 32);
                     }
-            }
-            DPROF_ADD(1); DPROF_OUT(0, 1);
+                    __syncwarp();
+                }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, NG, false, false);
-            uint32_t it = 0, cit = 0;
-            DPROF_DECL; DPROF_T0();
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
-                for (int ch = 0; ch < nchunk; ++ch, ++cit) {
-                    const int buf = cit & 1;
-                    DPROF_ADD(4);
-                    mbar_wait(&t_empty[buf], ((cit >> 1) & 1) ^ 1);
-                    DPROF_ADD(2);
+        // MMA issuer
+        const uint32_t idesc = make_idesc(128, NG, false, false);
+        uint32_t it = 0, cit = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x)
+            for (int ch = 0; ch < nchunk; ++ch, ++cit) {
+                const int buf = cit & 1;
+                mbar_wait(&t_empty[buf], ((cit >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * 128;
+                for (int ca = 0; ca < natom; ++ca, ++it) {
+                    const int s = it % kStagesDA;
+                    mbar_wait(&full[s], (it / kStagesDA) & 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * 128;
-                    for (int ca = 0; ca < natom; ++ca, ++it) {
-                        const int s = it % kStagesDA;
-                        DPROF_ADD(4);
-                        mbar_wait(&full[s], (it / kStagesDA) & 1);
-                        DPROF_ADD(3);
-                        tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t a_addr = smem_u32(ring + s * L::stage_bytes);
                         const uint32_t b_addr = a_addr + kAtomBytes;
 #pragma unroll
@@ -157,11 +151,11 @@ gcn_tc_da_kernel(const __grid_constant__ CUtensorMap dzmap, const __grid_constan
                                         make_desc(b_addr + ks * 32, 16, 1024), idesc,
                                         (ca | ks) ? 1u : 0u);
                         tc_commit(&empty[s]);
+                        if (ca == natom - 1) tc_commit(&t_full[buf]);
                     }
-                    tc_commit(&t_full[buf]);
+                    __syncwarp();
                 }
-            DPROF_ADD(4); DPROF_OUT(2, 4);
-        }
+            }
     } else if ((warp >= 4 && warp < 8) || warp >= 12) {
         // ---- epilogue: G rows from TMEM, dots against the x slice; team t takes the entries
         // beg + t, beg + t + kTeamsDA, ... of every (k, w) list

@@ -99,34 +99,36 @@ gcn_tc_dw_kernel(const __grid_constant__ CUtensorMap dzmap, GcnDwParams p) {
 
     if (warp == 0) {
         // =========================== TMA producer: dz atoms, once per (tile, row block, c-atom)
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                const int row0 = tile * F * V;
-                for (int rb = 0; rb < nrb; ++rb)
-                    for (int ca = 0; ca < natom; ++ca, ++it) {
-                        const int sb = it % kNBdw;
-                        mbar_wait(&b_empty[sb], ((it / kNBdw) & 1) ^ 1);
+        // (warp-convergent loop, elected issue: see gcn_tc2.cu)
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int row0 = tile * F * V;
+            for (int rb = 0; rb < nrb; ++rb)
+                for (int ca = 0; ca < natom; ++ca, ++it) {
+                    const int sb = it % kNBdw;
+                    mbar_wait(&b_empty[sb], ((it / kNBdw) & 1) ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(&b_full[sb], kAtomBytes);
                         tma_load_2d(Bs + sb * kAtomBytes, &dzmap, &b_full[sb], ca * 32, row0);
                     }
-            }
+                    __syncwarp();
+                }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, 32, true, true);
-            uint32_t it = 0, xit = 0;
-            bool first_tile = true;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                for (int rb = 0; rb < nrb; ++rb, ++xit) {
-                    const int b = xit & 1;
-                    mbar_wait(&xp_full[b], (xit >> 1) & 1);
-                    const uint32_t a_addr = smem_u32(XP) + b * 4 * kAtomBytes;
-                    for (int ca = 0; ca < natom; ++ca, ++it) {
-                        const int sb = it % kNBdw;
-                        mbar_wait(&b_full[sb], (it / kNBdw) & 1);
-                        tc_fence_after();
+        constexpr uint32_t idesc = make_idesc(128, 32, true, true);
+        uint32_t it = 0, xit = 0;
+        bool first_tile = true;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            for (int rb = 0; rb < nrb; ++rb, ++xit) {
+                const int b = xit & 1;
+                mbar_wait(&xp_full[b], (xit >> 1) & 1);
+                const uint32_t a_addr = smem_u32(XP) + b * 4 * kAtomBytes;
+                for (int ca = 0; ca < natom; ++ca, ++it) {
+                    const int sb = it % kNBdw;
+                    mbar_wait(&b_full[sb], (it / kNBdw) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t b_addr = smem_u32(Bs) + sb * kAtomBytes;
                         const uint32_t d_tmem = tmem_base + rb * Cout + ca * 32;
 #pragma unroll
@@ -135,13 +137,15 @@ gcn_tc_dw_kernel(const __grid_constant__ CUtensorMap dzmap, GcnDwParams p) {
                                         make_desc(b_addr + ks * 1024, kAtomBytes, 512, 1), idesc,
                                         (first_tile && ks == 0) ? 0u : 1u);
                         tc_commit(&b_empty[sb]);
+                        if (ca == natom - 1) tc_commit(&xp_empty[b]);
                     }
-                    tc_commit(&xp_empty[b]);
+                    __syncwarp();
                 }
-                first_tile = false;
             }
-            tc_commit(done);
+            first_tile = false;
         }
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
     } else if (warp >= 4 && warp < 8) {
         // =========================== final epilogue: accumulators -> dWc (fp32 atomics)
         const int ew = warp - 4;

@@ -101,38 +101,41 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
-                const int n = tile / p.tiles_per_clip;
-                const int to0 = (tile - n * p.tiles_per_clip) * F;
-                for (int tap = 0; tap < p.ntaps; ++tap) {
-                    const int t_first = to0 * p.in_step + p.tap_off[tap];
-                    for (int ch = 0; ch < nchunk; ++ch, ++it) {
-                        const int s = it % kStages;
-                        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+        // TMA producer (warp-convergent loop, elected issue: see gcn_tc2.cu)
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+            const int n = tile / p.tiles_per_clip;
+            const int to0 = (tile - n * p.tiles_per_clip) * F;
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+                const int t_first = to0 * p.in_step + p.tap_off[tap];
+                for (int ch = 0; ch < nchunk; ++ch, ++it) {
+                    const int s = it % kStages;
+                    mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+                    if (elect_one()) {
                         uint8_t* dst = ring + s * L::stage_bytes;
                         mbar_arrive_expect_tx(&full[s], a_bytes + L::kBAtomBytes);
                         tma_load_4d(dst, &amap, &full[s], ch * 32, 0, t_first, n);
                         tma_load_2d(dst + kAtomBytes, &wmap, &full[s], ch * 32, p.tap_w[tap] * Cout + n0);
                     }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, NCOLS, false, false);
-            uint32_t it = 0, tcount = 0;
-            for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
-                const int buf = tcount & 1;
-                mbar_wait(&t_empty[buf], ((tcount >> 1) & 1) ^ 1);
+        // MMA issuer
+        constexpr uint32_t idesc = make_idesc(128, NCOLS, false, false);
+        uint32_t it = 0, tcount = 0;
+        for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++tcount) {
+            const int buf = tcount & 1;
+            mbar_wait(&t_empty[buf], ((tcount >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + buf * NCOLS;
+            const int nst = p.ntaps * nchunk;
+            for (int st = 0; st < nst; ++st, ++it) {
+                const int s = it % kStages;
+                mbar_wait(&full[s], (it / kStages) & 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + buf * NCOLS;
-                const int nst = p.ntaps * nchunk;
-                for (int st = 0; st < nst; ++st, ++it) {
-                    const int s = it % kStages;
-                    mbar_wait(&full[s], (it / kStages) & 1);
-                    tc_fence_after();
+                if (elect_one()) {
                     const uint32_t a_addr = smem_u32(ring + s * L::stage_bytes);
                     const uint32_t b_addr = a_addr + kAtomBytes;
 #pragma unroll
@@ -140,8 +143,9 @@ tconv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant_
                         tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 32, 16, 1024),
                                     make_desc(b_addr + ks * 32, 16, 1024), idesc, (st | ks) ? 1u : 0u);
                     tc_commit(&empty[s]);
+                    if (st == nst - 1) tc_commit(&t_full[buf]);
                 }
-                tc_commit(&t_full[buf]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
