@@ -121,14 +121,27 @@ def algorithmic_bytes(kernel, batch, shape):
         if kernel == 'gcn_fwd':          # residual 1x1 conv (mma.sync engine): reads x, writes r
             if res == 2:
                 per_launch.append(4 * r_out * (cin + cout))
-        elif kernel == 'gcn_tc':         # forward: reads x, writes z; input gradient: reads g1, z
-            per_launch.append(4 * r_in * (cin + cout))                      # [+ go], writes gin + dz
-        elif kernel == 'gcn_tc_bwd':
-            per_launch.append(4 * r_in * (3 * cout + cin + (cin if res == 1 else 0)))
+        elif kernel == 'gcn_tc':         # forward: reads x, writes z (block 0 runs gcn_small_*)
+            if cin >= 32:
+                per_launch.append(4 * r_in * (cin + cout))
+        elif kernel == 'gcn_tc_bwd':     # input gradient: reads dz, writes gin (reduce-add on top
+            if cin >= 32:                # of the residual gradient: read + write)
+                per_launch.append(4 * r_in * (cout + cin * (2 if res else 1)))
+        elif kernel == 'bn_back_apply':  # reads g1, z, writes dz
+            if cin >= 32:
+                per_launch.append(4 * r_in * 3 * cout)
         elif kernel == 'gcn_tc_dvals':   # reads dz, x
-            per_launch.append(4 * r_in * (cout + cin))
+            if cin >= 32:
+                per_launch.append(4 * r_in * (cout + cin))
         elif kernel == 'gcn_tc_dw':      # reads dz, x (+ dz again for the bias-term column sums)
-            per_launch.append(4 * r_in * (2 * cout + cin))
+            if cin >= 32:
+                per_launch.append(4 * r_in * (2 * cout + cin))
+        elif kernel == 'gcn_small_fwd':  # block 0: reads x (3 channels), writes z
+            if cin < 32:
+                per_launch.append(4 * r_in * (cin + cout))
+        elif kernel == 'gcn_small_bwd':  # block 0: reads g1, z, x, writes dx
+            if cin < 32:
+                per_launch.append(4 * r_in * (2 * cout + 2 * cin))
         elif kernel == 'gcn_bwd_x':      # residual conv only: reads go, rres, read-modify-write gin
             if res == 2:
                 per_launch.append(4 * r_out * (2 * cout + 2 * cin))
