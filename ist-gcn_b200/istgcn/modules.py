@@ -128,22 +128,39 @@ class FusedBlockMixin(object):
                 self._cfg.bnr = ops.BNState(self.residual[1])
         return self._cfg
 
-    def forward_cl(self, x, adjs, m_imp, pattern):
-        """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
-        cfg = self._block_cfg(pattern)
-        cfg.training = self.training
-        cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
+    def prepare_operands(self, adjs, m_imp, pattern):
+        """The kernel operands of this block from the reference-layout parameters (~50 tiny
+        differentiable torch ops).  They depend on parameters only, so the model runs them for
+        ALL blocks on a side stream ahead of the block kernels (FusedModelMixin._trunk); autograd
+        runs their backward on that stream too, off the critical path."""
         conv = self._gcn_conv()
         vals, wc, biasterm, w2 = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
         wd, bd, weff, beff, wu, bu = bottleneck_tcn_operands(
             self.conv_1x1_start, self.tcn_1, self.tcn_2, self.tcn_3, self.conv_1x1_end, m_imp)
-        bn1, bn2 = self.tcn_start[0], self.tcn_end[0]
-        wr = btr = bnr_w = bnr_b = None
+        wr = btr = None
         if self._res_mode == 2:
-            rconv, rbn = self.residual[0], self.residual[1]
+            rconv = self.residual[0]
             cout, cin = rconv.weight.shape[0], rconv.weight.shape[1]
-            wr = rconv.weight.view(cout, cin).t()
-            btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout)
+            wr = rconv.weight.view(cout, cin).t().contiguous()
+            btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout).contiguous()
+        # everything the kernels touch is made contiguous here, not on the main stream
+        w2 = tuple(None if t is None else t.contiguous() for t in w2)
+        return (vals.contiguous(), wc.contiguous(), biasterm.contiguous(), w2, wd.contiguous(),
+                bd.contiguous(), weff.contiguous(), beff.contiguous(), wu.contiguous(), bu.contiguous(),
+                wr, btr)
+
+    def forward_cl(self, x, adjs, m_imp, pattern, operands=None):
+        """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
+        cfg = self._block_cfg(pattern)
+        cfg.training = self.training
+        cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
+        if operands is None:
+            operands = self.prepare_operands(adjs, m_imp, pattern)
+        vals, wc, biasterm, w2, wd, bd, weff, beff, wu, bu, wr, btr = operands
+        bn1, bn2 = self.tcn_start[0], self.tcn_end[0]
+        bnr_w = bnr_b = None
+        if self._res_mode == 2:
+            rbn = self.residual[1]
             bnr_w, bnr_b = rbn.weight, rbn.bias
         out = ops.STBlock.apply(x, vals, wc, biasterm, w2, bn1.weight, bn1.bias, wd, bd, weff, beff, wu,
                                 bu, bn2.weight, bn2.bias, wr, btr, bnr_w, bnr_b, cfg)
@@ -232,6 +249,35 @@ class FusedWideBlockMixin(object):
         return out
 
 
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+        # parameters are used on the side stream, so their AccumulateGrad nodes run there by
+        # design; autograd joins every stream it used with the caller's stream after backward
+        quiet = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+        if quiet is not None:
+            quiet(False)
+    return _side_streams[key]
+
+
+def _side_stream_enabled():
+    import os
+    return os.environ.get('ISTGCN_SIDE_STREAM', '1') != '0'
+
+
+def _flatten(operands):
+    for t in operands:
+        if isinstance(t, tuple):
+            for u in _flatten(t):
+                yield u
+        elif t is not None:
+            yield t
+
+
 class FusedModelMixin(object):
     """Model.forward / extract_feature shared by every variant (st_gcnold.py:71-120): data_bn
     with the layout change, the block loop, global pooling, the ``fcn`` 1x1 conv."""
@@ -267,12 +313,36 @@ class FusedModelMixin(object):
         imp2 = getattr(self, 'edge_importance2', None)
         imp3 = getattr(self, 'edge_importance3', None)
         m_imp = getattr(self, 'mstcn_importance', None)
-        for i, blk in enumerate(self.st_gcn_networks):
+        def adjs_of(i):
             adjs = [self.A * imp1[i]]
             if imp2 is not None:
                 adjs.append(self.A2 * imp2[i])
                 adjs.append(self.A3 * imp3[i])
-            x = blk.forward_cl(x, adjs, m_imp[i] if m_imp is not None else None, pattern)
+            return adjs
+
+        blocks = list(self.st_gcn_networks)
+        if _side_stream_enabled() and all(hasattr(b, 'prepare_operands') for b in blocks):
+            # parameter regrouping of every block on a side stream, one event per block: block i
+            # waits for ITS operands only, blocks i+1.. are regrouped while block i computes
+            main = torch.cuda.current_stream()
+            side = _side_stream(x.device)
+            side.wait_stream(main)
+            prepared = []
+            with torch.cuda.stream(side):
+                for i, blk in enumerate(blocks):
+                    opnds = blk.prepare_operands(adjs_of(i), m_imp[i] if m_imp is not None else None,
+                                                 pattern)
+                    for t in _flatten(opnds):
+                        t.record_stream(main)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    prepared.append((opnds, ev))
+            for blk, (opnds, ev) in zip(blocks, prepared):
+                main.wait_event(ev)
+                x = blk.forward_cl(x, None, None, pattern, operands=opnds)
+            return x
+        for i, blk in enumerate(blocks):
+            x = blk.forward_cl(x, adjs_of(i), m_imp[i] if m_imp is not None else None, pattern)
         return x
 
     def forward(self, x):
