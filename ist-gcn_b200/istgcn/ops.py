@@ -241,9 +241,21 @@ class STBlock(Function):
              i64(R_out), Cout, float(drop_p), u64(seed), step_counter(dev))
         p2, m12, c2, dg2, db2 = _coeffs(5, Cout, dev)
         call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2, Cout)
-        dWd, dbd = torch.zeros_like(Wd), torch.zeros(bp, device=dev)
-        dWeff, dbeff = torch.zeros_like(Weff), torch.zeros(bp, device=dev)
-        dWu, dbu = torch.zeros_like(Wu), torch.zeros(Cout, device=dev)
+        # every caller-zeroed fp32 accumulator of this block out of ONE zero-filled buffer (one fill
+        # launch instead of twelve); each view starts on a 16-byte boundary
+        need_r = cfg.res_mode == 2
+        shapes = [tuple(Wd.shape), (bp,), tuple(Weff.shape), (bp,), tuple(Wu.shape), (Cout,),
+                  tuple(vals.shape), tuple(Wc.shape), (V, Cout)]
+        if need_r:
+            shapes += [tuple(Wr.shape), (V, Cout)]
+        sizes = [(int(torch.Size(sh).numel()) + 3) // 4 * 4 for sh in shapes]
+        flat = torch.zeros(sum(sizes), device=dev, dtype=torch.float32)
+        views, off = [], 0
+        for sh, n in zip(shapes, sizes):
+            views.append(flat[off:off + torch.Size(sh).numel()].view(sh))
+            off += n
+        dWd, dbd, dWeff, dbeff, dWu, dbu, dvals, dWc, dbt = views[:9]
+        dWr_z, dbtr_z = (views[9], views[10]) if need_r else (None, None)
         g1 = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
         dh2 = torch.empty(R_out, bp, device=dev, dtype=torch.float32)
         dh1 = torch.empty(R_in, bp, device=dev, dtype=torch.float32)
@@ -256,7 +268,6 @@ class STBlock(Function):
         # gradient is accumulated onto it in place (TMA reduce-add on the tcgen05 engine); every
         # other reader of `go` has already run on this stream
         gin = go if cfg.res_mode == 1 else torch.empty_like(x)
-        dvals = torch.zeros_like(vals)
         add_in = gin if cfg.res_mode == 1 else None
         # strided-conv residual: its input gradient (one tap of the TMA-fed temporal-convolution
         # kernel, transposed) is written FIRST -- every `s`-th frame of a zeroed gin -- and the
@@ -274,7 +285,6 @@ class STBlock(Function):
             call('tconv_tc', dyr, Wr.contiguous(), None, gin, None, None, NM, T, Tout, V, Cout, Cin, 1, s, -1)
             add_in = gin
         small = _gcn_small_ok(Cin, Cout) and cfg.res_mode == 0
-        dWc, dbt = torch.zeros_like(Wc), torch.zeros(V, Cout, device=dev)
         if small:
             # first block: dz, dx, dvals, dWc and dbt in one CUDA-core kernel
             call('gcn_small_bwd', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.dst_ptr, pat.dst_src,
@@ -312,7 +322,7 @@ class STBlock(Function):
         if not fused_res:
             dgr = dbr = None
         if fused_res:
-            dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, Cout, device=dev)
+            dWr, dbtr = dWr_z, dbtr_z
             if Cout <= 128 or Cout % 128 == 0:
                 call('tconv_dw_tc', x, dyr, dWr, dbtr, NM, T, Tout, V, Cin, Cout, 1, s)
             else:
@@ -324,7 +334,7 @@ class STBlock(Function):
             pr, m1r, cr, dgr, dbr = _coeffs(5, Cout, dev)
             call('bn_bwd_coeffs', sums[2], sums[3], f64(R_out), bnr_w, rstd_r, pr, m1r, cr, dgr, dbr,
                  Cout)
-            dWr, dbtr = torch.zeros_like(Wr), torch.zeros(V, Cout, device=dev)
+            dWr, dbtr = dWr_z, dbtr_z
             if use_tc():
                 dyr = torch.empty_like(rres)
                 call('gcn_tc', go, rres, pr, m1r, cr, mean_r, Wr, cfg.ones, idn.t_ptr, idn.t_src,
