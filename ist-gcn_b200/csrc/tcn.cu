@@ -129,15 +129,17 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
     float* h2s = hs + TI * V * LDH;             // [256][LDH]
     float* Wts = h2s + kUpRows * LDH;           // [15*BP][LDW]
     float* Wus = Wts + kTaps * BP * LDW;        // [BP][LDU]
-    // BatchNorm partial sums in double (see gcn.cu: the one-pass variance cancels in fp32)
-    double* s_sum = reinterpret_cast<double*>(Wus + BP * LDU);   // [C]
-    double* s_sq = s_sum + C;                                    // [C]
+    // BatchNorm sums: fp32 column sums of each warp's 16 rows -> s_col[warp][C][2], then thread c
+    // adds the (at most 8) partials of channel c to its DOUBLE register accumulators once per
+    // tile (the one-pass variance cancels in fp32, see gcn.cu; no shared-memory atomics: the
+    // emulated fp64 atomics were ~40 % of this kernel's instructions)
+    float* s_col = Wus + BP * LDU;                               // [8][C][2]
+    double acc_s = 0.0, acc_q = 0.0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
     for (int i = tid; i < kTaps * BP * BP; i += kThreads) Wts[(i / BP) * LDW + (i % BP)] = p.Weff[i];
     for (int i = tid; i < BP * C; i += kThreads) Wus[(i / C) * LDU + (i % C)] = p.Wu[i];
-    for (int i = tid; i < 2 * C; i += kThreads) s_sum[i] = 0.0;
 
     const int total = p.NM * p.tiles_per_sample;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
                 }
                 const int c = nt * 8 + 2 * t;
                 const float b0 = p.bu[c], b1 = p.bu[c + 1];
-                double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
+                float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = mt * 16 + g + 8 * h;
@@ -232,26 +234,32 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
                         const float v0 = acc[2 * h] + b0, v1 = acc[2 * h + 1] + b1;
                         *reinterpret_cast<float2*>(
                             p.u + (((size_t)n * p.Tout + to0) * V + r) * C + c) = make_float2(v0, v1);
-                        s0 += v0; s1 += v1; q0 += (double)v0 * v0; q1 += (double)v1 * v1;
+                        s0 += v0; s1 += v1; q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
                     }
                 }
                 if (p.stat_sum) {
                     s0 = group_sum_g(s0); s1 = group_sum_g(s1);
                     q0 = group_sum_g(q0); q1 = group_sum_g(q1);
-                    if (g == 0) {
-                        atomicAdd(&s_sum[c], s0); atomicAdd(&s_sum[c + 1], s1);
-                        atomicAdd(&s_sq[c], q0); atomicAdd(&s_sq[c + 1], q1);
-                    }
+                    if (g == 0)
+                        *reinterpret_cast<float4*>(s_col + ((size_t)mt * C + c) * 2) =
+                            make_float4(s0, q0, s1, q1);
+                }
+            }
+        }
+        if (p.stat_sum) {
+            __syncthreads();
+            if (tid < C) {
+                for (int m = 0; m * 16 < valid; ++m) {
+                    const float2 v = *reinterpret_cast<const float2*>(s_col + ((size_t)m * C + tid) * 2);
+                    acc_s += (double)v.x;
+                    acc_q += (double)v.y;
                 }
             }
         }
     }
-    if (p.stat_sum) {
-        __syncthreads();
-        for (int c = tid; c < C; c += kThreads) {
-            atomicAdd(&p.stat_sum[c], s_sum[c]);
-            atomicAdd(&p.stat_sumsq[c], s_sq[c]);
-        }
+    if (p.stat_sum && tid < C) {
+        atomicAdd(&p.stat_sum[tid], acc_s);
+        atomicAdd(&p.stat_sumsq[tid], acc_q);
     }
 }
 
@@ -881,7 +889,7 @@ ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* mean1, const float* s
         p.tiles_per_sample = (Tout + p.TT - 1) / p.TT;
         const int TI = (p.TT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)TI * V * ld_g(bp) + kUpRows * ld_g(bp) +
-                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 4 * C);
+                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 16 * C);
         const int grid = grid_for((long long)NM * p.tiles_per_sample, 4);
 #define LAUNCH_UP(NT, PC)                                            \
     set_smem(tcn_up_kernel<NT, PC>, smem);                           \
