@@ -134,12 +134,14 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
     // tile (the one-pass variance cancels in fp32, see gcn.cu; no shared-memory atomics: the
     // emulated fp64 atomics were ~40 % of this kernel's instructions)
     float* s_col = Wus + BP * LDU;                               // [8][C][2]
+    float* bus = s_col + 16 * C;                                 // [C] conv_1x1_end bias
     double acc_s = 0.0, acc_q = 0.0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
 
     for (int i = tid; i < kTaps * BP * BP; i += kThreads) Wts[(i / BP) * LDW + (i % BP)] = p.Weff[i];
     for (int i = tid; i < BP * C; i += kThreads) Wus[(i / C) * LDU + (i % C)] = p.Wu[i];
+    for (int i = tid; i < C; i += kThreads) bus[i] = p.bu[i];
 
     const int total = p.NM * p.tiles_per_sample;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -215,27 +217,31 @@ __global__ void __launch_bounds__(kThreads) tcn_up_kernel(TcnUpParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     a[kk][i] = h2s[(mt * 16 + g + 8 * (i & 1)) * LDH + kk * 8 + t + 4 * (i >> 1)];
+            // row pointers and validity hoisted out of the column loop; the bias seeds the accumulator
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+            const bool ok0 = r0 < valid, ok1 = r1 < valid;
+            float* u0 = p.u + (((size_t)n * p.Tout + to0) * V + r0) * C + 2 * t;
+            float* u1 = u0 + (size_t)8 * C;
+            const float* wb = Wus + t * LDU + g;
             for (int nt = 0; nt < C / 8; ++nt) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float2 bb = *reinterpret_cast<const float2*>(bus + nt * 8 + 2 * t);
+                float acc[4] = {bb.x, bb.y, bb.x, bb.y};
 #pragma unroll
                 for (int kk = 0; kk < NT; ++kk) {
                     float b[2];
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) b[i] = Wus[(kk * 8 + t + 4 * i) * LDU + nt * 8 + g];
+                    for (int i = 0; i < 2; ++i) b[i] = wb[(kk * 8 + 4 * i) * LDU + nt * 8];
                     mma_step<PRECISE>(acc, a[kk], b);
                 }
                 const int c = nt * 8 + 2 * t;
-                const float b0 = p.bu[c], b1 = p.bu[c + 1];
                 float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int r = mt * 16 + g + 8 * h;
-                    if (r < valid) {
-                        const float v0 = acc[2 * h] + b0, v1 = acc[2 * h + 1] + b1;
-                        *reinterpret_cast<float2*>(
-                            p.u + (((size_t)n * p.Tout + to0) * V + r) * C + c) = make_float2(v0, v1);
-                        s0 += v0; s1 += v1; q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
-                    }
+                if (ok0) {
+                    *reinterpret_cast<float2*>(u0 + nt * 8) = make_float2(acc[0], acc[1]);
+                    s0 = acc[0]; s1 = acc[1]; q0 = acc[0] * acc[0]; q1 = acc[1] * acc[1];
+                }
+                if (ok1) {
+                    *reinterpret_cast<float2*>(u1 + nt * 8) = make_float2(acc[2], acc[3]);
+                    s0 += acc[2]; s1 += acc[3]; q0 = fmaf(acc[2], acc[2], q0); q1 = fmaf(acc[3], acc[3], q1);
                 }
                 if (p.stat_sum) {
                     s0 = group_sum_g(s0); s1 = group_sum_g(s1);
@@ -889,7 +895,7 @@ ISTGCN_API int istgcn_tcn_fwd(const float* z, const float* mean1, const float* s
         p.tiles_per_sample = (Tout + p.TT - 1) / p.TT;
         const int TI = (p.TT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)TI * V * ld_g(bp) + kUpRows * ld_g(bp) +
-                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 16 * C);
+                                             kTaps * bp * ld_t(bp) + bp * (C + 8) + 17 * C);
         const int grid = grid_for((long long)NM * p.tiles_per_sample, 4);
 #define LAUNCH_UP(NT, PC)                                            \
     set_smem(tcn_up_kernel<NT, PC>, smem);                           \
