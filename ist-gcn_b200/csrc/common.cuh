@@ -38,6 +38,13 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
     return r;
 }
 
+// Round-to-nearest TF32 for the fast mode in ONE integer add: the tensor core ignores the low 13
+// mantissa bits, so adding half a TF32 ulp to the fp32 bit pattern turns its truncation into
+// rounding.  (cvt.rna.tf32.f32 is emulated on sm_100a: FSETP + IADD + LOP3 + a constant move per
+// value, six values per mma -- a quarter of the TCN kernels' instructions.  Inf/NaN inputs are not
+// special-cased here; the 3xTF32 parity mode keeps the exact conversion.)
+__device__ __forceinline__ uint32_t to_tf32_fast(float x) { return __float_as_uint(x) + 0x1000u; }
+
 // D(16x8) += A(16x8, row) * B(8x8, col), TF32 inputs, fp32 accumulate (legacy mma.sync path;
 // used for the skinny GEMMs whose N or M is the 8..16-wide bottleneck).
 __device__ __forceinline__ void mma_m16n8k8(float (&d)[4], const uint32_t (&a)[4],
@@ -77,7 +84,7 @@ __device__ __forceinline__ void warp_mma_raw(float (&acc)[MT][NT][4], const floa
                 const int k = k0 + t + 4 * (i >> 1);
                 const float v = A_T ? A[k * lda + m] : A[m * lda + k];
                 if (PRECISE) split_tf32(v, ah[mt][i], al[mt][i]);
-                else ah[mt][i] = to_tf32(v);
+                else ah[mt][i] = to_tf32_fast(v);
             }
         }
 #pragma unroll
@@ -89,7 +96,7 @@ __device__ __forceinline__ void warp_mma_raw(float (&acc)[MT][NT][4], const floa
                 const int n = nt * 8 + g;
                 const float v = B_T ? B[n * ldb + k] : B[k * ldb + n];
                 if (PRECISE) split_tf32(v, bh[i], bl[i]);
-                else bh[i] = to_tf32(v);
+                else bh[i] = to_tf32_fast(v);
             }
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
@@ -141,12 +148,12 @@ __device__ __forceinline__ void mma_step(float (&acc)[4], const float (&a)[4], c
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (PRECISE) split_tf32(a[i], ah[i], al[i]);
-        else ah[i] = to_tf32(a[i]);
+        else ah[i] = to_tf32_fast(a[i]);
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         if (PRECISE) split_tf32(b[i], bh[i], bl[i]);
-        else bh[i] = to_tf32(b[i]);
+        else bh[i] = to_tf32_fast(b[i]);
     }
     if (PRECISE) {
         float part[4] = {0.f, 0.f, 0.f, 0.f};
@@ -192,16 +199,32 @@ __device__ __forceinline__ double group_sum_g(double v) {
     return v;
 }
 
-// Counter-based dropout keep decision: one 64-bit mix per element, identical in the forward
-// and backward kernels (nn.Dropout's Philox stream cannot be reproduced from a custom kernel;
-// parity tests read the mask back through istgcn_dropout_mask).
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p) {
-    uint64_t x = seed + idx * 0x9E3779B97F4A7C15ull;
+// Counter-based dropout keep decisions: ONE 64-bit mix per group of four consecutive elements
+// (every kernel walks float4 groups), 16 bits of it per element; identical in the forward and
+// backward kernels (nn.Dropout's Philox stream cannot be reproduced from a custom kernel; parity
+// tests read the mask back through istgcn_dropout_mask).  The per-element 64-bit mix this
+// replaces was ~30 integer instructions per element -- 25 % of tcn_bwd_up's instruction count.
+__device__ __forceinline__ uint64_t dropout_bits(uint64_t seed, uint64_t group) {
+    uint64_t x = seed + group * 0x9E3779B97F4A7C15ull;
     x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
     x ^= x >> 27; x *= 0x94D049BB133111EBull;
     x ^= x >> 31;
-    const float u = (float)(uint32_t)(x >> 40) * (1.0f / 16777216.0f);   // 24 bits -> [0, 1)
-    return u >= p;
+    return x;
+}
+__device__ __forceinline__ uint32_t dropout_threshold(float p) {      // keep iff 16 bits >= threshold
+    return (uint32_t)(p * 65536.0f + 0.5f);
+}
+// keep[j] for elements 4*group + j
+__device__ __forceinline__ void dropout_keep4(uint64_t seed, uint64_t group, float p, bool (&keep)[4]) {
+    const uint64_t x = dropout_bits(seed, group);
+    const uint32_t thr = dropout_threshold(p);
+    const uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    keep[0] = (lo & 0xFFFFu) >= thr; keep[1] = (lo >> 16) >= thr;
+    keep[2] = (hi & 0xFFFFu) >= thr; keep[3] = (hi >> 16) >= thr;
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p) {
+    const uint64_t x = dropout_bits(seed, idx >> 2);
+    return (uint32_t)((x >> (16 * (idx & 3))) & 0xFFFFu) >= dropout_threshold(p);
 }
 
 // BatchNorm forward on one element, cancellation-free: (x - mean) * scale + beta

@@ -188,9 +188,10 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
         float y[4] = {bn_apply(uu.x, mu.x, sc.x, be.x), bn_apply(uu.y, mu.y, sc.y, be.y),
                       bn_apply(uu.z, mu.z, sc.z, be.z), bn_apply(uu.w, mu.w, sc.w, be.w)};
         if (drop_p > 0.f) {
+            bool keep[4];
+            dropout_keep4(seed, (uint64_t)i, drop_p, keep);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                y[j] = dropout_keep(seed, (uint64_t)(i * 4 + j), drop_p) ? y[j] * keep_scale : 0.f;
+            for (int j = 0; j < 4; ++j) y[j] = keep[j] ? y[j] * keep_scale : 0.f;
         }
         if (mode == 1) {
             const float4 r = ld4(res + i * 4);
@@ -247,13 +248,14 @@ __global__ void block_tail_bwd_kernel(const float* __restrict__ gout, const floa
                 const float4 rv = ld4(rres + off);
                 r4[0] = rv.x; r4[1] = rv.y; r4[2] = rv.z; r4[3] = rv.w;
             }
+            bool keep[4] = {true, true, true, true};
+            if (drop_p > 0.f) dropout_keep4(seed, (uint64_t)(off >> 2), drop_p, keep);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float gj = o4[j] > 0.f ? g4[j] : 0.f;
                 g4[j] = gj;
                 float gy = gj;
-                if (drop_p > 0.f)
-                    gy = dropout_keep(seed, (uint64_t)(off + j), drop_p) ? gj * keep_scale : 0.f;
+                if (drop_p > 0.f) gy = keep[j] ? gj * keep_scale : 0.f;
                 a_g[j] += gy;
                 a_gx[j] += gy * (u4[j] - mu[j]) * rs[j];
                 if (HAS_R) {

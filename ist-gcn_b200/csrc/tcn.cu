@@ -340,10 +340,10 @@ __global__ void __launch_bounds__(kThreads, 4) tcn_bwd_up_kernel(TcnBwdUpParams 
                                      cv = ld4(p.c2 + c0 + c4), nv = ld4(p.mean2 + c0 + c4);
                         float gy[4] = {gv.x, gv.y, gv.z, gv.w};
                         if (p.drop_p > 0.f) {
+                            bool keep[4];
+                            dropout_keep4(eseed, (uint64_t)(off >> 2), p.drop_p, keep);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                gy[j] = dropout_keep(eseed, (uint64_t)(off + j), p.drop_p)
-                                            ? gy[j] * p.keep_scale : 0.f;
+                            for (int j = 0; j < 4; ++j) gy[j] = keep[j] ? gy[j] * p.keep_scale : 0.f;
                         }
                         v.x = bn_back(gy[0], uv.x, pv.x, mv.x, cv.x, nv.x);
                         v.y = bn_back(gy[1], uv.y, pv.y, mv.y, cv.y, nv.y);

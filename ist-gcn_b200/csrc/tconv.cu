@@ -42,9 +42,10 @@ __global__ void bn_back_apply_kernel(const float* __restrict__ go, const float* 
         const float4 pv = ld4(p + c), mv = ld4(m1 + c), cv = ld4(cc + c), nv = ld4(mean + c);
         float g[4] = {gv.x, gv.y, gv.z, gv.w};
         if (drop_p > 0.f) {
+            bool keep[4];
+            dropout_keep4(seed, (uint64_t)i, drop_p, keep);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                g[j] = dropout_keep(seed, (uint64_t)(i * 4 + j), drop_p) ? g[j] * keep_scale : 0.f;
+            for (int j = 0; j < 4; ++j) g[j] = keep[j] ? g[j] * keep_scale : 0.f;
         }
         st4(du + i * 4, make_float4(bn_back(g[0], uv.x, pv.x, mv.x, cv.x, nv.x),
                                     bn_back(g[1], uv.y, pv.y, mv.y, cv.y, nv.y),
