@@ -476,23 +476,28 @@ __global__ void __launch_bounds__(kThreads) tcn_bwd_t_kernel(TcnBwdTParams p) {
             if (r < valid) v = ld4(p.h1 + (((size_t)n * p.T + ti0) * V + r) * BP + c4);
             st4(h1s + r * LDT + c4, v);
         }
+        // per row: {n0 = ti0 + frame + 7, joint offset | valid-tap mask << 16}: tap `tap` reads output
+        // frame (n0 - tap) / s when bit `tap` of the mask is set (in range, right parity)
+        const int sh = s == 2 ? 1 : 0;
         for (int r = tid; r < kUpRows; r += kThreads) {
-            const int ti_l = r / V;
-            s_row[r] = r < valid ? make_int2(ti_l, (r - ti_l * V) * LDH) : make_int2(-1, 0);
+            int2 e = make_int2(0, 0);
+            if (r < valid) {
+                const int ti_l = r / V;
+                const int n0 = ti0 + ti_l + kHalf;
+                unsigned mask = 0;
+                for (int tap = 0; tap < kTaps; ++tap) {
+                    const int num = n0 - tap;
+                    if (num >= 0 && (num & sh) == 0 && (num >> sh) < p.Tout) mask |= 1u << tap;
+                }
+                e = make_int2(n0, ((r - ti_l * V) * LDH) | (int)(mask << 16));
+            }
+            s_row[r] = e;
         }
         __syncthreads();
-        // gather offset of the dh2 row that feeds input row (frame ri.x, joint) at `tap`; -1: none
+        const int VL = V * LDH;
         auto src_off = [&](int2 ri, int tap) -> int {
-            if (ri.x < 0) return -1;
-            const int num = ti0 + ri.x + kHalf - tap;
-            if (num < 0) return -1;
-            int to = num;
-            if (s == 2) {
-                if (num & 1) return -1;
-                to = num >> 1;
-            }
-            if (to >= p.Tout) return -1;
-            return (to - to_lo) * V * LDH + ri.y;
+            const int off = (((ri.x - tap) >> sh) - to_lo) * VL + (ri.y & 0xFFFF);
+            return ((ri.y >> (16 + tap)) & 1) ? off : -1;
         };
         // ---- dh1
         for (int mt = warp; mt * 16 < valid; mt += kWarps) {
