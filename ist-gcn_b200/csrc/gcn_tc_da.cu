@@ -18,6 +18,8 @@
 //               in shared memory (128-bit reads, four independent partial sums), shared-memory
 //               atomics per non-zero
 //   warps 8-11  loaders: x slice -> shared memory, [row][32 ci] with a 36-float pitch
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace istgcn {
@@ -284,6 +286,12 @@ ISTGCN_API int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float*
     ISTGCN_REQUIRE(Cin >= 1 && (Cin < 32 || Cin % 32 == 0), ISTGCN_E_SHAPE, "gcn_tc_dvals: Cin=%d unsupported", Cin);
     ISTGCN_REQUIRE(nnz >= 0 && nnz <= kMaxNnz, ISTGCN_E_SHAPE, "gcn_tc_dvals: nnz=%d", nnz);
     if (frames == 0) return 0;
+    // second-generation kernel (both contractions on the tensor core, gcn_tc_da2.cu)
+    static const bool force_v1 = getenv("ISTGCN_GCN_TC_V1") != nullptr;
+    if (!force_v1 && tc::gcn_tc_da2_eligible(V, K, Cin, Cout) &&
+        ((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(Wc)) & 15) == 0)
+        return tc::launch_gcn_tc_da2(dz, x, Wc, lptr, lsrc, lid, nnz, dvals, frames, V, K, Cin, Cout,
+                                     (cudaStream_t)s);
     tc::GcnDaParams p{x, nullptr, lptr, lsrc, lid, dvals, frames, V, K, Cin, (Cin + 31) / 32 * 32, Cout, nnz, 0};
     const int F = kTileRows / V > 8 ? 8 : kTileRows / V;
     p.tiles = (frames + F - 1) / F;

@@ -368,6 +368,11 @@ bool gcn_tc_dw2_eligible(int V, int K, int Cin, int Cout);
 int launch_gcn_tc_dw2(const float* dz, const float* x, const float* vals, const int* lptr,
                       const int* lsrc, const int* lid, float* dWc, int frames, int V, int K, int Cin,
                       int Cout, cudaStream_t st);
+// second-generation adjacency-gradient kernel (gcn_tc_da2.cu)
+bool gcn_tc_da2_eligible(int V, int K, int Cin, int Cout);
+int launch_gcn_tc_da2(const float* dz, const float* x, const float* Wc, const int* lptr, const int* lsrc,
+                      const int* lid, int nnz, float* dvals, int frames, int V, int K, int Cin, int Cout,
+                      cudaStream_t st);
 // out[j] += sum_f in[f][j], j < n (gcn_tc_dw.cu)
 int launch_frame_colsum(const float* in, float* out, int frames, int n, cudaStream_t st);
 
