@@ -194,6 +194,72 @@ def test_first_block_kernels_vs_fp64(env, layout, strategy, cin, nm, t):
     assert rel(dvals, A64.grad.reshape(-1)[pat.flat_idx.cpu()]) < 1e-5
 
 
+# ----------------------------------------------------------------------------- tcgen05, 2nd generation
+@pytest.mark.parametrize('layout,strategy,cin,cout,frames', [
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 64, 64, 1),        # a single frame (3 empty slots in the tile)
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 64, 64, 7),        # ragged last tile
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 64, 128, 333),
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 128, 128, 601),    # dw2: two CTA groups
+    ('ntu-rgb+d_sym', 'spatial_3_sym', 256, 256, 203),    # tc2 <256>; dw / dvals first generation
+    ('openpose_sym', 'spatial_3_sym', 64, 96, 250),       # V = 18, Cout not a power of two
+    ('ntu-rgb+d', 'spatial', 96, 64, 250),                # K = 3
+    ('ntu-rgb+d', 'uniform', 64, 64, 100),                # K = 1
+])
+def test_tensor_core_graph_conv_entry_points_vs_fp64(env, layout, strategy, cin, cout, frames):
+    """istgcn_gcn_tc (forward + BatchNorm sums, and the reduce-add input-gradient form),
+    istgcn_gcn_tc_dw and istgcn_gcn_tc_dvals called directly -- i.e. gcn_tc2 / gcn_tc_dw2 /
+    gcn_tc_da2 wherever they are eligible -- against an fp64 evaluation of tgcn.py:76-89.
+    Single-pass TF32 on every operand: 5e-3 relative (the mode's bar is 2e-2)."""
+    from istgcn._lib import call
+    from istgcn.sparse import SparsePattern
+    from net.utils.graph import Graph
+    dev = torch.device('cuda')
+    g = Graph(layout, strategy)
+    A = sum(torch.tensor(getattr(g, n), dtype=torch.float64) for n in ('A', 'A2', 'A3') if hasattr(g, n))
+    K, V = A.shape[0], A.shape[1]
+    pat = SparsePattern((A != 0).numpy(), dev)
+    vals = A.reshape(-1)[pat.flat_idx.cpu()].float().to(dev)
+    gen = torch.Generator().manual_seed(cin + 7 * cout + frames)
+    x = torch.randn(frames * V, cin, generator=gen).to(dev)
+    W2 = (torch.randn(K * cout, cin, generator=gen) * 0.05).to(dev)       # rows k*Cout + n
+    bias = torch.randn(K, cout, generator=gen).to(dev)
+    colsum = A.sum(1).float().contiguous().to(dev)
+    Ad = A.to(dev)
+    xa = torch.einsum('fvc,kvw->kfwc', x.view(frames, V, cin).double(), Ad)
+    ref = torch.einsum('kfwc,knc->fwn', xa, W2.view(K, cout, cin).double()) + \
+        torch.einsum('kw,kn->wn', colsum.double(), bias.double())[None]
+    z = torch.full((frames * V, cout), float('nan'), device=dev)
+    st = torch.zeros(2, cout, device=dev, dtype=torch.float64)
+    call('gcn_tc', x, None, None, None, None, None, W2, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz,
+         bias, colsum, None, z, None, st[0], st[1], frames, V, K, cin, cin, cout, 0, 0, 1, 0, 0)
+    ref2 = ref.reshape(frames * V, cout)
+    assert rel(z, ref2) < 5e-3
+    assert rel(st[0], ref2.sum(0), floor=1e-3 * ref2.abs().sum(0).max().item()) < 5e-3
+    assert rel(st[1], (ref2 * ref2).sum(0)) < 5e-3
+    # input-gradient form: transposed lists, Wc, accumulated in place onto the residual gradient
+    dz = torch.randn(frames * V, cout, generator=gen).to(dev)
+    Wc = W2.view(K, cout, cin).permute(0, 2, 1).reshape(K * cin, cout).contiguous()
+    gin0 = torch.randn(frames * V, cin, generator=gen).to(dev)
+    gin = gin0.clone()
+    call('gcn_tc', dz, None, None, None, None, None, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id, pat.nnz, None,
+         None, gin, gin, None, None, None, frames, V, K, cout, cout, cin, 0, 0, 1, 0, 0)
+    G = torch.einsum('fwn,kcn->kfwc', dz.view(frames, V, cout).double(), Wc.view(K, cin, cout).double())
+    dx = torch.einsum('kfwc,kvw->fvc', G, Ad).reshape(frames * V, cin) + gin0.double()
+    assert rel(gin, dx) < 5e-3
+    # weight gradient + bias-term gradient
+    dW, dbt = torch.zeros(K * cin, cout, device=dev), torch.zeros(V, cout, device=dev)
+    call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dW, dbt, frames, V, K, cin,
+         cout, 0, 0, 1, 0)
+    dW_ref = torch.einsum('kfwc,fwn->kcn', xa, dz.view(frames, V, cout).double()).reshape(K * cin, cout)
+    assert rel(dW, dW_ref) < 5e-3
+    assert rel(dbt, dz.view(frames, V, cout).double().sum(0), floor=1e-2) < 1e-4
+    # adjacency gradient on the non-zero pattern
+    dvals = torch.zeros(pat.nnz, device=dev)
+    call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals, frames, V, K, cin, cout)
+    dA = torch.einsum('fvc,kfwc->kvw', x.view(frames, V, cin).double(), G)
+    assert rel(dvals, dA.reshape(-1)[pat.flat_idx]) < 5e-3
+
+
 # ----------------------------------------------------------------------------- data_bn
 def test_data_bn_layout_and_stats(env):
     from istgcn import ops
