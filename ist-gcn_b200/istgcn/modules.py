@@ -221,24 +221,37 @@ class FusedWideBlockMixin(object):
                 self._cfg.bnr = ops.BNState(self.residual[1])
         return self._cfg
 
-    def forward_cl(self, x, adjs, m_imp, pattern):
-        """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
-        cfg = self._block_cfg(pattern)
-        cfg.training = self.training
-        cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
+    def prepare_operands(self, adjs, m_imp, pattern):
+        """Kernel operands from the reference-layout parameters (side stream, see
+        FusedBlockMixin.prepare_operands)."""
         conv = self._gcn_conv()
         vals, wc, biasterm, w2 = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
         if hasattr(self, 'tcn'):
             wtt, bt = merged_temporal_taps([self.tcn[2]], None)
         else:
             wtt, bt = merged_temporal_taps([self.tcn_1, self.tcn_2, self.tcn_3], m_imp, 3.0)
-        bn1, bn2 = self._bns()
-        wr = btr = bnr_w = bnr_b = None
+        wr = btr = None
         if self._res_mode == 2:
-            rconv, rbn = self.residual[0], self.residual[1]
+            rconv = self.residual[0]
             cout, cin = rconv.weight.shape[0], rconv.weight.shape[1]
-            wr = rconv.weight.view(cout, cin).t()
-            btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout)
+            wr = rconv.weight.view(cout, cin).t().contiguous()
+            btr = rconv.bias.unsqueeze(0).expand(pattern.V, cout).contiguous()
+        w2 = tuple(None if t is None else t.contiguous() for t in w2)
+        return (vals.contiguous(), wc.contiguous(), biasterm.contiguous(), w2, wtt.contiguous(),
+                bt.contiguous(), wr, btr)
+
+    def forward_cl(self, x, adjs, m_imp, pattern, operands=None):
+        """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
+        cfg = self._block_cfg(pattern)
+        cfg.training = self.training
+        cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
+        if operands is None:
+            operands = self.prepare_operands(adjs, m_imp, pattern)
+        vals, wc, biasterm, w2, wtt, bt, wr, btr = operands
+        bn1, bn2 = self._bns()
+        bnr_w = bnr_b = None
+        if self._res_mode == 2:
+            rbn = self.residual[1]
             bnr_w, bnr_b = rbn.weight, rbn.bias
         out = ops.STBlockWide.apply(x, vals, wc, biasterm, w2, bn1.weight, bn1.bias, wtt, bt,
                                     bn2.weight, bn2.bias, wr, btr, bnr_w, bnr_b, cfg)
