@@ -327,6 +327,8 @@ class FusedModelMixin(object):
         imp3 = getattr(self, 'edge_importance3', None)
         m_imp = getattr(self, 'mstcn_importance', None)
         def adjs_of(i):
+            if hasattr(self, '_block_adjs'):        # element-power adjacency variants
+                return self._block_adjs(i)
             adjs = [self.A * imp1[i]]
             if imp2 is not None:
                 adjs.append(self.A2 * imp2[i])

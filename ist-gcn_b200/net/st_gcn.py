@@ -16,10 +16,17 @@ from net.utils.tgcn import ConvTemporalGraphical
 
 class Model(FusedModelMixin, nn.Module):
     r"""Model(in_channels, num_class, graph_args, edge_importance_weighting, **kwargs)
-    (N, in_channels, T, V, M) -> (N, num_class)."""
+    (N, in_channels, T, V, M) -> (N, num_class).
+
+    ``BLOCK`` / ``N_IMPORTANCE`` are the hooks of the element-power adjacency variants
+    (net/st_gcn_multi3*.py, st_gcn_only3.py, st_gcn_learnA.py: the same file with another
+    ``ConvTemporalGraphical``)."""
+    BLOCK = None                 # set below (the class is defined after Model)
+    N_IMPORTANCE = 1             # 3: edge_importance, edge_importance2, edge_importance3
 
     def __init__(self, in_channels, num_class, graph_args, edge_importance_weighting, **kwargs):
         super().__init__()
+        st_gcn = self.BLOCK
         self.graph = Graph(**graph_args)
         A = torch.tensor(self.graph.A, dtype=torch.float32, requires_grad=False)
         self.register_buffer('A', A)
@@ -40,24 +47,33 @@ class Model(FusedModelMixin, nn.Module):
             st_gcn(256, 256, kernel_size, 1, **kwargs),
             st_gcn(256, 256, kernel_size, 1, **kwargs),
         ))
-        if edge_importance_weighting:
-            self.edge_importance = nn.ParameterList([
-                nn.Parameter(torch.ones(self.A.size())) for _ in self.st_gcn_networks])
-        else:
-            self.edge_importance = [1] * len(self.st_gcn_networks)
+        names = ['edge_importance', 'edge_importance2', 'edge_importance3'][:self.N_IMPORTANCE]
+        for name in names:
+            if edge_importance_weighting:
+                setattr(self, name, nn.ParameterList([
+                    nn.Parameter(torch.ones(self.A.size())) for _ in self.st_gcn_networks]))
+            else:
+                setattr(self, name, [1] * len(self.st_gcn_networks))
         self.fcn = nn.Conv2d(256, num_class, kernel_size=1)
+
+    def _block_adjs(self, i):
+        """Adjacency stacks of block i (FusedModelMixin._trunk): the block's graph conv decides."""
+        imps = [getattr(self, n)[i] for n in
+                ('edge_importance', 'edge_importance2', 'edge_importance3')[:self.N_IMPORTANCE]]
+        return self.st_gcn_networks[i].gcn.stacks(self.A, *imps)
 
 
 class st_gcn(FusedWideBlockMixin, nn.Module):
     r"""st_gcn(in_channels, out_channels, kernel_size=(9, K), stride=1, dropout=0, residual=True);
     forward(x, A) -> (relu(x), A) on (N, C, T, V) tensors."""
+    GCN = ConvTemporalGraphical
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, dropout=0, residual=True):
         super().__init__()
         assert len(kernel_size) == 2
         assert kernel_size[0] % 2 == 1
         padding = ((kernel_size[0] - 1) // 2, 0)
-        self.gcn = ConvTemporalGraphical(in_channels, out_channels, kernel_size[1])
+        self.gcn = self.GCN(in_channels, out_channels, kernel_size[1])
         self.tcn = nn.Sequential(
             nn.BatchNorm2d(out_channels),
             nn.ReLU(inplace=True),
@@ -77,8 +93,11 @@ class st_gcn(FusedWideBlockMixin, nn.Module):
         self.relu = nn.ReLU(inplace=True)
         self._init_fused(in_channels, out_channels, stride, dropout, residual)
 
-    def forward(self, x, A):
+    def forward(self, x, A, *importances):
         assert A.size(0) == self.gcn.kernel_size
         pattern = self.gcn._cache.get(A)
-        y = self.forward_cl(to_channels_last(x.float()), [A], None, pattern)
+        y = self.forward_cl(to_channels_last(x.float()), self.gcn.stacks(A, *importances), None, pattern)
         return to_channels_first(y), A
+
+
+Model.BLOCK = st_gcn

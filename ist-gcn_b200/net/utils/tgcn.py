@@ -51,9 +51,15 @@ class ConvTemporalGraphical(nn.Module):
                               bias=bias)
         self._cache = _PatternCache()
 
-    def forward(self, x, A):
+    def stacks(self, A, importance=None):
+        """The adjacency stacks this graph conv aggregates with (their einsums are summed; the
+        element-power variants in tgcn_multi3*.py / tgcn_only3.py / tgcn_learnA.py override it)."""
+        return [A if importance is None else A * importance]
+
+    def forward(self, x, A, *importances):
         assert A.size(0) == self.kernel_size
         pattern = self._cache.get(A)
-        vals, wc, biasterm, w2 = graph_conv_operands(self.conv.weight, self.conv.bias, [A], pattern)
+        vals, wc, biasterm, w2 = graph_conv_operands(self.conv.weight, self.conv.bias,
+                                                     self.stacks(A, *importances), pattern)
         y = ops.GraphConv.apply(to_channels_last(x.float()), vals, wc, biasterm, w2, pattern)
         return to_channels_first(y), A

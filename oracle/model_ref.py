@@ -49,7 +49,32 @@ ARCHS = {
     'st_gcn_mstcn_1x1_deep': ('single', 'incept_1x1', THIRTEEN, False),   # net/st_gcn_mstcn_1x1_deep.py:49-63
     'st_gcn_deep_msgcn': ('inception', 'plain', THIRTEEN, False),         # net/st_gcn_deep_msgcn.py:60-77
     'st_gcn_msgcn_new': ('inception', 'plain', SEVEN, False),             # net/st_gcn_msgcn_new.py:60-73
+    # element-power adjacency variants: st_gcnold with another A_eff
+    'st_gcn_multi3': ('pow_multi3', 'plain', TEN, True),           # net/utils/tgcn_multi3.py:86-89
+    'st_gcn_multi3_fix': ('pow_multi3_fix', 'plain', TEN, True),   # net/utils/tgcn_multi3_fix.py:86-89
+    'st_gcn_only3': ('pow_only3', 'plain', TEN, True),             # net/utils/tgcn_only3.py:86
+    'st_gcn_learnA': ('pow_learnA', 'plain', TEN, True),           # net/utils/tgcn_learnA.py:75,86
+    'st_gcn_multi3_fix_3A': ('pow_3A', 'plain', TEN, True),        # net/utils/tgcn_multi3_fix_3A.py:76-89
 }
+
+
+def adjacency_stacks(gcn_kind, A, imps, pa=None):
+    """The adjacency stacks one block aggregates with (their einsums are summed).  ``imps`` =
+    (importance, importance2, importance3); powers are ELEMENT-wise (tgcn_multi3.py:87-88)."""
+    a = A * imps[0]
+    if gcn_kind == 'single':
+        return [a]
+    if gcn_kind == 'pow_multi3':
+        return [a, a ** 2, a ** 3]
+    if gcn_kind == 'pow_multi3_fix':       # the sum is divided by 3 afterwards (block_forward)
+        return [a, a ** 2, a ** 3]
+    if gcn_kind == 'pow_only3':
+        return [a ** 3]
+    if gcn_kind == 'pow_learnA':
+        return [a ** (1 + pa)]
+    if gcn_kind == 'pow_3A':
+        return [a, A ** 2 * imps[1], A ** 3 * imps[2]]
+    raise ValueError(gcn_kind)
 
 
 def block_table(arch, in_channels):
@@ -89,7 +114,9 @@ def make_state(arch, in_channels, num_class, A, A2=None, A3=None,
     blocks = block_table(arch, in_channels)
     for i, (cin, cout, stride, residual) in enumerate(blocks):
         p = 'st_gcn_networks.%d.' % i
-        if gcn_kind == 'single':
+        if gcn_kind == 'pow_learnA':       # the module's own parameter precedes its sub-module's
+            items += [(p + 'gcn.pa', torch.ones(1))]
+        if gcn_kind != 'inception':
             items += _conv_entries(p + 'gcn.conv.', K * cout, cin, 1, gen)
         else:
             items += _conv_entries(p + 'gcn.branch.conv.', K * cout, cin, 1, gen)
@@ -116,7 +143,7 @@ def make_state(arch, in_channels, num_class, A, A2=None, A3=None,
             items += _bn_entries(p + 'residual.1.', cout, gen)
     if edge_importance_weighting:
         names = ['edge_importance'] + (['edge_importance2', 'edge_importance3']
-                                       if gcn_kind == 'inception' else [])
+                                       if gcn_kind in ('inception', 'pow_3A') else [])
         for name in names:
             items += [('%s.%d' % (name, i), torch.ones(K, V, V)) for i in range(len(blocks))]
     if tcn_kind != 'plain':
@@ -133,7 +160,7 @@ def perturb_state(state, seed=1, scale=0.2):
     for k, v in state.items():
         if k in ('A', 'A2', 'A3') or k.endswith('num_batches_tracked'):
             out[k] = v.clone()
-        elif 'importance' in k:
+        elif 'importance' in k or k.endswith('gcn.pa'):
             out[k] = v + scale * torch.randn(v.shape, generator=gen)
         elif k.endswith('running_var'):
             out[k] = v * (1.0 + 0.5 * torch.rand(v.shape, generator=gen))
@@ -198,8 +225,10 @@ def block_forward(state, p, arch, x, adjs, m_imp, cfg, training, dropout=0.0, up
         res = F.conv2d(x, state[p + 'residual.0.weight'], state[p + 'residual.0.bias'],
                        stride=(stride, 1))
         res = _bn(state, p + 'residual.1.', res, training, update=update)
-    g = 'gcn.conv.' if gcn_kind == 'single' else 'gcn.branch.conv.'
+    g = 'gcn.conv.' if gcn_kind != 'inception' else 'gcn.branch.conv.'
     x = graph_conv(x, state[p + g + 'weight'], state[p + g + 'bias'], adjs)
+    if gcn_kind == 'pow_multi3_fix':
+        x = x / 3                                   # tgcn_multi3_fix.py:89
     if tcn_kind == 'plain':
         x = F.relu(_bn(state, p + 'tcn.0.', x, training, update=update))
         x = F.conv2d(x, state[p + 'tcn.2.weight'], state[p + 'tcn.2.bias'], stride=(stride, 1),
@@ -234,7 +263,12 @@ def _trunk(state, x, arch, training, dropout, update, masks):
     blocks = block_table(arch, C)
     one = torch.ones((), dtype=x.dtype)
     for i, cfg in enumerate(blocks):
-        adjs = [state['A'] * state.get('edge_importance.%d' % i, one)]
+        if gcn_kind.startswith('pow_'):
+            imps = tuple(state.get('edge_importance%s.%d' % (sfx, i), one) for sfx in ('', '2', '3'))
+            adjs = adjacency_stacks(gcn_kind, state['A'], imps,
+                                    state.get('st_gcn_networks.%d.gcn.pa' % i))
+        else:
+            adjs = [state['A'] * state.get('edge_importance.%d' % i, one)]
         if gcn_kind == 'inception':
             adjs.append(state['A2'] * state.get('edge_importance2.%d' % i, one))
             adjs.append(state['A3'] * state.get('edge_importance3.%d' % i, one))

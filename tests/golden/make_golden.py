@@ -48,6 +48,11 @@ MODEL_CASES = {
                               (2, 3, 16, 25, 2)),
     'st_gcn_deep_msgcn': (dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60, (2, 3, 16, 25, 2)),
     'st_gcn_msgcn_new': (dict(layout='openpose_sym', strategy='spatial_3_sym'), 60, (2, 3, 16, 18, 2)),
+    'st_gcn_multi3': (dict(layout='ntu-rgb+d', strategy='spatial'), 60, (2, 3, 16, 25, 2)),
+    'st_gcn_multi3_fix': (dict(layout='openpose', strategy='spatial'), 60, (2, 3, 16, 18, 2)),
+    'st_gcn_only3': (dict(layout='ntu-rgb+d', strategy='spatial'), 60, (2, 3, 16, 25, 2)),
+    'st_gcn_learnA': (dict(layout='ntu-rgb+d', strategy='spatial'), 60, (2, 3, 16, 25, 2)),
+    'st_gcn_multi3_fix_3A': (dict(layout='ntu-rgb+d_sym', strategy='spatial_sym'), 60, (2, 3, 16, 25, 2)),
 }
 
 

@@ -395,7 +395,9 @@ def _load_case(name):
 @pytest.mark.parametrize('math', ['3xtf32', 'tf32'])
 @pytest.mark.parametrize('name', ['ist_gcn', 'ist_gcn_kinetics', 'st_gcn_mstcn_1x1', 'st_gcn',
                                   'st_gcn_msgcn', 'st_gcn_mstcn', 'st_gcn_mstcn_1x1_deep',
-                                  'st_gcn_deep_msgcn', 'st_gcn_msgcn_new'])
+                                  'st_gcn_deep_msgcn', 'st_gcn_msgcn_new', 'st_gcn_multi3',
+                                  'st_gcn_multi3_fix', 'st_gcn_only3', 'st_gcn_learnA',
+                                  'st_gcn_multi3_fix_3A'])
 def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
     """Logits, loss and EVERY parameter gradient of a training step vs the fixture generated
     from the reference's own modules and vs the live oracle."""
