@@ -229,7 +229,8 @@ class FusedWideBlockMixin(object):
         if hasattr(self, 'tcn'):
             wtt, bt = merged_temporal_taps([self.tcn[2]], None)
         else:
-            wtt, bt = merged_temporal_taps([self.tcn_1, self.tcn_2, self.tcn_3], m_imp, 3.0)
+            wtt, bt = merged_temporal_taps([self.tcn_1, self.tcn_2, self.tcn_3], m_imp,
+                                           getattr(self, 'TCN_DIVISOR', 3.0))
         wr = btr = None
         if self._res_mode == 2:
             rconv = self.residual[0]

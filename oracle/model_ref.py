@@ -55,6 +55,8 @@ ARCHS = {
     'st_gcn_only3': ('pow_only3', 'plain', TEN, True),             # net/utils/tgcn_only3.py:86
     'st_gcn_learnA': ('pow_learnA', 'plain', TEN, True),           # net/utils/tgcn_learnA.py:75,86
     'st_gcn_multi3_fix_3A': ('pow_3A', 'plain', TEN, True),        # net/utils/tgcn_multi3_fix_3A.py:76-89
+    # ... with the full-width Inception TCN, branches summed WITHOUT the /3 (:211-216)
+    'st_gcn_multi3_fix_3A_mstcn': ('pow_3A', 'incept_full_sum', TEN, False),
 }
 
 
@@ -126,7 +128,7 @@ def make_state(arch, in_channels, num_class, A, A2=None, A3=None,
             items += _conv_entries(p + 'tcn.2.', cout, cout, 9, gen)
             items += _bn_entries(p + 'tcn.3.', cout, gen)
         else:
-            b = int(cout ** 0.5) if tcn_kind == 'incept_1x1' else cout
+            b = int(cout ** 0.5) if tcn_kind == 'incept_1x1' else cout      # incept_full[_sum]: C -> C
             items += _bn_entries(p + 'tcn_start.0.', cout, gen)
             if tcn_kind == 'incept_1x1':
                 items += _conv_entries(p + 'conv_1x1_start.', b, cout, 1, gen)
@@ -246,6 +248,8 @@ def block_forward(state, p, arch, x, adjs, m_imp, cfg, training, dropout=0.0, up
         if tcn_kind == 'incept_1x1':
             x = F.conv2d(branches, state[p + 'conv_1x1_end.weight'],
                          state[p + 'conv_1x1_end.bias'])
+        elif tcn_kind == 'incept_full_sum':
+            x = branches
         else:
             x = branches / 3
         x = _bn(state, p + 'tcn_end.0.', x, training, update=update)

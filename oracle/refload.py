@@ -65,7 +65,8 @@ def build_reference_model(arch, in_channels, num_class, graph_args, edge_importa
              'st_gcn_deep_msgcn': 'net.st_gcn_deep_msgcn', 'st_gcn_msgcn_new': 'net.st_gcn_msgcn_new',
              'st_gcn_multi3': 'net.st_gcn_multi3', 'st_gcn_multi3_fix': 'net.st_gcn_multi3_fix',
              'st_gcn_only3': 'net.st_gcn_only3', 'st_gcn_learnA': 'net.st_gcn_learnA',
-             'st_gcn_multi3_fix_3A': 'net.st_gcn_multi3_fix_3A'}
+             'st_gcn_multi3_fix_3A': 'net.st_gcn_multi3_fix_3A',
+             'st_gcn_multi3_fix_3A_mstcn': 'net.st_gcn_multi3_fix_3A_mstcn'}
     if arch in table:
         return load(table[arch]).Model(in_channels, num_class, graph_args,
                                        edge_importance_weighting, **kwargs)

@@ -53,6 +53,7 @@ MODEL_CASES = {
     'st_gcn_only3': (dict(layout='ntu-rgb+d', strategy='spatial'), 60, (2, 3, 16, 25, 2)),
     'st_gcn_learnA': (dict(layout='ntu-rgb+d', strategy='spatial'), 60, (2, 3, 16, 25, 2)),
     'st_gcn_multi3_fix_3A': (dict(layout='ntu-rgb+d_sym', strategy='spatial_sym'), 60, (2, 3, 16, 25, 2)),
+    'st_gcn_multi3_fix_3A_mstcn': (dict(layout='openpose', strategy='spatial'), 60, (2, 3, 16, 18, 2)),
 }
 
 

@@ -94,6 +94,8 @@ def test_state_dict_layouts_match_oracle():
               dict(layout='ntu-rgb+d', strategy='spatial'), 60),
              (importlib.import_module('net.st_gcn_multi3_fix_3A').Model, 'st_gcn_multi3_fix_3A',
               dict(layout='ntu-rgb+d_sym', strategy='spatial_sym'), 60),
+             (importlib.import_module('net.st_gcn_multi3_fix_3A_mstcn').Model, 'st_gcn_multi3_fix_3A_mstcn',
+              dict(layout='openpose', strategy='spatial'), 60),
              (net.ist_gcn.Model, 'ist_gcn', dict(layout='ntu-rgb+d_sym', strategy='spatial_3_sym'), 60),
              (net.ist_gcn.Model, 'ist_gcn', dict(layout='openpose_sym', strategy='spatial_3_sym'), 400),
              (net.st_gcn_mstcn_1x1.Model, 'st_gcn_mstcn_1x1',

@@ -397,7 +397,7 @@ def _load_case(name):
                                   'st_gcn_msgcn', 'st_gcn_mstcn', 'st_gcn_mstcn_1x1_deep',
                                   'st_gcn_deep_msgcn', 'st_gcn_msgcn_new', 'st_gcn_multi3',
                                   'st_gcn_multi3_fix', 'st_gcn_only3', 'st_gcn_learnA',
-                                  'st_gcn_multi3_fix_3A'])
+                                  'st_gcn_multi3_fix_3A', 'st_gcn_multi3_fix_3A_mstcn'])
 def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
     """Logits, loss and EVERY parameter gradient of a training step vs the fixture generated
     from the reference's own modules and vs the live oracle."""
