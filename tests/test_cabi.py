@@ -73,6 +73,7 @@ def test_state_dict_layouts_match_oracle():
     import net.st_gcnold
     from oracle import model_ref
     assert net.st_gcnold.Model is net.st_gcn.Model
+    assert importlib.import_module('net.st_gcn_tanh').Model is net.st_gcn.Model
     cases = [(net.st_gcn.Model, 'st_gcn', dict(layout='ntu-rgb+d', strategy='spatial'), 60),
              (net.st_gcn.Model, 'st_gcn', dict(layout='openpose', strategy='uniform'), 400),
              (net.st_gcn_msgcn.Model, 'st_gcn_msgcn',
