@@ -132,7 +132,12 @@ int istgcn_gcn_bwd_w(const float* g, const float* z, const float* bn_p, const fl
  * Whole output tiles leave through TMA tile stores; when add_rows == out the kernel accumulates
  * in place with TMA reduce-add.  map_side selects where the temporal stride of the
  * residual branch applies (0: none, 1: input rows are read from frame n*t_in + to*t_stride,
- * 2: output / add_rows rows are written there).  TF32 inputs, fp32 accumulation in TMEM.     */
+ * 2: output / add_rows rows are written there).  TF32 inputs, fp32 accumulation in TMEM.
+ * Dispatch: plain calls (bn_p == NULL, in_out == NULL, map_side == 0, Cin and Cout multiples of
+ * 32, Cout <= 256, add_rows NULL or == out) run the second-generation kernel csrc/gcn_tc2.cu --
+ * aggregation AND channel mix on the tensor core, adjacency and aggregated operand in tensor
+ * memory, input frames by TMA; everything else the first-generation kernel csrc/gcn_tc.cu.
+ * The environment variable ISTGCN_GCN_TC_V1 forces the first generation everywhere.          */
 int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const float* bn_m1,
                   const float* bn_c, const float* bn_mu, const float* w_rows, const float* vals,
                   const int* lptr, const int* lsrc, const int* lid, int nnz,
