@@ -170,7 +170,9 @@ int istgcn_gcn_small_bwd(const float* g1, const float* z, const float* bn_p, con
 /* adjacency gradient on the tcgen05 engine (both operands fed by TMA):
  *   dvals[id] += sum_{f,ci} x[(f,v)][ci] * (dz Wc_k^T)[(f,w)][ci]   over the non-zeros (k,v,w)
  * dz [frames*V][Cout] (gradient w.r.t. the graph-conv output), Wc [K*Cin][Cout]; lists grouped
- * by (k, destination w) with lsrc = source joint v, lid = canonical id.  Cout % 32 == 0.     */
+ * by (k, destination w) with lsrc = source joint v, lid = canonical id.  Cout % 32 == 0.
+ * Cin % 32 == 0 and Cout <= 128: csrc/gcn_tc_da2.cu (second MMA with the A operand from tensor
+ * memory, accumulators over all frame tiles in TMEM, one read-out); else csrc/gcn_tc_da.cu.  */
 int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const int* lptr,
                         const int* lsrc, const int* lid, int nnz, float* dvals, int frames, int V,
                         int K, int Cin, int Cout, istgcn_stream_t s);
@@ -178,7 +180,10 @@ int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const 
 /* weight gradient on the tcgen05 engine: dWc[K*Cin][Cout] += X'^T dz with both operands read
  * MN-major (contraction over the rows of the frame tile), accumulators resident in tensor memory
  * for the whole kernel; dbiasterm[V][Cout] += sum over frames of dz (may be NULL).  Outputs are
- * caller-zeroed; lists grouped by (k, destination w); Cout % 32 == 0.                        */
+ * caller-zeroed; lists grouped by (k, destination w); Cout % 32 == 0.
+ * Plain frame maps (t_out == 0), Cin % 32 == 0, Cout <= 128 and at most two CTA groups:
+ * csrc/gcn_tc_dw2.cu (aggregation on the tensor core with the adjacency in tensor memory, converter
+ * warps TMEM -> MN-major operand atoms); else csrc/gcn_tc_dw.cu (aggregation on CUDA cores).   */
 int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* vals, const int* lptr,
                      const int* lsrc, const int* lid, int nnz, float* dWc, float* dbiasterm,
                      int frames, int V, int K, int Cin, int Cout,
