@@ -181,7 +181,7 @@ int istgcn_gcn_tc_dvals(const float* dz, const float* x, const float* Wc, const 
  * MN-major (contraction over the rows of the frame tile), accumulators resident in tensor memory
  * for the whole kernel; dbiasterm[V][Cout] += sum over frames of dz (may be NULL).  Outputs are
  * caller-zeroed; lists grouped by (k, destination w); Cout % 32 == 0.
- * Plain frame maps (t_out == 0), Cin % 32 == 0, Cout <= 128 and at most two CTA groups:
+ * Plain frame maps (t_out == 0), Cin % 32 == 0, Cout <= 256 and at most eight CTA groups:
  * csrc/gcn_tc_dw2.cu (aggregation on the tensor core with the adjacency in tensor memory, converter
  * warps TMEM -> MN-major operand atoms); else csrc/gcn_tc_dw.cu (aggregation on CUDA cores).   */
 int istgcn_gcn_tc_dw(const float* dz, const float* x, const float* vals, const int* lptr,

@@ -14,7 +14,9 @@
 //
 // A frame tile = 4 frames in 32-row slots (pad rows: zero lanes of MMA 1 / zero-filled dz rows).
 // Accumulators stay in tensor memory for the whole kernel (nrb row blocks x Cout columns <= 256
-// next to the adjacency and D1) and are flushed once with fp32 atomics.
+// next to the adjacency and D1) and are flushed once with fp32 atomics; the row blocks that do not
+// fit are spread over up to eight CTA groups (blockIdx.y), which walk the same tile sequence in
+// step so that the dz tiles they all read stay in L2 (Cout = 256: one row block per group).
 //
 //   warp 0  TMA producer (x slices)          warp 2  TMA producer (dz tiles, one per frame tile)
 //   warp 1  MMA issuer                        warps 4-7  converters, then the final epilogue
@@ -273,7 +275,7 @@ gcn_tc_dw2_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constan
 // Shapes the second-generation weight-gradient kernel takes (plain frame maps only).
 bool gcn_tc_dw2_eligible(int V, int K, int Cin, int Cout) {
     return V >= 1 && V <= 32 && K >= 1 && K <= 4 && Cin % 32 == 0 && Cin >= 32 && Cout % 32 == 0 &&
-           Cout >= 32 && Cout <= 128 && (256 / Cout) * 2 >= Cin / 32;     // at most two CTA groups
+           Cout >= 32 && Cout <= 256 && (256 / Cout) * 8 >= Cin / 32;     // at most eight CTA groups
 }
 
 int launch_gcn_tc_dw2(const float* dz, const float* x, const float* vals, const int* lptr,
