@@ -85,19 +85,23 @@ tconv_dw_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t ita = 0, itb = 0;
-            for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
-                const int n = kt_i / p.tiles_per_clip;
-                const int to0 = (kt_i - n * p.tiles_per_clip) * p.FK;
-                const int bb = itb & 1;
-                mbar_wait(&b_empty[bb], ((itb >> 1) & 1) ^ 1);
+        // TMA producer (warp-convergent loop, elected issue: see gcn_tc2.cu)
+        uint32_t ita = 0, itb = 0;
+        for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
+            const int n = kt_i / p.tiles_per_clip;
+            const int to0 = (kt_i - n * p.tiles_per_clip) * p.FK;
+            const int bb = itb & 1;
+            mbar_wait(&b_empty[bb], ((itb >> 1) & 1) ^ 1);
+            if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[bb], atom_tx * natom);
                 for (int j = 0; j < natom; ++j)
                     tma_load_4d(Bs + (bb * 4 + j) * kSubBytes, &dmap, &b_full[bb], col0 + 32 * j, 0, to0, n);
-                for (int mb = 0; mb < nmb; ++mb, ++ita) {
-                    const int sa = ita % kNAst;
-                    mbar_wait(&a_empty[sa], ((ita / kNAst) & 1) ^ 1);
+            }
+            __syncwarp();
+            for (int mb = 0; mb < nmb; ++mb, ++ita) {
+                const int sa = ita % kNAst;
+                mbar_wait(&a_empty[sa], ((ita / kNAst) & 1) ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[sa], atom_tx * 4);
                     for (int j = 0; j < 4; ++j) {
                         const int R = (mb0 + mb) * 128 + 32 * j;         // first stacked row of the atom
@@ -108,21 +112,23 @@ tconv_dw_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                                     R < rows_total ? ci0 : 0, 0, t_first, n);
                     }
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, nb, true, true);
-            uint32_t ita = 0, itb = 0;
-            bool first = true;
-            for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
-                const int bb = itb & 1;
-                mbar_wait(&b_full[bb], (itb >> 1) & 1);
-                const uint32_t b_addr = smem_u32(Bs + bb * 4 * kSubBytes);
-                for (int mb = 0; mb < nmb; ++mb, ++ita) {
-                    const int sa = ita % kNAst;
-                    mbar_wait(&a_full[sa], (ita / kNAst) & 1);
-                    tc_fence_after();
+        // MMA issuer
+        const uint32_t idesc = make_idesc(128, nb, true, true);
+        uint32_t ita = 0, itb = 0;
+        bool first = true;
+        for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
+            const int bb = itb & 1;
+            mbar_wait(&b_full[bb], (itb >> 1) & 1);
+            const uint32_t b_addr = smem_u32(Bs + bb * 4 * kSubBytes);
+            for (int mb = 0; mb < nmb; ++mb, ++ita) {
+                const int sa = ita % kNAst;
+                mbar_wait(&a_full[sa], (ita / kNAst) & 1);
+                tc_fence_after();
+                if (elect_one()) {
                     const uint32_t a_addr = smem_u32(As + sa * 4 * kSubBytes);
                     const uint32_t d_tmem = tmem_base + mb * nb;
                     for (int ks = 0; ks < p.ksteps; ++ks)
@@ -130,12 +136,14 @@ tconv_dw_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                                     make_desc(b_addr + ks * 1024, kSubBytes, 512, 1), idesc,
                                     (first && ks == 0) ? 0u : 1u);
                     tc_commit(&a_empty[sa]);
+                    if (mb == nmb - 1) tc_commit(&b_empty[bb]);
                 }
-                tc_commit(&b_empty[bb]);
-                first = false;
+                __syncwarp();
             }
-            tc_commit(done);
+            first = false;
         }
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
     } else if (warp >= 4) {
         const int ew = warp - 4;
         const int m = ew * 32 + lane;
