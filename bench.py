@@ -127,15 +127,15 @@ def algorithmic_bytes(kernel, batch, shape):
         elif kernel == 'gcn_tc_bwd':     # input gradient: reads dz, writes gin (reduce-add on top
             if cin >= 32:                # of the residual gradient: read + write)
                 per_launch.append(4 * r_in * (cout + cin * (2 if res else 1)))
-        elif kernel == 'bn_back_apply':  # reads g1, z, writes dz
+        elif kernel in ('bn_back_apply', 'bn_back_colsum'):  # reads g1, z, writes dz (+ frame sums)
             if cin >= 32:
                 per_launch.append(4 * r_in * 3 * cout)
         elif kernel == 'gcn_tc_dvals':   # reads dz, x
             if cin >= 32:
                 per_launch.append(4 * r_in * (cout + cin))
-        elif kernel == 'gcn_tc_dw':      # reads dz, x (+ dz again for the bias-term column sums)
+        elif kernel == 'gcn_tc_dw':      # reads dz, x (the bias-term column sums ride on bn_back_colsum)
             if cin >= 32:
-                per_launch.append(4 * r_in * (2 * cout + cin))
+                per_launch.append(4 * r_in * (cout + cin))
         elif kernel == 'gcn_small_fwd':  # block 0: reads x (3 channels), writes z
             if cin < 32:
                 per_launch.append(4 * r_in * (cin + cout))

@@ -250,6 +250,12 @@ int istgcn_bn_back_apply(const float* go, const float* u, const float* p, const 
                          const float* c, const float* mean, float* du, long long rows, int C,
                          float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
                          istgcn_stream_t s);
+/* dz = p*((g - m1) - c*(z - mean)) per channel, written to dz [frames*V][C], and in the same pass
+ * colsum[V][C] += sum over frames of dz (caller-zeroed): the input of the tensor-core graph-conv
+ * gradient kernels and the gradient of the graph convolution's bias term (tgcn.py:79-86).    */
+int istgcn_bn_back_colsum(const float* g, const float* z, const float* p, const float* m1,
+                          const float* c, const float* mean, float* dz, float* colsum, int frames,
+                          int V, int C, istgcn_stream_t s);
 int istgcn_relu_bn_bwd(const float* da, const float* a, const float* z, const float* mean1,
                        const float* rstd1, float* g1, double* sg, double* sgx, long long rows, int C,
                        istgcn_stream_t s);

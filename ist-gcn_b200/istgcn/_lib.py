@@ -19,7 +19,7 @@ SYMBOLS = (
     'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
     'istgcn_gcn_small_fwd', 'istgcn_gcn_small_bwd',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
-    'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_relu_bn_bwd', 'istgcn_tconv_tc',
+    'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_bn_back_colsum', 'istgcn_relu_bn_bwd', 'istgcn_tconv_tc',
     'istgcn_tconv_dw_tc',
     'istgcn_block_tail_fwd', 'istgcn_block_tail_bwd', 'istgcn_dropout_mask',
     'istgcn_pool_fwd', 'istgcn_pool_bwd',
@@ -89,6 +89,8 @@ def call(name, *args):
         _checked_device = True
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     launch_count += KERNELS_PER_CALL.get(name, 1)
+    if name == 'gcn_tc_dw' and args[8] is None:        # no bias-term column sums: one kernel
+        launch_count -= 1
     if timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -285,6 +285,7 @@ class STBlock(Function):
             call('tconv_tc', dyr, Wr.contiguous(), None, gin, None, None, NM, T, Tout, V, Cout, Cin, 1, s, -1)
             add_in = gin
         small = _gcn_small_ok(Cin, Cout) and cfg.res_mode == 0
+        dbt_done = False
         if small:
             # first block: dz, dx, dvals, dWc and dbt in one CUDA-core kernel
             call('gcn_small_bwd', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.dst_ptr, pat.dst_src,
@@ -297,7 +298,9 @@ class STBlock(Function):
             if _gcn_tc2_ok(Cout, Cin):
                 # second-generation engine (csrc/gcn_tc2.cu): its input arrives by TMA, so dz
                 # (BatchNorm backward of g1) is materialised by the element-wise kernel first
-                call('bn_back_apply', g1, z, p1, m11, c1, mean1, dz, i64(R_in), Cout, 0.0, u64(0), None)
+                # (the same pass sums dz over frames: the bias-term gradient dbt)
+                call('bn_back_colsum', g1, z, p1, m11, c1, mean1, dz, dbt, NM * T, V, Cout)
+                dbt_done = True
                 call('gcn_tc', dz, None, None, None, None, None, Wc, vals, pat.t_ptr, pat.t_src,
                      pat.t_id, pat.nnz, None, None, add_in, gin, None, None, None, NM * T, V, K, Cout,
                      Cout, Cin, 0, 0, 1, 0, 0)
@@ -313,8 +316,8 @@ class STBlock(Function):
         if small:
             pass
         elif use_tc():
-            call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc, dbt,
-                 NM * T, V, K, Cin, Cout, 0, 0, 1, 0)
+            call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc,
+                 None if dbt_done else dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, 0)
         else:
             call('gcn_bwd_w', g1, z, p1, m11, c1, mean1, x, vals, pat.dst_ptr, pat.dst_src,
                  pat.dst_id, pat.nnz, dWc, dbt, NM * T, V, K, Cin, Cout, 0, 0, 1, 0, math)

@@ -14,7 +14,7 @@ ENTRY = (('tc::gcn_tc2_kernel', 'gcn_tc'), ('tc::gcn_tc_kernel', 'gcn_tc'), ('tc
          ('tc::frame_colsum', 'gcn_tc_dw'), ('tc::gcn_tc_da', 'gcn_tc_dvals'),
          ('istgcn::tcn_bwd', 'tcn_bwd'), ('istgcn::tcn_down', 'tcn_fwd'), ('istgcn::tcn_up', 'tcn_fwd'),
          ('istgcn::block_tail_fwd', 'block_tail_fwd'), ('istgcn::block_tail_bwd', 'block_tail_bwd'),
-         ('istgcn::bn_back_apply', 'bn_back_apply'), ('istgcn::gcn_small_fwd', 'gcn_small_fwd'),
+         ('istgcn::bn_back_apply', 'bn_back_apply'), ('istgcn::bn_back_colsum', 'bn_back_colsum'), ('istgcn::gcn_small_fwd', 'gcn_small_fwd'),
          ('istgcn::gcn_small_bwd', 'gcn_small_bwd'))
 
 with open(sys.argv[1], newline='') as f:
