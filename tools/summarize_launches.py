@@ -57,8 +57,8 @@ if len(sys.argv) > 2:
     out = {}
     for key, (n, b, t) in ent.items():
         calls = n / per_call.get(key, 1)
-        if key == 'gcn_tc_dw':                    # frame_colsum rides along with every call
-            calls = n / 2
+        if key == 'gcn_tc_dw':                    # a frame_colsum launch may ride along: count the dw kernels
+            calls = sum(v[0] for k2, v in rows.items() if k2.startswith('tc::gcn_tc_dw'))
         out[key] = {'dram_bytes_per_launch': b / calls, 'launches': int(calls), 'ms_per_launch': t / calls,
                     'workload': 'ntu', 'clips_per_gpu': 64,
                     'source': 'profiles/r1_launches_dram.md (ncu dram__bytes_read.sum + dram__bytes_write.sum)'}
