@@ -63,8 +63,12 @@ __global__ void bn_back_colsum_kernel(const float* __restrict__ g, const float* 
                                       const float* __restrict__ cc, const float* __restrict__ mean,
                                       float* __restrict__ dz, float* __restrict__ colsum, int frames,
                                       int n, int C, int frames_per_cta) {
-    const int f0 = blockIdx.y * frames_per_cta, f1 = min(frames, f0 + frames_per_cta);
-    for (int j4 = blockIdx.x * blockDim.x + threadIdx.x; j4 < n / 4; j4 += gridDim.x * blockDim.x) {
+    // flat (slab, column) index: no idle lanes when V*C/4 is not a multiple of the block size
+    const int n4 = n / 4;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int slab = (int)(gid / n4);
+    const int f0 = slab * frames_per_cta, f1 = min(frames, f0 + frames_per_cta);
+    for (int j4 = (int)(gid - (long long)slab * n4); f0 < f1 && j4 < n4; j4 += n4) {
         const int c = (j4 * 4) % C;
         const float4 pv = ld4(p + c), mv = ld4(m1 + c), cv = ld4(cc + c), nv = ld4(mean + c);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -208,7 +212,8 @@ ISTGCN_API int istgcn_bn_back_colsum(const float* g, const float* z, const float
     if (slabs < 1) slabs = 1;
     if (slabs > frames) slabs = frames;
     const int fpc = (frames + slabs - 1) / slabs;
-    dim3 grid((n / 4 + 255) / 256, (frames + fpc - 1) / fpc);
+    const long long items = (long long)(n / 4) * ((frames + fpc - 1) / fpc);
+    const int grid = (int)((items + 255) / 256);
     bn_back_colsum_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(g, z, p, m1, c, mean, dz, colsum, frames, n,
                                                              C, fpc);
     return finish_launch("bn_back_colsum");
