@@ -290,6 +290,17 @@ int istgcn_pool_fwd(const float* x, float* pooled, int N, int M, int TV, int C,
 int istgcn_pool_bwd(const float* gpooled, float* gx, int N, int M, int TV, int C,
                     istgcn_stream_t s);
 
+/* ---- optimiser step (processor/recognition.py:152-159: optim.SGD(momentum=0.9, nesterov,
+ * weight_decay); :287-289 optimizer.step()) over flat fp32 buffers of n elements:
+ *   g' = g*grad_scale + weight_decay*p;  buf = momentum*buf + g';
+ *   p -= lr * (nesterov ? g' + momentum*buf : buf)
+ * lr is read from DEVICE memory (the step schedule of recognition.py:168-176 changes it without
+ * re-capturing a CUDA graph); grad_scale = 1/world folds the data-parallel average in.
+ * buf zero-initialised by the caller before the first step.  16-byte aligned buffers.        */
+int istgcn_sgd_step(float* p, const float* g, float* buf, long long n, const float* lr,
+                    float momentum, float weight_decay, int nesterov, float grad_scale,
+                    istgcn_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,8 @@ restated for one process per GPU: same initialisation (``weights_init`` :31-44),
 schedule (``adjust_lr`` :168-176); the DataParallel wrap is replaced by ``dp.GradBuckets``.
 Logging / TensorBoard / confusion matrices of the reference are out of scope.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -27,8 +29,11 @@ def weights_init(m):
 def adjust_lr(optimizer, base_lr, step, epoch):
     """lr = base_lr * 0.1 ** #{s in step : epoch >= s}  (recognition.py:168-176)."""
     lr = base_lr * (0.1 ** sum(1 for s in (step or []) if epoch >= s))
-    for group in optimizer.param_groups:
-        group['lr'] = lr
+    if hasattr(optimizer, 'set_lr'):          # dp.FlatSGD: the rate lives in device memory
+        optimizer.set_lr(lr)
+    else:
+        for group in optimizer.param_groups:
+            group['lr'] = lr
     return lr
 
 
@@ -36,74 +41,85 @@ class Trainer(object):
     """model + SGD(nesterov) + gradient buckets; ``step(x, label)`` is one iteration of
     recognition.py:249-298 (forward, loss, zero_grad, backward, optimizer step).
 
-    ``use_graph=True`` captures the iteration in a CUDA graph after two eager warm-up steps and
-    replays it afterwards: the block launches ~800 small kernels per step (the fused kernels plus
-    the tiny parameter-regrouping ops), which is launch-bound from Python at B200 speeds.  With
-    more than one rank the graph holds forward + backward only; the bucket all-reduces and the
-    optimiser step run right after the replay (the collective is 4.4 MB, i.e. latency-bound, so
-    little is lost against the eager mode where it overlaps the backward pass)."""
+    ``use_graph=True`` captures the WHOLE iteration -- forward, backward, the bucket all-reduces
+    (launched from the gradient hooks on NCCL's stream, so they overlap the rest of the backward
+    pass inside the graph too) and the optimiser kernel -- in one CUDA graph per input shape after
+    two eager warm-up steps at that shape, and replays it afterwards: a step is ~200 kernels plus
+    the parameter regrouping, which is launch-bound from Python at B200 speeds.  The learning
+    rate is read from device memory by the optimiser kernel, so the step schedule needs no
+    re-capture.  ``ISTGCN_GRAPH_COLLECTIVES=0`` keeps the collectives and the optimiser outside
+    the graph (replay forward + backward, then reduce and step eagerly)."""
 
     def __init__(self, model, base_lr=0.1, weight_decay=1e-4, nesterov=True, momentum=0.9,
                  bucket_bytes=2 << 20, group=None, use_graph=False):
         self.model = model
-        self.buckets = dp.GradBuckets(list(model.named_parameters()), bucket_bytes, group)
-        params = [p for b in self.buckets.buckets for _, p in b['params']]
-        self.optimizer = torch.optim.SGD(params, lr=base_lr, momentum=momentum, nesterov=nesterov,
-                                         weight_decay=weight_decay, foreach=True)
+        self.buckets = dp.GradBuckets(list(model.named_parameters()), bucket_bytes, group,
+                                      flatten_params=True)
+        self.optimizer = dp.FlatSGD(self.buckets, base_lr, momentum=momentum, nesterov=nesterov,
+                                    weight_decay=weight_decay)
         self.base_lr = base_lr
         self.use_graph = use_graph
-        self._graph = None
-        self._static = None
-        self._eager_steps = 0
+        self._graphs = {}           # (x.shape, label.shape) -> (graph, static x, static label, loss)
+        self._eager_seen = {}
+        self.graph_collectives = os.environ.get('ISTGCN_GRAPH_COLLECTIVES', '1') != '0'
 
-    # one iteration; ``with_optimizer`` False leaves the averaged gradients in the buckets
-    def _iteration(self, x, label, with_optimizer):
-        from . import ops
+    # one iteration; ``with_optimizer`` False leaves the summed gradients in the buckets
+    def _iteration(self, x, label, with_optimizer=True):
+        from . import modules, ops
         self.model.train()
+        if x.is_cuda:
+            streams = [torch.cuda.current_stream(x.device)]
+            if modules._side_stream_enabled():
+                streams.append(modules._side_stream(x.device))
+            self.buckets.streams = streams
         ops.step_counter(x.device).add_(1)
         self.buckets.zero()
         output = self.model(x)
         loss = F.cross_entropy(output, label)
         loss.backward()
         if with_optimizer:
-            self.buckets.finish()
+            self.buckets.finish(average=False)      # FlatSGD applies the 1/world factor
             self.optimizer.step()
         return loss
 
     def invalidate_graph(self):
-        """Call after changing the learning rate (it is baked into the captured kernels)."""
-        self._graph = None
+        """Drop every captured graph (e.g. after the model's structure or mode flags changed)."""
+        self._graphs = {}
 
     def set_lr(self, lr):
-        for group in self.optimizer.param_groups:
-            if group['lr'] != lr:
+        if hasattr(self.optimizer, 'set_lr'):
+            self.optimizer.set_lr(lr)
+        else:
+            for group in self.optimizer.param_groups:
                 group['lr'] = lr
-                self.invalidate_graph()
 
     def step(self, x, label):
         if not self.use_graph:
-            return self._iteration(x, label, True)
-        single = self.buckets.world == 1
-        if self._eager_steps < 2:               # momentum buffers, caches, cuda handles
-            self._eager_steps += 1
-            return self._iteration(x, label, True)
-        if self._graph is None:
+            return self._iteration(x, label)
+        key = (tuple(x.shape), tuple(label.shape))
+        ent = self._graphs.get(key)
+        if ent is None:
+            seen = self._eager_seen.get(key, 0)
+            if seen < 2:                # momentum buffers, caches, cuda handles, lazy attributes
+                self._eager_seen[key] = seen + 1
+                return self._iteration(x, label)
+            whole = self.buckets.world == 1 or self.graph_collectives
             sx, sy = torch.empty_like(x), torch.empty_like(label)
             sx.copy_(x)
             sy.copy_(label)
-            self.buckets.defer = not single
+            self.buckets.defer = not whole
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                sloss = self._iteration(sx, sy, single)
-            self._graph, self._static = graph, (sx, sy, sloss)
+                sloss = self._iteration(sx, sy, whole)
+            ent = self._graphs[key] = (graph, sx, sy, sloss, whole)
             # the capture itself did not execute anything: fall through to the first replay
-        sx, sy, sloss = self._static
+        graph, sx, sy, sloss, whole = ent
         sx.copy_(x, non_blocking=True)
         sy.copy_(label, non_blocking=True)
-        self._graph.replay()
-        if not single:
-            self.buckets.finish()
+        graph.replay()
+        if not whole:
+            self.buckets.finish(average=False)
             self.optimizer.step()
         return sloss
 
@@ -146,8 +162,6 @@ class Trainer(object):
         for data, label in loader:
             data = data.float().to(device, non_blocking=True)
             label = label.long().to(device, non_blocking=True)
-            if self._static is not None and self._static[0].shape != data.shape:
-                self.invalidate_graph()             # ragged last batch: re-capture for its shape
             loss = self.step(data, label).detach()
             total = loss.clone() if total is None else total + loss
             count += 1

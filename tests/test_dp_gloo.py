@@ -62,6 +62,45 @@ def _worker(rank, world, port, defer, out):
     dist.destroy_process_group()
 
 
+def _replay_worker(rank, world, port, out):
+    """What a CUDA-graph replay looks like to the host: the flat gradient buffers are refilled by
+    the device, neither the hooks nor zero() run, only finish() is called -- step after step."""
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from istgcn import dp
+    torch.manual_seed(0)
+    model = Tiny()
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    buckets = dp.GradBuckets(list(model.named_parameters()), bucket_bytes=256, flatten_params=True)
+    for n, p in model.named_parameters():                # flattening keeps values, 16-byte alignment
+        assert torch.equal(p.detach(), before[n])
+        if not dp.is_unused(n):
+            assert p.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0
+    x, y = _data(rank)
+    buckets.zero()
+    nn.functional.cross_entropy(model(x), y).backward()
+    buckets.finish()
+    results = []
+    for step in range(3):                                # three "replays"
+        for b in buckets.buckets:
+            b['flat'].fill_(float(rank + 1 + step))      # rank-local gradient written by the device
+        buckets.finish()
+        results.append([b['flat'].clone() for b in buckets.buckets])
+    if rank == 0:
+        torch.save(results, out)
+    dist.destroy_process_group()
+
+
+def test_finish_without_zero_still_reduces(tmp_path):
+    """after the first finish() every later finish() skipped the all-reduce."""
+    out = str(tmp_path / 'replay.pt')
+    mp.spawn(_replay_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for step, flats in enumerate(torch.load(out)):
+        for flat in flats:
+            assert torch.all(flat == 1.5 + step), (step, flat[:4])
+
+
 def _free_port():
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
