@@ -314,6 +314,13 @@ def run_istgcn(args):
         barrier()
         fwd = world * B * args.steps / (e0.elapsed_time(e1) / 1e3)
 
+    replicas_ok = dp.replicas_equal(model) if world > 1 else None
+    extras = {}
+    if world == 1 and not args.no_extras:
+        del tr, model
+        torch.cuda.empty_cache()
+        extras = run_extras(args, dev)
+
     line = {
         'metric': '%s_train_clips_per_s' % args.arch, 'value': value, 'unit': 'clips/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
@@ -331,6 +338,10 @@ def run_istgcn(args):
                 'h2d_bytes_per_step': xh.numel() * 4 + yh.numel() * 8, 'd2h_bytes_per_step': 4},
         'roofline': roof, 'kernel_shares': shares, 'fwd_clips_per_s': fwd, 'loss': final_loss,
     }
+    if replicas_ok is not None:
+        line['replicas_equal_after_run'] = replicas_ok
+        assert replicas_ok, 'data-parallel replicas diverged during the timed loop'
+    line.update(extras)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_reference(args, steps=1, warmup=1)
@@ -338,6 +349,212 @@ def run_istgcn(args):
     if world > 1:
         dist.destroy_process_group()
 
+
+
+# ------------------------------------------------------------------------------------------
+def _timed_training(workload, arch, math, batch, dev, steps, warmup=3, use_graph=True):
+    """clips/s of ``steps`` training iterations (CUDA events) of a freshly built model."""
+    import istgcn
+    from istgcn import trainer
+    w = WORKLOADS[workload]
+    old = istgcn.set_math(math)
+    try:
+        torch.manual_seed(0)
+        model = build_model(workload, dev, arch=arch)
+        tr = trainer.Trainer(model, base_lr=0.01, use_graph=use_graph)
+        x = torch.randn(batch, *w['shape'], device=dev)
+        y = torch.randint(0, w['num_class'], (batch,), device=dev)
+        for _ in range(max(3, warmup)):
+            tr.step(x, y)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            loss = tr.step(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {'clips_per_s': batch / (ms / 1e3), 'ms_per_step': ms, 'batch': batch, 'loss': loss.item()}
+    finally:
+        istgcn.set_math(old)
+    del tr, model, x, y
+    torch.cuda.empty_cache()
+    return out
+
+
+def gpu_eager_reference(args, dev, steps=3):
+    """The real competitor: the reference's own algorithm as stock
+    PyTorch eager ops (conv2d / einsum / batch_norm -> cuDNN / cuBLAS) on the SAME GPU, same
+    batch, fwd + bwd + SGD(nesterov), with TF32 enabled (PyTorch's default for convolutions plus
+    matmul TF32) and with full fp32.  Uses the fixture-pinned oracle port of the reference's
+    modules; a reported baseline, never part of the product path."""
+    from net.utils.graph import Graph
+    from oracle import model_ref
+    w = WORKLOADS[args.workload]
+    g = Graph(**graph_args_for(args.workload, args.arch))
+    out = {'kind': 'oracle port of the reference modules, PyTorch %s eager on cuda' % torch.__version__,
+           'batch': args.batch}
+    for label, flags in (('tf32', (True, True)), ('fp32', (False, False))):
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flags
+        try:
+            torch.manual_seed(0)
+            state = model_ref.make_state(args.arch, w['shape'][0], w['num_class'], g.A,
+                                         getattr(g, 'A2', None), getattr(g, 'A3', None), seed=0)
+            state = {k: v.to(dev) for k, v in state.items()}
+            names = [k for k, v in state.items() if v.is_floating_point() and 'running' not in k
+                     and k not in ('A', 'A2', 'A3') and '.gcn.branch.bn.' not in k and '.linear.' not in k]
+            params = [state[k].requires_grad_(True) for k in names]
+            opt = torch.optim.SGD(params, lr=0.01, momentum=0.9, nesterov=True, weight_decay=1e-4,
+                                  foreach=True)
+            x = torch.randn(args.batch, *w['shape'], device=dev)
+            y = torch.randint(0, w['num_class'], (args.batch,), device=dev)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                loss = F.cross_entropy(model_ref.forward(state, x, args.arch, training=True, dropout=0.5), y)
+                loss.backward()
+                opt.step()
+                return loss
+
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[label] = {'clips_per_s': args.batch / (ms / 1e3), 'ms_per_step': ms,
+                          'peak_mem_gb': torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+        del state, params, opt, x, y
+        torch.cuda.empty_cache()
+    return out
+
+
+def build_twostream(workload, dev, arch):
+    """net.st_gcn_twostream.Model (reference net/st_gcn_twostream.py:11-26: joint stream + motion
+    stream, logits summed) -- or, with another --arch, the same wrapper around that network."""
+    import importlib
+    import net.st_gcn_twostream as ts
+    from istgcn import trainer
+    w = WORKLOADS[workload]
+    args_ = (w['shape'][0], w['num_class'], graph_args_for(workload, arch), True)
+    model = ts.Model(*args_)
+    if arch != 'st_gcn':
+        cls = importlib.import_module('net.' + arch).Model
+        model.origin_stream, model.motion_stream = cls(*args_), cls(*args_)
+    model.apply(trainer.weights_init)
+    return model.to(dev).eval()
+
+
+def twostream_sweep(args, dev, batches, world=1, rank=0, chunk=512, reps=5):
+    """BASELINE.json configs[4]: two-stream inference, batch sweep.  A batch is sharded over the
+    ranks (batch < world: fewer ranks active); each rank runs its share in chunks of at most
+    ``chunk`` clips through one CUDA graph per chunk shape.  Per point: whole-job clips/s and
+    the latency of the batch (device time, max over ranks)."""
+    w = WORKLOADS[args.workload]
+    model = build_twostream(args.workload, dev, args.ts_arch)
+    graphs = {}
+
+    @torch.no_grad()
+    def run_chunk(xc):
+        n = xc.shape[0]
+        if n not in graphs:
+            sx = torch.empty_like(xc)
+            sx.copy_(xc)
+            for _ in range(2):
+                model(sx)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = model(sx)
+            graphs[n] = (g, sx, out)
+        g, sx, out = graphs[n]
+        sx.copy_(xc, non_blocking=True)
+        g.replay()
+        return out
+
+    points = []
+    for b in batches:
+        share = b // world + (1 if rank < b % world else 0)
+        x = torch.randn(max(share, 1), *w['shape'], device=dev) if share else None
+
+        def run_batch():
+            outs = []
+            for i in range(0, share, chunk):
+                outs.append(run_chunk(x[i:i + chunk]).clone())
+            return outs
+
+        if share:
+            run_batch()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            if share:
+                run_batch()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        points.append({'batch': b, 'latency_ms': ms, 'clips_per_s': b / (ms / 1e3),
+                       'active_ranks': min(b, world)})
+        del x
+    del model, graphs
+    torch.cuda.empty_cache()
+    return points
+
+
+def run_extras(args, dev):
+    """Driver-visible datapoints beside the headline (N = 1 only): the <= 1e-4 parity mode's
+    throughput, BASELINE.json configs[2] (Kinetics-skeleton, batch 256), the stock-PyTorch-eager
+    competitor on this GPU, and three points of the configs[4] two-stream inference sweep."""
+    import copy
+    out = {}
+    steps = max(2, min(args.steps, 5))
+    if args.math == 'tf32':
+        out['value_3xtf32'] = _timed_training(args.workload, args.arch, '3xtf32', args.batch, dev, steps)
+    if args.workload == 'ntu' and args.arch == 'ist_gcn':
+        out['kinetics_b256'] = _timed_training('kinetics', args.arch, args.math, 256, dev, steps)
+    out['gpu_eager'] = gpu_eager_reference(args, dev)
+    ts_args = copy.copy(args)
+    out['twostream_inference'] = {'stream_arch': args.ts_arch,
+                                  'points': twostream_sweep(ts_args, dev, [1, 64, 1024])}
+    return out
+
+
+def run_sweep(args):
+    """``--sweep``: the full configs[4] batch sweep 1..4096 (one JSON line)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    import istgcn
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    istgcn.set_math(args.math)
+    batches = [1 << i for i in range(13)]
+    points = twostream_sweep(args, dev, batches, world, rank)
+    if rank == 0:
+        w = WORKLOADS[args.workload]
+        print(json.dumps({'metric': 'twostream_inference_clips_per_s', 'unit': 'clips/s', 'n_gpus': world,
+                          'dtype': args.math, 'data': 'synthetic', 'higher_is_better': True,
+                          'config': {'workload': 'two-stream (joint + motion) inference, %s, eval' % w['name'],
+                                     'stream_arch': args.ts_arch, 'cuda_graph': True,
+                                     'sharding': 'batch over ranks, chunks of <= 512 clips per graph'},
+                          'points': points}))
+    if world > 1:
+        dist.destroy_process_group()
 
 # ------------------------------------------------------------------------------------------
 def cpu_reference(args, steps, warmup):
@@ -374,7 +591,21 @@ def cpu_reference(args, steps, warmup):
         if it >= warmup:
             times.append(dt)
     best = min(times)
-    return {'value': bs / best, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+    # BASELINE.json configs[0]: baseline ST-GCN (net.st_gcn) forward, (8, 3, 300, 25, 2), eval, CPU
+    cfg1 = None
+    if args.workload == 'ntu':
+        g1 = Graph(layout='ntu-rgb+d', strategy='spatial')
+        st1 = model_ref.make_state('st_gcn', 3, 60, g1.A, None, None, seed=0)
+        x1 = torch.randn(8, 3, 300, 25, 2)
+        t1 = []
+        with torch.no_grad():
+            for it in range(2):
+                t0 = time.perf_counter()
+                model_ref.forward(st1, x1, 'st_gcn', training=False)
+                t1.append(time.perf_counter() - t0)
+        cfg1 = {'metric': 'st_gcn_cpu_fwd_clips_per_s', 'value': 8 / min(t1), 'batch': 8,
+                'threads': torch.get_num_threads()}
+    return {'value': bs / best, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'cfg1_st_gcn_cpu_forward': cfg1,
             'sample': '%d clip(s) of the same shape per step, %d timed step(s), best' % (bs, steps),
             'torch_threads': torch.get_num_threads(), 's_per_step': best}
 
@@ -412,9 +643,17 @@ def main():
     ap.add_argument('--cpu-batch', type=int, default=4, help='clips per CPU-baseline step')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true', help='eager launches instead of a CUDA graph')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip value_3xtf32 / kinetics_b256 / gpu_eager / twostream_inference')
+    ap.add_argument('--sweep', action='store_true',
+                    help='two-stream inference batch sweep 1..4096 (BASELINE.json configs[4])')
+    ap.add_argument('--ts-arch', default='st_gcn', choices=ARCHS,
+                    help='network of each stream of the two-stream model (reference: net.st_gcn)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.sweep:
+        run_sweep(args)
     else:
         run_istgcn(args)
 

@@ -3,7 +3,8 @@ compared with the CPU oracle (oracle/model_ref.py, fp64 where stated) or with th
 fixtures generated from the reference.
 
 Tolerances (BASELINE.json north_star): <= 1e-4 relative in the fp32-grade mode ('3xtf32'),
-<= 2e-2 in the fast tensor-core mode ('tf32'); "relative" = max |a - b| / max |b| per tensor.
+<= 5e-3 per operator / 2e-3 on logits and loss in the fast tensor-core mode ('tf32', budget
+2e-2); "relative" = max |a - b| / max |b| per tensor.
 These hold as stated for every operator output, for the logits and for the loss.
 
 Gradients of the WHOLE network are ill-conditioned: plain fp32 PyTorch (the reference's own
@@ -18,9 +19,11 @@ not a property even of the reference against itself, so gradient parity is CALIB
             itself - tools/diag_chain.py - so a tensor on which fp32 PyTorch happens to be
             lucky cannot be matched tensor-by-tensor, but no tensor may be worse than fp32
             PyTorch's own worst.)
-  'tf32'    per-tensor relative L2 error vs the fp64 oracle <= 0.35 and cosine similarity of
-            the full gradient vector >= 0.98 (single-pass TF32 is 2^13 times coarser than fp32
-            and meets the same amplification; the logits stay within 4e-4)
+  'tf32'    calibrated the same way against STOCK PYTORCH WITH TF32 ENABLED (the oracle run on
+            the GPU with torch.backends.cudnn.allow_tf32 = cuda.matmul.allow_tf32 = True, i.e.
+            what the reference itself computes on this hardware by default for its convolutions):
+            per-tensor relative L2 error vs the fp64 oracle <= max(2e-2, 4 x that run's error for
+            the same tensor, 4 x its worst tensor); cosine of the full gradient >= 0.995.
 """
 import importlib.util
 import os
@@ -32,8 +35,25 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL = {'3xtf32': 1e-4, 'tf32': 2e-2}
-TOL_GRAD = {'3xtf32': 1e-4, 'tf32': 1e-1}     # one block, relative L2 for 'tf32'
+# 'tf32': 5x the observed error (1e-3 per operator, 4e-4 on the logits); the mode's budget in
+# BASELINE.json is 2e-2
+TOL = {'3xtf32': 1e-4, 'tf32': 5e-3}
+TOL_LOGITS = {'3xtf32': 1e-4, 'tf32': 2e-3}
+TOL_GRAD = {'3xtf32': 1e-4, 'tf32': 5e-2}     # one block, relative L2 for 'tf32'
+
+
+def calib_log(line):
+    """Observed errors next to their bounds, appended to $ISTGCN_CALIB_LOG when set."""
+    path = os.environ.get('ISTGCN_CALIB_LOG')
+    if path:
+        with open(path, 'a') as f:
+            f.write(line + '\n')
+
+
+def tf32_torch(flag):
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = flag
+    return old
 
 
 def rel(a, b, floor=1e-30):
@@ -130,6 +150,9 @@ def test_graph_conv_op(env, math, layout, strategy, cin, cout, nm, t):
     finally:
         env.set_math(old)
     tol = TOL[math]
+    calib_log('graph conv %d->%d %-6s out %.2e dx %.2e dW %.2e db %.2e' % (
+        cin, cout, math, rel(out, ref), rel(xg.grad, x64.grad), rel(conv.weight.grad, w64.grad),
+        rel(conv.bias.grad, b64.grad)))
     assert rel(out, ref) < tol
     assert rel(xg.grad, x64.grad) < tol
     assert rel(conv.weight.grad, w64.grad) < tol
@@ -370,6 +393,8 @@ def test_block_vs_oracle(env, math, cin, cout, stride, residual, t):
     for i in range(3):
         errs['A%d' % i] = metric(ag[i].grad * union.to(dev), a64[i].grad * union)
     errs['m_imp'] = metric(mg_.grad, m64.grad)
+    calib_log('block %d->%d s%d %-6s out %.2e worst grad %.2e (%s)' % (
+        cin, cout, stride, math, rel(out, ref), max(errs.values()), max(errs, key=errs.get)))
     assert not report(errs, tolg), report(errs, tolg)
     # running statistics of every BatchNorm that ran
     after = blk.state_dict()
@@ -424,7 +449,11 @@ def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
         loss.backward()
     finally:
         env.set_math(old)
-    tol, tolg = TOL[math], TOL_GRAD[math]
+    tol = TOL_LOGITS[math]
+    calib_log('model %-28s %-6s logits eval %.2e train %.2e loss %.2e' % (
+        name, math, rel(ev, torch.from_numpy(fix['logits_eval'])),
+        rel(logits, torch.from_numpy(fix['logits_train'])),
+        abs(loss.item() - float(fix['loss'])) / abs(float(fix['loss']))))
     assert rel(ev, torch.from_numpy(fix['logits_eval'])) < tol
     assert rel(logits, torch.from_numpy(fix['logits_train'])) < tol
     assert abs(loss.item() - float(fix['loss'])) < tol * abs(float(fix['loss']))
@@ -444,7 +473,14 @@ def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
     check_outliers(errs, loose)
     # calibrated bound vs the fp64 oracle (see the module docstring)
     g64 = _oracle_grads(state, x, label, arch, torch.float64)
-    g32 = _oracle_grads(state, x, label, arch, torch.float32)
+    if math == '3xtf32':
+        g32 = _oracle_grads(state, x, label, arch, torch.float32)
+    else:                       # the calibration run: stock PyTorch on this GPU with TF32 enabled
+        old_flags = tf32_torch((True, True))
+        try:
+            g32 = _oracle_grads(state, x, label, arch, torch.float32, device='cuda')
+        finally:
+            tf32_torch(old_flags)
     gmax = max(v.abs().max().item() for v in g64.values())
     errs, dot, n1, n2 = {}, 0.0, 0.0, 0.0
     worst_ref = max(rel_l2(g32[k], g64[k]) for k in names if g64[k].abs().max().item() >= 1e-6 * gmax)
@@ -461,10 +497,13 @@ def test_model_vs_golden_and_oracle(env, math, name, golden_dir):
             # here); they are bounded in absolute terms and through the global cosine below
             assert (mine - g64[k]).abs().max().item() < (2e-2 if math == '3xtf32' else 0.2) * gmax, k
             continue
-        errs[k] = e_mine / max(1e-4, 8 * e_ref, 8 * worst_ref) if math == '3xtf32' else e_mine / 0.35
-    assert not report(errs, 1.0), report(errs, 1.0)
+        errs[k] = e_mine / max(1e-4, 8 * e_ref, 8 * worst_ref) if math == '3xtf32' else \
+            e_mine / max(2e-2, 4 * e_ref, 4 * worst_ref)
     cos = dot / (n1 ** 0.5 * n2 ** 0.5)
-    assert cos > (0.9999 if math == '3xtf32' else 0.98), cos
+    calib_log('model %-28s %-6s grads: worst ratio %.2f, worst ref err %.2e, cosine %.6f' % (
+        name, math, max(errs.values()) if errs else 0.0, worst_ref, cos))
+    assert not report(errs, 1.0), report(errs, 1.0)
+    assert cos > (0.9999 if math == '3xtf32' else 0.995), cos
 
 
 @pytest.mark.parametrize('math', ['3xtf32', 'tf32'])
@@ -491,8 +530,8 @@ def test_twostream_vs_oracle(env, math):
         tr = model(x.to(dev))
     finally:
         env.set_math(old)
-    assert rel(ev, model_ref.twostream_forward(both, x, 'st_gcn', training=False)) < TOL[math]
-    assert rel(tr, model_ref.twostream_forward(both, x, 'st_gcn', training=True)) < TOL[math]
+    assert rel(ev, model_ref.twostream_forward(both, x, 'st_gcn', training=False)) < TOL_LOGITS[math]
+    assert rel(tr, model_ref.twostream_forward(both, x, 'st_gcn', training=True)) < TOL_LOGITS[math]
 
 
 @pytest.mark.parametrize('shape', [(3, 20, 25, 64, 9, 1, 1), (3, 20, 25, 64, 9, 2, 1),
@@ -585,7 +624,8 @@ def test_fused_temporal_conv_model_vs_oracle(env, arch):
     assert len(used.get('tconv_dw_tc', [])) >= len(model.st_gcn_networks)      # + strided residual convs
     ref = model_ref.forward({k: v.double() if v.is_floating_point() else v for k, v in state.items()},
                             x.double(), arch, training=True)
-    assert rel(logits, ref) < TOL['tf32']
+    calib_log('fused tconv model %s: logits %.2e' % (arch, rel(logits, ref)))
+    assert rel(logits, ref) < TOL_LOGITS['tf32']
     g64 = _oracle_grads(state, x, label, arch, torch.float64)
     dot = n1 = n2 = 0.0
     for k, prm in model.named_parameters():
@@ -593,17 +633,19 @@ def test_fused_temporal_conv_model_vs_oracle(env, arch):
             continue
         mine = prm.grad.detach().cpu().double()
         dot += (mine * g64[k]).sum().item(); n1 += mine.pow(2).sum().item(); n2 += g64[k].pow(2).sum().item()
-    assert dot / (n1 ** 0.5 * n2 ** 0.5) > 0.98
+    calib_log('fused tconv model %s: gradient cosine %.6f' % (arch, dot / (n1 ** 0.5 * n2 ** 0.5)))
+    assert dot / (n1 ** 0.5 * n2 ** 0.5) > 0.995
 
 
-def _oracle_grads(state, x, label, arch, dtype):
+def _oracle_grads(state, x, label, arch, dtype, device='cpu'):
     from oracle import model_ref
-    lv = {k: (v.detach().clone().to(dtype).requires_grad_(True)
+    lv = {k: (v.detach().clone().to(device, dtype).requires_grad_(True)
               if v.is_floating_point() and 'running' not in k and k not in ('A', 'A2', 'A3')
-              else (v.to(dtype) if v.is_floating_point() else v)) for k, v in state.items()}
-    out = model_ref.forward(lv, x.to(dtype), arch, training=True)
-    F.cross_entropy(out, label).backward()
-    return {k: v.grad.detach().double() for k, v in lv.items()
+              else (v.to(device, dtype) if v.is_floating_point() else v.to(device)))
+          for k, v in state.items()}
+    out = model_ref.forward(lv, x.to(device, dtype), arch, training=True)
+    F.cross_entropy(out, label.to(device)).backward()
+    return {k: v.grad.detach().double().cpu() for k, v in lv.items()
             if getattr(v, 'requires_grad', False) and v.grad is not None}
 
 
