@@ -217,6 +217,39 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
                    int stride, float drop_p, uint64_t drop_seed,
                    const unsigned long long* drop_step, int math, istgcn_stream_t s);
 
+/* The same chain in the 'tf32' math mode as six streaming kernels, one entry point per kernel
+ * (csrc/tcn2.cu): activation rows go from global memory straight into mma.sync fragments, every big
+ * tensor is touched once, only the bp-wide intermediates make round trips.  C in {64, 128, 256},
+ * bp in {8, 16}; rows_in = NM*T*V, rows_out = NM*Tout*V, Tout = (T-1)/stride + 1.  Same operands,
+ * layouts and accumulation conventions (caller-zeroed fp32 / double accumulators) as above.
+ *   tcn2_down      h1 = relu((z - mean1)*scale1 + beta1) Wd + bd          [rows_in][bp]
+ *   tcn2_conv      h2[to] = sum_tap Weff[tap] h1[to*stride + tap - 7] + beff   [rows_out][bp]
+ *   tcn2_up        u = h2 Wu + bu; stat_sum / stat_sumsq (double[C], may both be NULL)
+ *   tcn2_bwd_up    du = p2*((gy - m12) - c2*(u - mean2)); dh2 = du Wu^T (written);
+ *                  dWu += h2^T du, dbu += sum du, dbeff += sum dh2
+ *   tcn2_bwd_conv  dh1 = transposed temporal conv of dh2 (written); dWeff += ..., dbd += sum dh1
+ *   tcn2_bwd_down  g1 = (dh1 Wd^T) where relu(BN1(z)) > 0 (written); sg1 += sum g1,
+ *                  sg1x += sum g1*zhat (double[C]); dWd += a^T dh1                              */
+int istgcn_tcn2_down(const float* z, const float* mean1, const float* scale1, const float* beta1,
+                     const float* Wd, const float* bd, float* h1, long long rows_in, int C, int bp,
+                     istgcn_stream_t s);
+int istgcn_tcn2_conv(const float* h1, const float* Weff, const float* beff, float* h2, int NM, int T,
+                     int V, int bp, int stride, istgcn_stream_t s);
+int istgcn_tcn2_up(const float* h2, const float* Wu, const float* bu, float* u, double* stat_sum,
+                   double* stat_sumsq, long long rows_out, int C, int bp, istgcn_stream_t s);
+int istgcn_tcn2_bwd_up(const float* go, const float* u, const float* p2, const float* m12,
+                       const float* c2, const float* mean2, const float* h2, const float* Wu,
+                       float* dh2, float* dWu, float* dbu, float* dbeff, long long rows_out, int C,
+                       int bp, float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                       istgcn_stream_t s);
+int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const float* Weff, float* dh1,
+                         float* dWeff, float* dbd, int NM, int T, int V, int bp, int stride,
+                         istgcn_stream_t s);
+int istgcn_tcn2_bwd_down(const float* dh1, const float* z, const float* mean1, const float* scale1,
+                         const float* beta1, const float* rstd1, const float* Wd, float* g1,
+                         float* dWd, double* sg1, double* sg1x, long long rows_in, int C, int bp,
+                         istgcn_stream_t s);
+
 /* ---- full-width temporal convolution (net/st_gcnold.py:160-174: BN -> ReLU -> Conv2d(C, C,
  * (kt,1), (stride,1), (pad,0)) -> BN -> Dropout; net/st_gcn_mstcn.py: three such convs of 3/9/15
  * taps scaled by mstcn_importance = one 15-tap conv).  The convolution itself is the sum over

@@ -19,6 +19,8 @@ SYMBOLS = (
     'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
     'istgcn_gcn_small_fwd', 'istgcn_gcn_small_bwd',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
+    'istgcn_tcn2_down', 'istgcn_tcn2_conv', 'istgcn_tcn2_up', 'istgcn_tcn2_bwd_up', 'istgcn_tcn2_bwd_conv',
+    'istgcn_tcn2_bwd_down',
     'istgcn_bn_relu_apply', 'istgcn_bn_back_apply', 'istgcn_bn_back_colsum', 'istgcn_relu_bn_bwd', 'istgcn_tconv_tc',
     'istgcn_tconv_dw_tc',
     'istgcn_block_tail_fwd', 'istgcn_block_tail_bwd', 'istgcn_dropout_mask',

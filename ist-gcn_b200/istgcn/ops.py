@@ -139,6 +139,13 @@ def _gcn_small_ok(cin, cout):
     return cin <= 4 and cout == 64 and use_tc() and os.environ.get('ISTGCN_GCN_SMALL_OFF') is None
 
 
+def _tcn2_ok(C, bp):
+    """Shapes the streaming TCN kernels of the fast mode take (csrc/tcn2.cu); the fp32-grade
+    '3xtf32' mode keeps the error-compensated kernels of csrc/tcn.cu."""
+    return use_tc() and C in (64, 128, 256) and bp in (8, 16) and \
+        os.environ.get('ISTGCN_TCN_V1') is None
+
+
 def _tconv_fused_ok(C, V):
     """Shapes the tcgen05 temporal-convolution kernel takes (csrc/tconv_tc.cu)."""
     F = min(8, 128 // V)
@@ -178,8 +185,14 @@ class STBlock(Function):
         h1 = torch.empty(NM, T, V, bp, device=dev, dtype=torch.float32)
         h2 = torch.empty(NM, Tout, V, bp, device=dev, dtype=torch.float32)
         u = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-        call('tcn_fwd', z, mean1, scale1, bn1_b, Wd, bd, Weff, beff, Wu, bu, h1, h2, u, stats[2], stats[3],
-             NM, T, V, Cout, bp, s, math)
+        tcn2 = _tcn2_ok(Cout, bp)
+        if tcn2:
+            call('tcn2_down', z, mean1, scale1, bn1_b, Wd, bd, h1, i64(R_in), Cout, bp)
+            call('tcn2_conv', h1, Weff, beff, h2, NM, T, V, bp, s)
+            call('tcn2_up', h2, Wu, bu, u, stats[2], stats[3], i64(R_out), Cout, bp)
+        else:
+            call('tcn_fwd', z, mean1, scale1, bn1_b, Wd, bd, Weff, beff, Wu, bu, h1, h2, u, stats[2],
+                 stats[3], NM, T, V, Cout, bp, s, math)
         mean2, scale2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w, cfg.bn2,
                                                   Cout, dev)
         rres = scale_r = mean_r = rstd_r = None
@@ -216,6 +229,7 @@ class STBlock(Function):
 
         ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
         ctx.dims = (NM, T, Tout, V, Cin, Cout)
+        ctx.tcn2 = tcn2
         if training:
             ctx.save_for_backward(x, vals, Wc, z, h1, h2, u, out, rres, scale1, bn1_b, mean1, rstd1,
                                   mean2, rstd2, mean_r, rstd_r, Wd, Weff, Wu, Wr, bn1_w, bn2_w, bnr_w)
@@ -259,9 +273,16 @@ class STBlock(Function):
         g1 = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
         dh2 = torch.empty(R_out, bp, device=dev, dtype=torch.float32)
         dh1 = torch.empty(R_in, bp, device=dev, dtype=torch.float32)
-        call('tcn_bwd', go, u, p2, m12, c2, mean2, z, scale1, beta1, mean1, rstd1, h1, h2, Wd, Weff, Wu, dh2,
-             dh1, g1, sums[4], sums[5], dWd, dbd, dWeff, dbeff, dWu, dbu, NM, T, V, Cout, bp, s,
-             float(drop_p), u64(seed), step_counter(dev), math)
+        if ctx.tcn2:
+            call('tcn2_bwd_up', go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, i64(R_out), Cout,
+                 bp, float(drop_p), u64(seed), step_counter(dev))
+            call('tcn2_bwd_conv', dh2, h1, Weff, dh1, dWeff, dbd, NM, T, V, bp, s)
+            call('tcn2_bwd_down', dh1, z, mean1, scale1, beta1, rstd1, Wd, g1, dWd, sums[4], sums[5],
+                 i64(R_in), Cout, bp)
+        else:
+            call('tcn_bwd', go, u, p2, m12, c2, mean2, z, scale1, beta1, mean1, rstd1, h1, h2, Wd, Weff, Wu,
+                 dh2, dh1, g1, sums[4], sums[5], dWd, dbd, dWeff, dbeff, dWu, dbu, NM, T, V, Cout, bp, s,
+                 float(drop_p), u64(seed), step_counter(dev), math)
         p1, m11, c1, dg1, db1 = _coeffs(5, Cout, dev)
         call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
         # identity residual: the block-input gradient starts as `go` and the graph-conv input

@@ -284,6 +284,93 @@ def test_tensor_core_graph_conv_entry_points_vs_fp64(env, layout, strategy, cin,
     assert rel(dvals, dA.reshape(-1)[pat.flat_idx]) < 5e-3
 
 
+
+# ----------------------------------------------------------------------------- streaming TCN kernels
+@pytest.mark.parametrize('nm,t,v,c,b,stride,drop', [
+    (3, 23, 25, 64, 8, 1, 0.0),         # rows not a multiple of 16 (ragged last tile)
+    (2, 20, 25, 128, 11, 2, 0.0),       # bottleneck 11 padded to 16, two channel slices
+    (2, 15, 18, 256, 16, 1, 0.0),       # four channel slices, V = 18
+    (1, 9, 25, 64, 8, 2, 0.0),          # odd T with stride 2
+    (2, 31, 25, 256, 16, 2, 0.5),       # dropout mask inside bwd_up
+    (128, 30, 25, 64, 8, 1, 0.0),       # many tiles per persistent warp
+])
+def test_tcn2_kernels_vs_fp64(env, nm, t, v, c, b, stride, drop):
+    """The six streaming kernels of csrc/tcn2.cu (fast-mode Inception TCN,
+    net/st_gcn_mstcn_1x1.py:250-266) one by one against an fp64 evaluation: every output, every
+    weight / bias gradient, the BatchNorm sums; single-pass TF32 -> 5e-3."""
+    from istgcn import ops
+    from istgcn._lib import call, i64, u64
+    dev = torch.device('cuda')
+    gen = torch.Generator().manual_seed(nm + t + c + b)
+    bp = 8 if b <= 8 else 16
+    tout = (t - 1) // stride + 1
+    rin, rout = nm * t * v, nm * tout * v
+
+    def rnd(*shape, scale=1.0):
+        return torch.randn(*shape, generator=gen) * scale
+
+    z = rnd(rin, c)
+    mean1, scale1, beta1, rstd1 = rnd(c, scale=0.3), 1 + rnd(c, scale=0.1), rnd(c, scale=0.3), 1 + rnd(c, scale=0.1).abs()
+    Wd, bd = torch.zeros(c, bp), torch.zeros(bp)
+    Wd[:, :b], bd[:b] = rnd(c, b, scale=0.1), rnd(b, scale=0.1)
+    Weff, beff = torch.zeros(15, bp, bp), torch.zeros(bp)
+    Weff[:, :b, :b], beff[:b] = rnd(15, b, b, scale=0.1), rnd(b, scale=0.1)
+    Wu, bu = torch.zeros(bp, c), rnd(c, scale=0.1)
+    Wu[:b] = rnd(b, c, scale=0.2)
+    go = rnd(rout, c)
+    p2, m12, c2, mean2 = 1 + rnd(c, scale=0.1), rnd(c, scale=0.1), rnd(c, scale=0.1), rnd(c, scale=0.3)
+    d = lambda x: x.double().to(dev)                                            # noqa: E731
+    f = lambda x: x.float().to(dev).contiguous()                                # noqa: E731
+    # ---- fp64 reference
+    z64, Wd64, Weff64, Wu64 = (d(x).requires_grad_(True) for x in (z, Wd, Weff, Wu))
+    bd64, beff64, bu64 = (d(x).requires_grad_(True) for x in (bd, beff, bu))
+    a64 = torch.relu((z64 - d(mean1)) * d(scale1) + d(beta1))
+    h1 = a64 @ Wd64 + bd64
+    h1.retain_grad()
+    h1n = h1.view(nm, t, v, bp).permute(0, 3, 1, 2)
+    w = Weff64.permute(2, 1, 0).unsqueeze(-1)                                   # (out, in, tap, 1)
+    h2 = F.conv2d(h1n, w, beff64, stride=(stride, 1), padding=(7, 0)).permute(0, 2, 3, 1).reshape(rout, bp)
+    h2.retain_grad()
+    u = h2 @ Wu64 + bu64
+    # ---- forward kernels
+    h1g, h2g, ug = (torch.full(sh, float('nan'), device=dev) for sh in ((rin, bp), (rout, bp), (rout, c)))
+    st = torch.zeros(2, c, device=dev, dtype=torch.float64)
+    call('tcn2_down', f(z), f(mean1), f(scale1), f(beta1), f(Wd), f(bd), h1g, i64(rin), c, bp)
+    call('tcn2_conv', h1g, f(Weff), f(beff), h2g, nm, t, v, bp, stride)
+    call('tcn2_up', h2g, f(Wu), f(bu), ug, st[0], st[1], i64(rout), c, bp)
+    assert rel(h1g, h1) < 5e-3
+    assert rel(h2g, h2) < 5e-3
+    assert rel(ug, u) < 5e-3
+    assert rel(st[0], u.sum(0), floor=1e-3 * u.abs().sum(0).max().item()) < 5e-3
+    assert rel(st[1], (u * u).sum(0)) < 5e-3
+    # ---- backward
+    seed = 1234567
+    if drop > 0:
+        keep = ops.dropout_mask(rout * c, drop, seed, dev).view(rout, c).double() / (1 - drop)
+    else:
+        keep = torch.ones(rout, c, device=dev, dtype=torch.float64)
+    du = d(p2) * ((d(go) * keep - d(m12)) - d(c2) * (u.detach() - d(mean2)))
+    u.backward(du)
+    g1_ref = z64.grad                               # = (dh1 Wd^T) masked by the ReLU, times scale1
+    g1_ref = g1_ref / d(scale1)                     # the kernel returns the gradient w.r.t. BN1's output
+    dh2g, dh1g, g1g = (torch.full(sh, float('nan'), device=dev) for sh in ((rout, bp), (rin, bp), (rin, c)))
+    dWu, dbu, dbeff = torch.zeros(bp, c, device=dev), torch.zeros(c, device=dev), torch.zeros(bp, device=dev)
+    dWeff, dbd = torch.zeros(15, bp, bp, device=dev), torch.zeros(bp, device=dev)
+    dWd = torch.zeros(c, bp, device=dev)
+    sg = torch.zeros(2, c, device=dev, dtype=torch.float64)
+    call('tcn2_bwd_up', f(go), ug, f(p2), f(m12), f(c2), f(mean2), h2g, f(Wu), dh2g, dWu, dbu, dbeff,
+         i64(rout), c, bp, float(drop), u64(seed), ops.step_counter(dev))
+    call('tcn2_bwd_conv', dh2g, h1g, f(Weff), dh1g, dWeff, dbd, nm, t, v, bp, stride)
+    call('tcn2_bwd_down', dh1g, f(z), f(mean1), f(scale1), f(beta1), f(rstd1), f(Wd), g1g, dWd, sg[0], sg[1],
+         i64(rin), c, bp)
+    errs = {'dh2': rel(dh2g, h2.grad), 'dWu': rel(dWu, Wu64.grad), 'dbu': rel(dbu, bu64.grad),
+            'dbeff': rel(dbeff, beff64.grad), 'dh1': rel(dh1g, h1.grad), 'dWeff': rel(dWeff, Weff64.grad),
+            'dbd': rel(dbd, bd64.grad), 'g1': rel(g1g, g1_ref), 'dWd': rel(dWd, Wd64.grad),
+            'sg': rel(sg[0], g1_ref.sum(0)),
+            'sgx': rel(sg[1], (g1_ref * (z64.detach() - d(mean1)) * d(rstd1)).sum(0))}
+    calib_log('tcn2 %s: %s' % ((nm, t, v, c, b, stride, drop), ' '.join('%s=%.1e' % kv for kv in errs.items())))
+    assert not report(errs, 5e-3), report(errs, 5e-3)
+
 # ----------------------------------------------------------------------------- data_bn
 def test_data_bn_layout_and_stats(env):
     from istgcn import ops
