@@ -34,6 +34,7 @@ namespace {
 
 constexpr int kT2Taps = 15, kT2Half = 7;
 constexpr int kT2Threads = 256;
+constexpr int kT2HeavyWarps = 4;      // warps per CTA of the register-heavy backward kernels
 
 __device__ __forceinline__ uint32_t tf(float x) { return to_tf32_fast(x); }
 __device__ __forceinline__ float tff(float x) { return __uint_as_float(to_tf32_fast(x)); }
@@ -108,6 +109,32 @@ __device__ __forceinline__ void rows_mma(float (&acc)[8][4], const uint32_t (&a)
         const uint32_t b[2] = {tf(r0[col]), tf(r1[col])};
         mma_m16n8k8(acc[nt], a, b);
     }
+}
+
+// Row -> (sample n, frame, joint v) without per-row divisions: one 32-bit division pair per
+// 16-row tile (uniform over the warp), then a few compares per row.  (64-bit divisions are
+// emulated with ~100 instructions each; four of them per row pair made the first version of the
+// temporal kernels instruction-bound on address arithmetic.)
+struct TileDec {
+    unsigned nb;    // sample of the tile's first row
+    int tb, vb;     // its frame and joint
+};
+__device__ __forceinline__ TileDec decode_tile(unsigned row, int V, int Tper) {
+    const unsigned fb = row / (unsigned)V;
+    TileDec d;
+    d.vb = (int)(row - fb * (unsigned)V);
+    d.nb = fb / (unsigned)Tper;
+    d.tb = (int)(fb - d.nb * (unsigned)Tper);
+    return d;
+}
+// row = tile row + o (0 <= o < 16)
+__device__ __forceinline__ void decode_row(const TileDec& d, int o, int V, int Tper, unsigned& n,
+                                           int& frame, int& v) {
+    v = d.vb + o;
+    frame = d.tb;
+    n = d.nb;
+    while (v >= V) { v -= V; ++frame; }
+    while (frame >= Tper) { frame -= Tper; ++n; }
 }
 
 // ============================================================================ down
@@ -215,16 +242,15 @@ __global__ void __launch_bounds__(kT2Threads) tcn2_conv_kernel(ConvP p) {
     for (long long tile = (long long)blockIdx.x * 8 + warp; tile < ntiles; tile += (long long)gridDim.x * 8) {
         long long base[2];
         int lo[2], hi[2];
+        const TileDec td = decode_tile((unsigned)(tile * 16), V, p.Tout);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
             const long long r = tile * 16 + g + 8 * hh;
-            const long long rc = r < p.rows_out ? r : p.rows_out - 1;
-            const long long f = rc / V;
-            const int v = (int)(rc - f * V);
-            const long long n = f / p.Tout;
-            const int to = (int)(f - n * p.Tout);
+            unsigned n;
+            int to, v;
+            decode_row(td, g + 8 * hh, V, p.Tout, n, to, v);
             const int ti0 = to * s - kT2Half;                        // input frame of tap 0
-            base[hh] = ((n * p.T + ti0) * V + v) * BP;
+            base[hh] = (((long long)n * p.T + ti0) * V + v) * BP;
             lo[hh] = ti0 < 0 ? -ti0 : 0;                             // first valid tap
             hi[hh] = p.T - ti0 < kT2Taps ? p.T - ti0 : kT2Taps;      // one past the last valid tap
             if (r >= p.rows_out) hi[hh] = 0;
@@ -344,8 +370,6 @@ struct BwdUpP {
     uint64_t seed;
     const unsigned long long* step;
 };
-
-constexpr int kT2HeavyWarps = 4;      // warps per CTA of the two register-heavy backward kernels
 
 template <int NT>
 __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdUpP p) {
@@ -554,7 +578,7 @@ __global__ void __launch_bounds__(kT2Threads) tcn2_bwd_conv_kernel(BwdConvP p) {
     for (int i = tid; i < BP; i += kT2Threads) s_dbd[i] = 0.f;
     __syncthreads();
     const int V = p.V, s = p.stride;
-    // ---- phase A: dh1[(n,ti,v)][ci] = sum_tap sum_co Weff[tap][ci][co] dh2[(n,to,v)][co], to*s + tap - 7 = ti
+    // ---- dh1[(n,ti,v)][ci] = sum_tap sum_co Weff[tap][ci][co] dh2[(n,to,v)][co], to*s + tap - 7 = ti
     float dbd[NT][2];
 #pragma unroll
     for (int a = 0; a < NT; ++a) dbd[a][0] = dbd[a][1] = 0.f;
@@ -563,16 +587,15 @@ __global__ void __launch_bounds__(kT2Threads) tcn2_bwd_conv_kernel(BwdConvP p) {
         long long nbase[2];
         int num0[2], vv[2];
         bool okr[2];
+        const TileDec td = decode_tile((unsigned)(tile * 16), V, p.T);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
-            const long long r = tile * 16 + g + 8 * hh;
-            okr[hh] = r < p.rows_in;
-            const long long rc = okr[hh] ? r : p.rows_in - 1;
-            const long long f = rc / V;
-            vv[hh] = (int)(rc - f * V);
-            const long long n = f / p.T;
-            num0[hh] = (int)(f - n * p.T) + kT2Half;                 // to*s = num0 - tap
-            nbase[hh] = n * p.Tout;
+            okr[hh] = tile * 16 + g + 8 * hh < p.rows_in;
+            unsigned n;
+            int ti;
+            decode_row(td, g + 8 * hh, V, p.T, n, ti, vv[hh]);
+            num0[hh] = ti + kT2Half;                                 // to*s = num0 - tap
+            nbase[hh] = (long long)n * p.Tout;
         }
         float acc[NT][4];
 #pragma unroll
@@ -614,17 +637,36 @@ __global__ void __launch_bounds__(kT2Threads) tcn2_bwd_conv_kernel(BwdConvP p) {
             const float v = group_sum_g(dbd[nt][e]);
             if (g == 0) atomicAdd(&s_dbd[nt * 8 + 2 * t + e], v);
         }
-    // ---- phase B: dWeff[tap][ci][co] += h1[(n, to*s + tap - 7, v)][ci] dh2[(n,to,v)][co]
-    // every warp of the CTA walks the CTA's output-row tiles for its own taps (warp, warp + 8)
-    float accw[2][NT][4];
+    __syncthreads();
+    for (int i = tid; i < BP; i += kT2Threads) atomicAdd(&p.dbd[i], s_dbd[i]);
+}
+
+// dWeff[tap][ci][co] += h1[(n, to*s + tap - 7, v)][ci] dh2[(n,to,v)][co]:  m = ci, n = co, k = output
+// rows.  A warp walks its own 16-row tiles for the TPG taps of its tap group (bp = 16: two warps
+// share a tile, 8 + 7 taps, so that the accumulators fit in registers).
+template <int NT>
+__global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_convw_kernel(BwdConvP p) {
+    constexpr int BP = NT * 8, W = kT2HeavyWarps, NTHR = W * 32;
+    constexpr int TG = NT;                       // tap groups
+    constexpr int TPG = (kT2Taps + TG - 1) / TG; // taps per group (15 or 8)
+    extern __shared__ __align__(16) float smem[];
+    float* s_dW = smem;                                             // [15][BP][BP]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    for (int i = tid; i < kT2Taps * BP * BP; i += NTHR) s_dW[i] = 0.f;
+    __syncthreads();
+    const int V = p.V, s = p.stride;
+    const int tgrp = warp % TG, tsub = warp / TG, tpc = W / TG;
+    const int tap_lo = tgrp * TPG;
+    float accw[TPG][NT][4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < TPG; ++a)
 #pragma unroll
         for (int b = 0; b < NT; ++b)
 #pragma unroll
             for (int c = 0; c < 4; ++c) accw[a][b][c] = 0.f;
     const long long ntout = (p.rows_out + 15) >> 4;
-    for (long long tile = blockIdx.x; tile < ntout; tile += gridDim.x) {
+    for (long long tile = (long long)blockIdx.x * tpc + tsub; tile < ntout; tile += (long long)gridDim.x * tpc) {
+        const TileDec td = decode_tile((unsigned)(tile * 16), V, p.Tout);
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
             long long src[2];                                        // h1 row of tap 0 (may be out of range)
@@ -633,21 +675,21 @@ __global__ void __launch_bounds__(kT2Threads) tcn2_bwd_conv_kernel(BwdConvP p) {
             uint32_t b[NT][2];
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
-                const long long r = tile * 16 + 8 * ks + t + 4 * hh;
+                const int o = 8 * ks + t + 4 * hh;
+                const long long r = tile * 16 + o;
                 okr[hh] = r < p.rows_out;
-                const long long rc = okr[hh] ? r : p.rows_out - 1;
-                const long long f = rc / V;
-                const int v = (int)(rc - f * V);
-                const long long n = f / p.Tout;
-                ti0[hh] = (int)(f - n * p.Tout) * s - kT2Half;
-                src[hh] = ((n * p.T + ti0[hh]) * V + v) * BP;
+                unsigned n;
+                int to, v;
+                decode_row(td, o, V, p.Tout, n, to, v);
+                ti0[hh] = to * s - kT2Half;
+                src[hh] = (((long long)n * p.T + ti0[hh]) * V + v) * BP;
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
-                    b[nt][hh] = tf(okr[hh] ? __ldg(p.dh2 + rc * BP + nt * 8 + g) : 0.f);
+                    b[nt][hh] = tf(okr[hh] ? __ldg(p.dh2 + r * BP + nt * 8 + g) : 0.f);
             }
 #pragma unroll
-            for (int sel = 0; sel < 2; ++sel) {
-                const int tap = warp + 8 * sel;
+            for (int j = 0; j < TPG; ++j) {
+                const int tap = tap_lo + j;
                 if (tap < kT2Taps) {
                     uint32_t a[4];
 #pragma unroll
@@ -659,26 +701,26 @@ __global__ void __launch_bounds__(kT2Threads) tcn2_bwd_conv_kernel(BwdConvP p) {
                         a[2 * hh + 1] = NT == 2 ? tf(ok ? __ldg(q + 8) : 0.f) : 0u;
                     }
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) mma_m16n8k8(accw[sel][nt], a, b[nt]);
+                    for (int nt = 0; nt < NT; ++nt) mma_m16n8k8(accw[j][nt], a, b[nt]);
                 }
             }
         }
     }
 #pragma unroll
-    for (int sel = 0; sel < 2; ++sel) {
-        const int tap = warp + 8 * sel;
+    for (int j = 0; j < TPG; ++j) {
+        const int tap = tap_lo + j;
         if (tap < kT2Taps) {
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const int ci = g + 8 * (i >> 1), co = nt * 8 + 2 * t + (i & 1);
-                    if (ci < BP) atomicAdd(&p.dWeff[(tap * BP + ci) * BP + co], accw[sel][nt][i]);
+                    if (ci < BP) atomicAdd(&s_dW[(tap * BP + ci) * BP + co], accw[j][nt][i]);
                 }
         }
     }
     __syncthreads();
-    for (int i = tid; i < BP; i += kT2Threads) atomicAdd(&p.dbd[i], s_dbd[i]);
+    for (int i = tid; i < kT2Taps * BP * BP; i += NTHR) atomicAdd(&p.dWeff[i], s_dW[i]);
 }
 
 // ============================================================================ backward: down
@@ -852,6 +894,7 @@ ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float*
     const int Tout = (T - 1) / stride + 1;
     ConvP p{h1, Weff, beff, h2, T, Tout, V, stride, (long long)NM * Tout * V};
     const int nt = bp / 8;
+    ISTGCN_REQUIRE((long long)NM * T * V < (1ll << 31), ISTGCN_E_SHAPE, "tcn2_conv: more than 2^31 rows");
     const size_t smem = sizeof(float) * kT2Taps * nt * nt * 64;
     const int grid = grid2((p.rows_out + 127) / 128, 4);
     if (nt == 1) {
@@ -922,14 +965,20 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
     BwdConvP p{dh2, h1, Weff, dh1, dWeff, dbd, T, Tout, V, stride, (long long)NM * T * V,
                (long long)NM * Tout * V};
     const int nt = bp / 8;
+    ISTGCN_REQUIRE(p.rows_in < (1ll << 31), ISTGCN_E_SHAPE, "tcn2_bwd_conv: more than 2^31 rows");
     const size_t smem = sizeof(float) * (kT2Taps * nt * nt * 64 + bp);
-    const int grid = grid2((p.rows_in + 127) / 128, 2);
+    const size_t smem_w = sizeof(float) * kT2Taps * bp * bp;
+    constexpr int W = kT2HeavyWarps;
+    const int grid = grid2((p.rows_in + 127) / 128, 4);
+    const int grid_w = grid2(((p.rows_out + 15) / 16 + W / nt - 1) / (W / nt), 3);
     if (nt == 1) {
         set_smem2(tcn2_bwd_conv_kernel<1>, smem);
         tcn2_bwd_conv_kernel<1><<<grid, kT2Threads, smem, (cudaStream_t)s>>>(p);
+        tcn2_bwd_convw_kernel<1><<<grid_w, W * 32, smem_w, (cudaStream_t)s>>>(p);
     } else {
         set_smem2(tcn2_bwd_conv_kernel<2>, smem);
         tcn2_bwd_conv_kernel<2><<<grid, kT2Threads, smem, (cudaStream_t)s>>>(p);
+        tcn2_bwd_convw_kernel<2><<<grid_w, W * 32, smem_w, (cudaStream_t)s>>>(p);
     }
     return finish_launch("tcn2_bwd_conv");
 }

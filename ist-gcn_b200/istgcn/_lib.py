@@ -72,7 +72,7 @@ def _conv(a):
 
 # kernels launched per C-ABI call (tcn_fwd = down + up, tcn_bwd = up + temporal + down,
 # pool_fwd = kernel behind a memset) -- used for the ``gpu_launches`` count of bench.py
-KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2, 'tconv_dw_tc': 2}
+KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2, 'tconv_dw_tc': 2, 'tcn2_bwd_conv': 2}
 launch_count = 0          # kernels launched through this binding since import
 timing = None             # set to a dict by bench.py: name -> list of (start_event, end_event)
 

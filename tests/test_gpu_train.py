@@ -110,75 +110,83 @@ def _model(arch, shape, num_class, g_args, state, dropout=0.0):
 
 
 # ----------------------------------------------------------------------------- training step
-@pytest.mark.parametrize('math', ['3xtf32', 'tf32'])
-def test_trainer_step_eager_vs_graph_vs_oracle(env, math):
-    """Five iterations of Trainer.step -- eager launches, and CUDA-graph capture + replay (steps
-    3..5 are replays) -- against five oracle iterations in fp64: loss trajectory, parameters,
-    BatchNorm running statistics.
+def _momentum_views(tr):
+    """name -> the momentum buffer of that parameter (a view into FlatSGD's flat state)."""
+    out = {}
+    for b, buf in zip(tr.buckets.buckets, tr.optimizer.state):
+        for n, prm in b['params']:
+            off = prm.grad.storage_offset()
+            out[n] = buf[off:off + prm.numel()].view_as(prm)
+    return out
 
-    A training trajectory amplifies gradient rounding from step to step (gradients of this
-    network carry ~1e-2 relative rounding noise per tensor in plain fp32 PyTorch already,
-    tests/test_gpu_parity.py), so the bounds are calibrated on STOCK PYTORCH running the same five
-    steps on this GPU in fp32 (for '3xtf32') or with TF32 enabled (for 'tf32'): our deviation
-    from the fp64 trajectory may be at most max(floor, 4 x PyTorch's own deviation)."""
+
+def _expected_step(before, bufs, arch, lr, x, label, dtype, tf32_flags=(False, False)):
+    """One oracle iteration (recognition.py:273-289) from the given pre-step state:
+    -> loss, {name: parameter after the step}, {BatchNorm buffers after the step}."""
+    from oracle import model_ref
+    old = _tf32_torch(tf32_flags)
+    try:
+        ora = OracleTrainer(before, arch, lr, dtype=dtype)
+        loss, grads, upd = ora.grads(x, label)
+        params = [ora.state[k].clone() for k in ora.names]
+        model_ref.sgd_nesterov_step(params, list(grads), [bufs[k].to(params[0]).clone() for k in ora.names], lr)
+    finally:
+        _tf32_torch(old)
+    return loss.item(), dict(zip(ora.names, params)), upd
+
+
+@pytest.mark.parametrize('math', ['3xtf32', 'tf32'])
+@pytest.mark.parametrize('mode', ['eager', 'graph'])
+def test_trainer_step_vs_oracle(env, math, mode):
+    """Five iterations of Trainer.step -- eager launches, or CUDA-graph capture + replay (steps
+    3..5 are replays) -- each checked against ONE oracle iteration in fp64 started from the
+    trainer's own pre-step state (parameters, momentum, running statistics): loss, parameter
+    update, BatchNorm running statistics.  (Comparing whole trajectories instead measures chaos:
+    by step 4 stock fp32 PyTorch is 1e-2 away from fp64 on the loss.)
+
+    The update is bounded relative to stock PyTorch doing the same single step on this GPU in fp32
+    (for '3xtf32') or with TF32 enabled (for 'tf32'): relative L2 distance to the fp64 update
+    <= max(floor, 4 x PyTorch's own distance)."""
     from istgcn import trainer
     mg, g_args, num_class, shape, state, x, label = _case('ist_gcn')
-    lr, steps = 0.01, 5
+    lr, steps = 0.05, 5
     gen = torch.Generator().manual_seed(9)
     xs = [x] + [torch.randn(shape, generator=gen) for _ in range(steps - 1)]
     ys = [label] + [torch.randint(0, num_class, (shape[0],), generator=gen) for _ in range(steps - 1)]
+    tol = TOL_FWD[math]
     old = env.set_math(math)
-    runs = {}
     try:
-        for mode in ('eager', 'graph'):
-            model = _model('ist_gcn', shape, num_class, g_args, state)
-            tr = trainer.Trainer(model, base_lr=lr, use_graph=(mode == 'graph'))
-            losses = [tr.step(xs[i].cuda(), ys[i].cuda()).item() for i in range(steps)]
-            if mode == 'graph':
-                assert len(tr._graphs) == 1, 'steps 3.. must have been graph replays'
-            runs[mode] = (losses, {k: v.detach().clone() for k, v in model.state_dict().items()})
+        model = _model('ist_gcn', shape, num_class, g_args, state)
+        tr = trainer.Trainer(model, base_lr=lr, use_graph=(mode == 'graph'))
+        mom = _momentum_views(tr)
+        for i in range(steps):
+            before = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+            bufs = {k: v.detach().clone().double() for k, v in mom.items()}
+            loss = tr.step(xs[i].cuda(), ys[i].cuda()).item()
+            after = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+            ref_loss, ref_p, ref_upd = _expected_step(before, bufs, 'ist_gcn', lr, xs[i], ys[i], torch.float64)
+            _, cal_p, _ = _expected_step(before, bufs, 'ist_gcn', lr, xs[i], ys[i], torch.float32,
+                                         (True, True) if math == 'tf32' else (False, False))
+            assert abs(loss - ref_loss) < tol * abs(ref_loss), (i, loss, ref_loss)
+            names = list(ref_p)
+            dm = torch.cat([(after[k].double() - before[k].double()).reshape(-1) for k in names])
+            dr = torch.cat([(ref_p[k].cpu() - before[k].double()).reshape(-1) for k in names])
+            dc = torch.cat([(cal_p[k].double().cpu() - before[k].double()).reshape(-1) for k in names])
+            e_mine, e_cal = rel_l2(dm, dr), rel_l2(dc, dr)
+            print('trainer %s %s step %d: loss %.6f (oracle %.6f) update rel-L2 %.2e (pytorch %.2e)' % (
+                math, mode, i, loss, ref_loss, e_mine, e_cal))
+            assert e_mine < max(2e-3 if math == '3xtf32' else 2e-2, 4 * e_cal), (i, e_mine, e_cal)
+            for k, v in ref_upd.items():
+                if '.gcn.branch.bn.' in k:
+                    continue
+                if k.endswith('num_batches_tracked'):
+                    assert int(after[k]) == int(v), k
+                else:
+                    assert rel(after[k], v) < 2.5 * tol, (i, k)
+        if mode == 'graph':
+            assert len(tr._graphs) == 1, 'steps 3.. must have been graph replays'
     finally:
         env.set_math(old)
-    ora = OracleTrainer(state, 'ist_gcn', lr)
-    ref_losses = [ora.step(xs[i], ys[i]).item() for i in range(steps)]
-    old_flags = _tf32_torch((True, True) if math == 'tf32' else (False, False))
-    try:
-        cal = OracleTrainer(state, 'ist_gcn', lr, dtype=torch.float32)
-        cal_losses = [cal.step(xs[i], ys[i]).item() for i in range(steps)]
-    finally:
-        _tf32_torch(old_flags)
-    tol = TOL_FWD[math]
-    p0 = {k: v.double() for k, v in state.items()}
-
-    def update(after):
-        return torch.cat([(after[k].double().cpu() - p0[k]).reshape(-1) for k in ora.names])
-
-    dr = update(ora.state)
-    dc = update(cal.state)
-    cal_l2 = rel_l2(dc, dr)
-    cal_cos = (dc @ dr / (dc.norm() * dr.norm())).item()
-    for mode, (losses, after) in runs.items():
-        for i in range(steps):
-            bound = max(tol, 4 * abs(cal_losses[i] - ref_losses[i]) / abs(ref_losses[i]))
-            assert abs(losses[i] - ref_losses[i]) < bound * abs(ref_losses[i]), \
-                (mode, i, losses, ref_losses, cal_losses)
-        # parameters: the UPDATE p_after - p_before vs the oracle's, all tensors as one vector
-        dm = update(after)
-        cos = (dm @ dr / (dm.norm() * dr.norm())).item()
-        print('trainer %s %s: update rel-L2 %.2e (pytorch %.2e), cosine %.6f (pytorch %.6f)' % (
-            math, mode, rel_l2(dm, dr), cal_l2, cos, cal_cos))
-        assert 1 - cos < max(1e-4, 4 * (1 - cal_cos)), (mode, cos, cal_cos)
-        assert rel_l2(dm, dr) < max(1e-3, 4 * cal_l2), (mode, rel_l2(dm, dr), cal_l2)
-        for k, v in ora.state.items():
-            if 'running_' in k and '.gcn.branch.bn.' not in k:
-                assert rel(after[k], v) < max(5 * tol, 4 * rel(cal.state[k], v)), (mode, k)
-            elif k.endswith('num_batches_tracked') and '.gcn.branch.bn.' not in k:
-                assert int(after[k]) == int(v), (mode, k)
-    # eager and graph replay run the same kernels on the same data (atomics order differs)
-    le, lg = runs['eager'][0], runs['graph'][0]
-    assert max(abs(a - b) / abs(a) for a, b in zip(le, lg)) < max(tol, 1e-3)
-    de, dg = update(runs['eager'][1]), update(runs['graph'][1])
-    assert rel_l2(dg, de) < max(1e-3, 4 * cal_l2)
 
 
 def test_graph_replay_with_dropout_draws_fresh_masks_and_matches_oracle(env):
@@ -200,11 +208,7 @@ def test_graph_replay_with_dropout_draws_fresh_masks_and_matches_oracle(env):
         losses = [tr.step(xd, yd).item() for _ in range(2)]
         assert losses[0] != losses[1]
         before = {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
-        bufs = {}
-        for b, buf in zip(tr.buckets.buckets, tr.optimizer.state):
-            for n, prm in b['params']:
-                off = prm.grad.storage_offset()
-                bufs[n] = buf[off:off + prm.numel()].view_as(prm).detach().clone().double()
+        bufs = {n: v.detach().clone().double() for n, v in _momentum_views(tr).items()}
         loss = tr.step(xd, yd).item()
     finally:
         env.set_math(old)
