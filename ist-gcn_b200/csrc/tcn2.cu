@@ -22,21 +22,26 @@
 //     tiles of a warp and are flushed once: shuffles -> shared -> one double atomic per CTA.
 // Kernels (one C-ABI entry point each, so that every launch can be timed on its own):
 //   tcn2_down      z -> h1 = relu(BN1(z)) Wd + bd
-//   tcn2_conv      h1 -> h2 = sum_tap Weff[tap] h1[to*s + tap - 7] + beff        (bp-wide only)
+//   tcn2_conv      h1 -> h2 = sum_tap Weff[tap] h1[to*s + tap - 7] + beff        (csrc/tcn2_small.cu)
 //   tcn2_up        h2 -> u = h2 Wu + bu, BN2 sums
 //   tcn2_bwd_up    go, u, h2 -> du -> dh2 = du Wu^T, dWu, dbu, dbeff
-//   tcn2_bwd_conv  dh2, h1 -> dh1, dWeff, dbd                                    (bp-wide only)
+//   tcn2_bwd_conv  dh2, h1 -> dh1, dWeff, dbd                                    (csrc/tcn2_small.cu)
 //   tcn2_bwd_down  dh1, z -> g1 = (dh1 Wd^T) masked by the ReLU, BN1-backward sums, dWd
 #include "common.cuh"
 
 namespace istgcn {
 namespace {
 
-constexpr int kT2Taps = 15, kT2Half = 7;
 constexpr int kT2Threads = 256;
 constexpr int kT2HeavyWarps = 4;      // warps per CTA of the register-heavy backward kernels
 
 __device__ __forceinline__ uint32_t tf(float x) { return to_tf32_fast(x); }
+// value rounded to TF32 (stored form of the bottleneck tensors h1, h2, dh2, dh1: they are only ever
+// tensor-core operands, so their consumers need no conversion instruction)
+__device__ __forceinline__ float rnd_tf32(float x) {
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+}
+__device__ __forceinline__ uint32_t raw(float x) { return __float_as_uint(x); }
 __device__ __forceinline__ float tff(float x) { return __uint_as_float(to_tf32_fast(x)); }
 
 __device__ __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], float2 w) {
@@ -64,12 +69,12 @@ __device__ __forceinline__ void load_small_a(uint32_t (&a)[NT][4], const float* 
     if (NT == 1) {
         const float2 x = ok0 ? ldg2(base + off0 + 2 * t) : make_float2(0.f, 0.f);
         const float2 y = ok1 ? ldg2(base + off1 + 2 * t) : make_float2(0.f, 0.f);
-        a[0][0] = tf(x.x); a[0][1] = tf(y.x); a[0][2] = tf(x.y); a[0][3] = tf(y.y);
+        a[0][0] = raw(x.x); a[0][1] = raw(y.x); a[0][2] = raw(x.y); a[0][3] = raw(y.y);
     } else {
         const float4 x = ok0 ? ldg4(base + off0 + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 y = ok1 ? ldg4(base + off1 + 4 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
-        a[0][0] = tf(x.x); a[0][1] = tf(y.x); a[0][2] = tf(x.y); a[0][3] = tf(y.y);
-        a[NT - 1][0] = tf(x.z); a[NT - 1][1] = tf(y.z); a[NT - 1][2] = tf(x.w); a[NT - 1][3] = tf(y.w);
+        a[0][0] = raw(x.x); a[0][1] = raw(y.x); a[0][2] = raw(x.y); a[0][3] = raw(y.y);
+        a[NT - 1][0] = raw(x.z); a[NT - 1][1] = raw(y.z); a[NT - 1][2] = raw(x.w); a[NT - 1][3] = raw(y.w);
     }
 }
 // first channel of slot (k = t) of k-step kk under that re-labelling (slot k = t + 4 is the next one)
@@ -86,11 +91,11 @@ __device__ __forceinline__ void load_small_at(uint32_t (&a)[4], const float* __r
     const float* pa = base + ra * BP + g;
     const float* pb = base + rb * BP + g;
     const bool oka = ra < rows, okb = rb < rows;
-    a[0] = tf(oka ? __ldg(pa) : 0.f);
-    a[2] = tf(okb ? __ldg(pb) : 0.f);
+    a[0] = raw(oka ? __ldg(pa) : 0.f);
+    a[2] = raw(okb ? __ldg(pb) : 0.f);
     if (NT == 2) {
-        a[1] = tf(oka ? __ldg(pa + 8) : 0.f);
-        a[3] = tf(okb ? __ldg(pb + 8) : 0.f);
+        a[1] = raw(oka ? __ldg(pa + 8) : 0.f);
+        a[3] = raw(okb ? __ldg(pb + 8) : 0.f);
     } else {
         a[1] = 0u;
         a[3] = 0u;
@@ -109,32 +114,6 @@ __device__ __forceinline__ void rows_mma(float (&acc)[8][4], const uint32_t (&a)
         const uint32_t b[2] = {tf(r0[col]), tf(r1[col])};
         mma_m16n8k8(acc[nt], a, b);
     }
-}
-
-// Row -> (sample n, frame, joint v) without per-row divisions: one 32-bit division pair per
-// 16-row tile (uniform over the warp), then a few compares per row.  (64-bit divisions are
-// emulated with ~100 instructions each; four of them per row pair made the first version of the
-// temporal kernels instruction-bound on address arithmetic.)
-struct TileDec {
-    unsigned nb;    // sample of the tile's first row
-    int tb, vb;     // its frame and joint
-};
-__device__ __forceinline__ TileDec decode_tile(unsigned row, int V, int Tper) {
-    const unsigned fb = row / (unsigned)V;
-    TileDec d;
-    d.vb = (int)(row - fb * (unsigned)V);
-    d.nb = fb / (unsigned)Tper;
-    d.tb = (int)(fb - d.nb * (unsigned)Tper);
-    return d;
-}
-// row = tile row + o (0 <= o < 16)
-__device__ __forceinline__ void decode_row(const TileDec& d, int o, int V, int Tper, unsigned& n,
-                                           int& frame, int& v) {
-    v = d.vb + o;
-    frame = d.tb;
-    n = d.nb;
-    while (v >= V) { v -= V; ++frame; }
-    while (frame >= Tper) { frame -= Tper; ++n; }
 }
 
 // ============================================================================ down
@@ -209,77 +188,11 @@ __global__ void __launch_bounds__(kT2Threads, 2) tcn2_down_kernel(DownP p) {
             const int c = nt * 8 + 2 * t;
             const float2 b = ldg2(p.bd + c);
             if (r0 < p.rows)
-                *reinterpret_cast<float2*>(p.h1 + r0 * BP + c) = make_float2(acc[nt][0] + b.x, acc[nt][1] + b.y);
+                *reinterpret_cast<float2*>(p.h1 + r0 * BP + c) =
+                    make_float2(rnd_tf32(acc[nt][0] + b.x), rnd_tf32(acc[nt][1] + b.y));
             if (r1 < p.rows)
-                *reinterpret_cast<float2*>(p.h1 + r1 * BP + c) = make_float2(acc[nt][2] + b.x, acc[nt][3] + b.y);
-        }
-    }
-}
-
-// ============================================================================ temporal conv
-struct ConvP {
-    const float *h1, *Weff, *beff;
-    float* h2;
-    int T, Tout, V, stride;
-    long long rows_out;
-};
-
-template <int NT>
-__global__ void __launch_bounds__(kT2Threads) tcn2_conv_kernel(ConvP p) {
-    constexpr int BP = NT * 8;
-    extern __shared__ __align__(16) float smem[];
-    float2* s_w = reinterpret_cast<float2*>(smem);                  // [15][NT kk][NT nt][32]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    for (int i = tid; i < kT2Taps * NT * NT * 32; i += kT2Threads) {
-        const int l = i & 31, q = i >> 5;
-        const int nt = q % NT, kk = (q / NT) % NT, tap = q / (NT * NT);
-        const int ci = small_ch<NT>(l & 3, kk), co = nt * 8 + (l >> 2);
-        s_w[i] = make_float2(tff(p.Weff[(tap * BP + ci) * BP + co]), tff(p.Weff[(tap * BP + ci + 1) * BP + co]));
-    }
-    __syncthreads();
-    const int V = p.V, s = p.stride;
-    const long long ntiles = (p.rows_out + 15) >> 4;
-    for (long long tile = (long long)blockIdx.x * 8 + warp; tile < ntiles; tile += (long long)gridDim.x * 8) {
-        long long base[2];
-        int lo[2], hi[2];
-        const TileDec td = decode_tile((unsigned)(tile * 16), V, p.Tout);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            const long long r = tile * 16 + g + 8 * hh;
-            unsigned n;
-            int to, v;
-            decode_row(td, g + 8 * hh, V, p.Tout, n, to, v);
-            const int ti0 = to * s - kT2Half;                        // input frame of tap 0
-            base[hh] = (((long long)n * p.T + ti0) * V + v) * BP;
-            lo[hh] = ti0 < 0 ? -ti0 : 0;                             // first valid tap
-            hi[hh] = p.T - ti0 < kT2Taps ? p.T - ti0 : kT2Taps;      // one past the last valid tap
-            if (r >= p.rows_out) hi[hh] = 0;
-        }
-        float acc[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-        const long long tapstep = (long long)V * BP;
-#pragma unroll
-        for (int tap = 0; tap < kT2Taps; ++tap) {
-            uint32_t a[NT][4];
-            load_small_a<NT>(a, p.h1, base[0] + tap * tapstep, base[1] + tap * tapstep,
-                             tap >= lo[0] && tap < hi[0], tap >= lo[1] && tap < hi[1], t);
-#pragma unroll
-            for (int kk = 0; kk < NT; ++kk)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma(acc[nt], a[kk], s_w[((tap * NT + kk) * NT + nt) * 32 + lane]);
-        }
-        const long long r0 = tile * 16 + g, r1 = r0 + 8;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int c = nt * 8 + 2 * t;
-            const float2 b = ldg2(p.beff + c);
-            if (r0 < p.rows_out)
-                *reinterpret_cast<float2*>(p.h2 + r0 * BP + c) = make_float2(acc[nt][0] + b.x, acc[nt][1] + b.y);
-            if (r1 < p.rows_out)
-                *reinterpret_cast<float2*>(p.h2 + r1 * BP + c) = make_float2(acc[nt][2] + b.x, acc[nt][3] + b.y);
+                *reinterpret_cast<float2*>(p.h1 + r1 * BP + c) =
+                    make_float2(rnd_tf32(acc[nt][2] + b.x), rnd_tf32(acc[nt][3] + b.y));
         }
     }
 }
@@ -495,8 +408,10 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) {
                     const int c = nt * 8 + 2 * t;
-                    if (r0 < p.rows) *reinterpret_cast<float2*>(p.dh2 + r0 * BP + c) = make_float2(acch[nt][0], acch[nt][1]);
-                    if (r1 < p.rows) *reinterpret_cast<float2*>(p.dh2 + r1 * BP + c) = make_float2(acch[nt][2], acch[nt][3]);
+                    if (r0 < p.rows)
+                        *reinterpret_cast<float2*>(p.dh2 + r0 * BP + c) = make_float2(rnd_tf32(acch[nt][0]), rnd_tf32(acch[nt][1]));
+                    if (r1 < p.rows)
+                        *reinterpret_cast<float2*>(p.dh2 + r1 * BP + c) = make_float2(rnd_tf32(acch[nt][2]), rnd_tf32(acch[nt][3]));
                     dbe[nt][0] += acch[nt][0] + acch[nt][2];
                     dbe[nt][1] += acch[nt][1] + acch[nt][3];
                 }
@@ -518,8 +433,10 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
                         sum.x += o.x; sum.y += o.y; sum.z += o.z; sum.w += o.w;
                     }
                     const int c = nt * 8 + 2 * t;
-                    if (r0 < p.rows) *reinterpret_cast<float2*>(p.dh2 + r0 * BP + c) = make_float2(sum.x, sum.y);
-                    if (r1 < p.rows) *reinterpret_cast<float2*>(p.dh2 + r1 * BP + c) = make_float2(sum.z, sum.w);
+                    if (r0 < p.rows)
+                        *reinterpret_cast<float2*>(p.dh2 + r0 * BP + c) = make_float2(rnd_tf32(sum.x), rnd_tf32(sum.y));
+                    if (r1 < p.rows)
+                        *reinterpret_cast<float2*>(p.dh2 + r1 * BP + c) = make_float2(rnd_tf32(sum.z), rnd_tf32(sum.w));
                     dbe[nt][0] += sum.x + sum.z;
                     dbe[nt][1] += sum.y + sum.w;
                 }
@@ -552,175 +469,6 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
     for (int i = tid; i < BP * C; i += NTHR) atomicAdd(&p.dWu[i], s_dW[i]);
     for (int i = tid; i < C; i += NTHR) atomicAdd(&p.dbu[i], s_dbu[i]);
     for (int i = tid; i < BP; i += NTHR) atomicAdd(&p.dbeff[i], s_dbe[i]);
-}
-
-// ============================================================================ backward: temporal
-struct BwdConvP {
-    const float *dh2, *h1, *Weff;
-    float *dh1, *dWeff, *dbd;
-    int T, Tout, V, stride;
-    long long rows_in, rows_out;
-};
-
-template <int NT>
-__global__ void __launch_bounds__(kT2Threads) tcn2_bwd_conv_kernel(BwdConvP p) {
-    constexpr int BP = NT * 8;
-    extern __shared__ __align__(16) float smem[];
-    float2* s_w = reinterpret_cast<float2*>(smem);                  // [15][NT kk][NT nt][32]   Weff^T
-    float* s_dbd = smem + kT2Taps * NT * NT * 64;                   // [BP]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    for (int i = tid; i < kT2Taps * NT * NT * 32; i += kT2Threads) {
-        const int l = i & 31, q = i >> 5;
-        const int nt = q % NT, kk = (q / NT) % NT, tap = q / (NT * NT);
-        const int co = small_ch<NT>(l & 3, kk), ci = nt * 8 + (l >> 2);
-        s_w[i] = make_float2(tff(p.Weff[(tap * BP + ci) * BP + co]), tff(p.Weff[(tap * BP + ci) * BP + co + 1]));
-    }
-    for (int i = tid; i < BP; i += kT2Threads) s_dbd[i] = 0.f;
-    __syncthreads();
-    const int V = p.V, s = p.stride;
-    // ---- dh1[(n,ti,v)][ci] = sum_tap sum_co Weff[tap][ci][co] dh2[(n,to,v)][co], to*s + tap - 7 = ti
-    float dbd[NT][2];
-#pragma unroll
-    for (int a = 0; a < NT; ++a) dbd[a][0] = dbd[a][1] = 0.f;
-    const long long ntin = (p.rows_in + 15) >> 4;
-    for (long long tile = (long long)blockIdx.x * 8 + warp; tile < ntin; tile += (long long)gridDim.x * 8) {
-        long long nbase[2];
-        int num0[2], vv[2];
-        bool okr[2];
-        const TileDec td = decode_tile((unsigned)(tile * 16), V, p.T);
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-            okr[hh] = tile * 16 + g + 8 * hh < p.rows_in;
-            unsigned n;
-            int ti;
-            decode_row(td, g + 8 * hh, V, p.T, n, ti, vv[hh]);
-            num0[hh] = ti + kT2Half;                                 // to*s = num0 - tap
-            nbase[hh] = (long long)n * p.Tout;
-        }
-        float acc[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-#pragma unroll
-        for (int tap = 0; tap < kT2Taps; ++tap) {
-            long long off[2];
-            bool ok[2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int num = num0[hh] - tap;
-                const int to = s == 2 ? num >> 1 : num;
-                ok[hh] = okr[hh] && num >= 0 && (s == 1 || (num & 1) == 0) && to < p.Tout;
-                off[hh] = ((nbase[hh] + to) * V + vv[hh]) * BP;
-            }
-            uint32_t a[NT][4];
-            load_small_a<NT>(a, p.dh2, off[0], off[1], ok[0], ok[1], t);
-#pragma unroll
-            for (int kk = 0; kk < NT; ++kk)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) mma(acc[nt], a[kk], s_w[((tap * NT + kk) * NT + nt) * 32 + lane]);
-        }
-        const long long r0 = tile * 16 + g, r1 = r0 + 8;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int c = nt * 8 + 2 * t;
-            if (okr[0]) *reinterpret_cast<float2*>(p.dh1 + r0 * BP + c) = make_float2(acc[nt][0], acc[nt][1]);
-            if (okr[1]) *reinterpret_cast<float2*>(p.dh1 + r1 * BP + c) = make_float2(acc[nt][2], acc[nt][3]);
-            dbd[nt][0] += acc[nt][0] + acc[nt][2];                   // invalid rows accumulated zeros
-            dbd[nt][1] += acc[nt][1] + acc[nt][3];
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float v = group_sum_g(dbd[nt][e]);
-            if (g == 0) atomicAdd(&s_dbd[nt * 8 + 2 * t + e], v);
-        }
-    __syncthreads();
-    for (int i = tid; i < BP; i += kT2Threads) atomicAdd(&p.dbd[i], s_dbd[i]);
-}
-
-// dWeff[tap][ci][co] += h1[(n, to*s + tap - 7, v)][ci] dh2[(n,to,v)][co]:  m = ci, n = co, k = output
-// rows.  A warp walks its own 16-row tiles for the TPG taps of its tap group (bp = 16: two warps
-// share a tile, 8 + 7 taps, so that the accumulators fit in registers).
-template <int NT>
-__global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_convw_kernel(BwdConvP p) {
-    constexpr int BP = NT * 8, W = kT2HeavyWarps, NTHR = W * 32;
-    constexpr int TG = NT;                       // tap groups
-    constexpr int TPG = (kT2Taps + TG - 1) / TG; // taps per group (15 or 8)
-    extern __shared__ __align__(16) float smem[];
-    float* s_dW = smem;                                             // [15][BP][BP]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    for (int i = tid; i < kT2Taps * BP * BP; i += NTHR) s_dW[i] = 0.f;
-    __syncthreads();
-    const int V = p.V, s = p.stride;
-    const int tgrp = warp % TG, tsub = warp / TG, tpc = W / TG;
-    const int tap_lo = tgrp * TPG;
-    float accw[TPG][NT][4];
-#pragma unroll
-    for (int a = 0; a < TPG; ++a)
-#pragma unroll
-        for (int b = 0; b < NT; ++b)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) accw[a][b][c] = 0.f;
-    const long long ntout = (p.rows_out + 15) >> 4;
-    for (long long tile = (long long)blockIdx.x * tpc + tsub; tile < ntout; tile += (long long)gridDim.x * tpc) {
-        const TileDec td = decode_tile((unsigned)(tile * 16), V, p.Tout);
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            long long src[2];                                        // h1 row of tap 0 (may be out of range)
-            int ti0[2];
-            bool okr[2];
-            uint32_t b[NT][2];
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-                const int o = 8 * ks + t + 4 * hh;
-                const long long r = tile * 16 + o;
-                okr[hh] = r < p.rows_out;
-                unsigned n;
-                int to, v;
-                decode_row(td, o, V, p.Tout, n, to, v);
-                ti0[hh] = to * s - kT2Half;
-                src[hh] = (((long long)n * p.T + ti0[hh]) * V + v) * BP;
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-                    b[nt][hh] = tf(okr[hh] ? __ldg(p.dh2 + r * BP + nt * 8 + g) : 0.f);
-            }
-#pragma unroll
-            for (int j = 0; j < TPG; ++j) {
-                const int tap = tap_lo + j;
-                if (tap < kT2Taps) {
-                    uint32_t a[4];
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int ti = ti0[hh] + tap;
-                        const bool ok = okr[hh] && ti >= 0 && ti < p.T;
-                        const float* q = p.h1 + src[hh] + (long long)tap * V * BP + g;
-                        a[2 * hh] = tf(ok ? __ldg(q) : 0.f);
-                        a[2 * hh + 1] = NT == 2 ? tf(ok ? __ldg(q + 8) : 0.f) : 0u;
-                    }
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) mma_m16n8k8(accw[j][nt], a, b[nt]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < TPG; ++j) {
-        const int tap = tap_lo + j;
-        if (tap < kT2Taps) {
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ci = g + 8 * (i >> 1), co = nt * 8 + 2 * t + (i & 1);
-                    if (ci < BP) atomicAdd(&s_dW[(tap * BP + ci) * BP + co], accw[j][nt][i]);
-                }
-        }
-    }
-    __syncthreads();
-    for (int i = tid; i < kT2Taps * BP * BP; i += NTHR) atomicAdd(&p.dWeff[i], s_dW[i]);
 }
 
 // ============================================================================ backward: down
@@ -854,13 +602,6 @@ int check2(const char* who, long long rows, int C, int bp) {
     return 0;
 }
 
-int check2t(const char* who, int NM, int T, int V, int bp, int stride) {
-    ISTGCN_REQUIRE(NM >= 0 && T >= 1 && V >= 1, ISTGCN_E_SHAPE, "%s: bad NM/T/V (%d,%d,%d)", who, NM, T, V);
-    ISTGCN_REQUIRE(bp == 8 || bp == 16, ISTGCN_E_SHAPE, "%s: padded bottleneck bp=%d must be 8 or 16", who, bp);
-    ISTGCN_REQUIRE(stride == 1 || stride == 2, ISTGCN_E_SHAPE, "%s: stride=%d unsupported", who, stride);
-    return 0;
-}
-
 }  // namespace
 }  // namespace istgcn
 
@@ -884,27 +625,6 @@ ISTGCN_API int istgcn_tcn2_down(const float* z, const float* mean1, const float*
     else { if (nt == 1) { T2_DOWN(256, 1); } else { T2_DOWN(256, 2); } }
 #undef T2_DOWN
     return finish_launch("tcn2_down");
-}
-
-ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float* beff, float* h2,
-                                int NM, int T, int V, int bp, int stride, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(h1 && Weff && beff && h2, ISTGCN_E_ARG, "tcn2_conv: null pointer");
-    if (int e = check2t("tcn2_conv", NM, T, V, bp, stride)) return e;
-    if (NM == 0) return 0;
-    const int Tout = (T - 1) / stride + 1;
-    ConvP p{h1, Weff, beff, h2, T, Tout, V, stride, (long long)NM * Tout * V};
-    const int nt = bp / 8;
-    ISTGCN_REQUIRE((long long)NM * T * V < (1ll << 31), ISTGCN_E_SHAPE, "tcn2_conv: more than 2^31 rows");
-    const size_t smem = sizeof(float) * kT2Taps * nt * nt * 64;
-    const int grid = grid2((p.rows_out + 127) / 128, 4);
-    if (nt == 1) {
-        set_smem2(tcn2_conv_kernel<1>, smem);
-        tcn2_conv_kernel<1><<<grid, kT2Threads, smem, (cudaStream_t)s>>>(p);
-    } else {
-        set_smem2(tcn2_conv_kernel<2>, smem);
-        tcn2_conv_kernel<2><<<grid, kT2Threads, smem, (cudaStream_t)s>>>(p);
-    }
-    return finish_launch("tcn2_conv");
 }
 
 ISTGCN_API int istgcn_tcn2_up(const float* h2, const float* Wu, const float* bu, float* u,
@@ -953,34 +673,6 @@ ISTGCN_API int istgcn_tcn2_bwd_up(const float* go, const float* u, const float* 
         tcn2_bwd_up_kernel<2><<<grid, W * 32, smem, (cudaStream_t)s>>>(p);
     }
     return finish_launch("tcn2_bwd_up");
-}
-
-ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const float* Weff, float* dh1,
-                                    float* dWeff, float* dbd, int NM, int T, int V, int bp, int stride,
-                                    istgcn_stream_t s) {
-    ISTGCN_REQUIRE(dh2 && h1 && Weff && dh1 && dWeff && dbd, ISTGCN_E_ARG, "tcn2_bwd_conv: null pointer");
-    if (int e = check2t("tcn2_bwd_conv", NM, T, V, bp, stride)) return e;
-    if (NM == 0) return 0;
-    const int Tout = (T - 1) / stride + 1;
-    BwdConvP p{dh2, h1, Weff, dh1, dWeff, dbd, T, Tout, V, stride, (long long)NM * T * V,
-               (long long)NM * Tout * V};
-    const int nt = bp / 8;
-    ISTGCN_REQUIRE(p.rows_in < (1ll << 31), ISTGCN_E_SHAPE, "tcn2_bwd_conv: more than 2^31 rows");
-    const size_t smem = sizeof(float) * (kT2Taps * nt * nt * 64 + bp);
-    const size_t smem_w = sizeof(float) * kT2Taps * bp * bp;
-    constexpr int W = kT2HeavyWarps;
-    const int grid = grid2((p.rows_in + 127) / 128, 4);
-    const int grid_w = grid2(((p.rows_out + 15) / 16 + W / nt - 1) / (W / nt), 3);
-    if (nt == 1) {
-        set_smem2(tcn2_bwd_conv_kernel<1>, smem);
-        tcn2_bwd_conv_kernel<1><<<grid, kT2Threads, smem, (cudaStream_t)s>>>(p);
-        tcn2_bwd_convw_kernel<1><<<grid_w, W * 32, smem_w, (cudaStream_t)s>>>(p);
-    } else {
-        set_smem2(tcn2_bwd_conv_kernel<2>, smem);
-        tcn2_bwd_conv_kernel<2><<<grid, kT2Threads, smem, (cudaStream_t)s>>>(p);
-        tcn2_bwd_convw_kernel<2><<<grid_w, W * 32, smem_w, (cudaStream_t)s>>>(p);
-    }
-    return finish_launch("tcn2_bwd_conv");
 }
 
 ISTGCN_API int istgcn_tcn2_bwd_down(const float* dh1, const float* z, const float* mean1,
