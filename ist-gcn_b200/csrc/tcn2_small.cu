@@ -37,20 +37,39 @@ struct SmallP {
     float* out;          // FWD: h2, BWD: dh1  ([NM][Tf][V][BP]);  weight kernel: dWeff
     float* colsum;       // BWD: dbd[BP] += column sums of out; else nullptr
     int NM, Tin, Tf, V, stride, inv16;
+    unsigned inv_per;    // ceil(2^32 / (V*BP/4))
 };
 
-// stage frames [q0, q0 + Q) of sample n: source frame of staged frame q given by `src_of(q)` (-1 = zeros)
+// Stage Q frames of sample n into shared memory; staged frame q comes from source frame src_of(q)
+// (-1 = zeros: temporal padding / the zero frames of the upsampled stride-2 gradient).  The copy is
+// flat over the 16-byte elements of the staged array -- element -> (frame, offset) by a multiply-high
+// with the precomputed reciprocal of the frame size -- and every thread first issues a batch of
+// independent loads, then the stores: one L2 round trip per batch instead of one per element.
 template <int BP, typename F>
 __device__ __forceinline__ void stage_frames(float* __restrict__ dst, const float* __restrict__ in,
-                                             long long n, int Tin, int V, int Q, F src_of, int warp,
-                                             int lane) {
-    const int per = V * BP / 4;
-    for (int q = warp; q < Q; q += kThr / 32) {
-        const int src = src_of(q);
-        const float* sp = in + ((n * Tin + (src < 0 ? 0 : src)) * V) * BP;
-        float* dp = dst + q * V * BP;
-        for (int i = lane; i < per; i += 32)
-            st4(dp + 4 * i, src >= 0 ? __ldg(reinterpret_cast<const float4*>(sp) + i) : make_float4(0.f, 0.f, 0.f, 0.f));
+                                             long long n, int Tin, int V, int Q, unsigned inv_per,
+                                             F src_of, int tid) {
+    constexpr int kBatch = 6;
+    const int per = V * BP / 4, total = Q * per;
+    const float4* base = reinterpret_cast<const float4*>(in + (n * Tin) * V * BP);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i0 = tid; i0 < total; i0 += kBatch * kThr) {
+        float4 v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int idx = i0 + k * kThr;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < total) {
+                const int q = (int)__umulhi((unsigned)idx, inv_per);
+                const int src = src_of(q);
+                if (src >= 0) v[k] = __ldg(base + src * per + (idx - q * per));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            const int idx = i0 + k * kThr;
+            if (idx < total) d4[idx] = v[k];
+        }
     }
 }
 
@@ -96,17 +115,17 @@ __global__ void __launch_bounds__(kThr, 2) tcn2_small_conv_kernel(SmallP p) {
         __syncthreads();                         // the previous tile's readers are done (and s_w is filled)
         if (!BWD) {
             const int first = f0 * s - kHalf;
-            stage_frames<BP>(s_in, p.in, n, p.Tin, V, Q,
-                             [&](int q) { const int f = first + q; return f >= 0 && f < p.Tin ? f : -1; }, warp, lane);
+            stage_frames<BP>(s_in, p.in, n, p.Tin, V, Q, p.inv_per,
+                             [&](int q) { const int f = first + q; return f >= 0 && f < p.Tin ? f : -1; }, tid);
         } else {
             const int first = f0 - kHalf;        // staged frame q <-> num = to*s = first + q
-            stage_frames<BP>(s_in, p.in, n, p.Tin, V, Q,
+            stage_frames<BP>(s_in, p.in, n, p.Tin, V, Q, p.inv_per,
                              [&](int q) {
                                  const int num = first + q;
                                  if (num < 0 || (s == 2 && (num & 1))) return -1;
                                  const int to = s == 2 ? num >> 1 : num;
                                  return to < p.Tin ? to : -1;
-                             }, warp, lane);
+                             }, tid);
         }
         __syncthreads();
         for (int wt = warp; wt * 16 < valid; wt += kThr / 32) {
@@ -206,10 +225,10 @@ __global__ void __launch_bounds__(kThr, 2) tcn2_small_dw_kernel(SmallP p) {
         __syncthreads();
         {
             const int first = f0 * s - kHalf;
-            stage_frames<BP>(s_h, p.in, n, p.Tin, V, Q,
-                             [&](int q) { const int f = first + q; return f >= 0 && f < p.Tin ? f : -1; }, warp, lane);
-            stage_frames<BP>(s_d, p.in2, n, p.Tf, V, kTT,
-                             [&](int q) { return q < nfr ? f0 + q : -1; }, warp, lane);
+            stage_frames<BP>(s_h, p.in, n, p.Tin, V, Q, p.inv_per,
+                             [&](int q) { const int f = first + q; return f >= 0 && f < p.Tin ? f : -1; }, tid);
+            stage_frames<BP>(s_d, p.in2, n, p.Tf, V, kTT, p.inv_per,
+                             [&](int q) { return q < nfr ? f0 + q : -1; }, tid);
         }
         __syncthreads();
         for (int wt = wq; wt * 16 < valid; wt += 4) {
@@ -288,7 +307,8 @@ ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float*
     if (int e = check_small("tcn2_conv", NM, T, V, bp, stride)) return e;
     if (NM == 0) return 0;
     const int Tout = (T - 1) / stride + 1, nt = bp / 8;
-    SmallP p{h1, nullptr, Weff, beff, h2, nullptr, NM, T, Tout, V, stride, (65536 + V - 1) / V};
+    const unsigned inv_per = (unsigned)(((1ull << 32) + (unsigned)(V * bp / 4) - 1) / (unsigned)(V * bp / 4));
+    SmallP p{h1, nullptr, Weff, beff, h2, nullptr, NM, T, Tout, V, stride, (65536 + V - 1) / V, inv_per};
     const int Q = (kTT - 1) * stride + kTaps;
     const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
     const int grid = grid_small(NM, Tout);
@@ -310,8 +330,9 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
     if (NM == 0) return 0;
     const int Tout = (T - 1) / stride + 1, nt = bp / 8;
     const int inv16 = (65536 + V - 1) / V;
+    const unsigned inv_per = (unsigned)(((1ull << 32) + (unsigned)(V * bp / 4) - 1) / (unsigned)(V * bp / 4));
     {   // dh1 (frames of the output = T) from the zero-upsampled dh2, column sums -> dbd
-        SmallP p{dh2, nullptr, Weff, nullptr, dh1, dbd, NM, Tout, T, V, stride, inv16};
+        SmallP p{dh2, nullptr, Weff, nullptr, dh1, dbd, NM, Tout, T, V, stride, inv16, inv_per};
         const int Q = kTT + 2 * kHalf;
         const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
         const int grid = grid_small(NM, T);
@@ -325,7 +346,7 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
         if (int e = finish_launch("tcn2_bwd_conv (data)")) return e;
     }
     {   // dWeff
-        SmallP p{h1, dh2, Weff, nullptr, dWeff, nullptr, NM, T, Tout, V, stride, inv16};
+        SmallP p{h1, dh2, Weff, nullptr, dWeff, nullptr, NM, T, Tout, V, stride, inv16, inv_per};
         const int Q = (kTT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)kTaps * bp * bp + (size_t)kTT * V * bp + (size_t)Q * V * bp);
         const int grid = grid_small(NM, Tout);
