@@ -75,7 +75,7 @@ __device__ __forceinline__ void stage_frames(float* __restrict__ dst, const floa
 
 // ---------------------------------------------------------------------------- data kernel
 template <int NT, bool BWD>
-__global__ void __launch_bounds__(kThr, 2) tcn2_small_conv_kernel(SmallP p) {
+__global__ void __launch_bounds__(kThr, 3) tcn2_small_conv_kernel(SmallP p) {
     constexpr int BP = NT * 8;
     extern __shared__ __align__(16) float smem[];
     float2* s_w = reinterpret_cast<float2*>(smem);                  // [15][NT kk][NT nt][32]
@@ -134,19 +134,21 @@ __global__ void __launch_bounds__(kThr, 2) tcn2_small_conv_kernel(SmallP p) {
             const int fl0 = (rc0 * p.inv16) >> 16, fl1 = (rc1 * p.inv16) >> 16;
             const float* a0p = s_in + ((fl0 * sq) * V + (rc0 - fl0 * V)) * BP + (NT == 1 ? 2 : 4) * t;
             const float* a1p = s_in + ((fl1 * sq) * V + (rc1 - fl1 * V)) * BP + (NT == 1 ? 2 : 4) * t;
-            float acc[NT][4];
+            // two accumulator sets (even / odd taps): the dependent-MMA chain is the critical path
+            float acc[NT][4], acc2[NT][4];
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
+                for (int i = 0; i < 4; ++i) acc[nt][i] = acc2[nt][i] = 0.f;
 #pragma unroll
             for (int tap = 0; tap < kTaps; ++tap) {
+                float (&ac)[NT][4] = (tap & 1) ? acc2 : acc;
                 if (NT == 1) {
                     const float2 x = *reinterpret_cast<const float2*>(a0p + tap * tapstep);
                     const float2 y = *reinterpret_cast<const float2*>(a1p + tap * tapstep);
                     const float a[4] = {x.x, y.x, x.y, y.y};
                     const float2 w = s_w[tap * 32 + lane];
-                    mma_f(acc[0], a, w.x, w.y);
+                    mma_f(ac[0], a, w.x, w.y);
                 } else {
                     const float4 x = *reinterpret_cast<const float4*>(a0p + tap * tapstep);
                     const float4 y = *reinterpret_cast<const float4*>(a1p + tap * tapstep);
@@ -156,10 +158,14 @@ __global__ void __launch_bounds__(kThr, 2) tcn2_small_conv_kernel(SmallP p) {
 #pragma unroll
                         for (int nt = 0; nt < NT; ++nt) {
                             const float2 w = s_w[((tap * NT + kk) * NT + nt) * 32 + lane];
-                            mma_f(acc[nt], a[kk], w.x, w.y);
+                            mma_f(ac[nt], a[kk], w.x, w.y);
                         }
                 }
             }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[nt][i] += acc2[nt][i];
             float* o0 = p.out + (((long long)n * p.Tf + f0) * V + rl0) * BP + 2 * t;
             float* o1 = o0 + 8 * BP;
             const bool ok0 = rl0 < valid, ok1 = rl1 < valid;
@@ -289,9 +295,12 @@ int check_small(const char* who, int NM, int T, int V, int bp, int stride) {
     return 0;
 }
 
-int grid_small(int NM, int Tf) {
+template <typename K>
+int grid_small(K kern, size_t smem, int NM, int Tf) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThr, smem) != cudaSuccess || occ < 1) occ = 1;
     const long long items = (long long)NM * ((Tf + kTT - 1) / kTT);
-    long long n = (long long)num_sms() * 2;
+    long long n = (long long)num_sms() * occ;
     if (n > items) n = items;
     return (int)(n < 1 ? 1 : n);
 }
@@ -311,13 +320,12 @@ ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float*
     SmallP p{h1, nullptr, Weff, beff, h2, nullptr, NM, T, Tout, V, stride, (65536 + V - 1) / V, inv_per};
     const int Q = (kTT - 1) * stride + kTaps;
     const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
-    const int grid = grid_small(NM, Tout);
     if (nt == 1) {
         set_smem3(tcn2_small_conv_kernel<1, false>, smem);
-        tcn2_small_conv_kernel<1, false><<<grid, kThr, smem, (cudaStream_t)s>>>(p);
+        tcn2_small_conv_kernel<1, false><<<grid_small(tcn2_small_conv_kernel<1, false>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
     } else {
         set_smem3(tcn2_small_conv_kernel<2, false>, smem);
-        tcn2_small_conv_kernel<2, false><<<grid, kThr, smem, (cudaStream_t)s>>>(p);
+        tcn2_small_conv_kernel<2, false><<<grid_small(tcn2_small_conv_kernel<2, false>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
     }
     return finish_launch("tcn2_conv");
 }
@@ -335,13 +343,12 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
         SmallP p{dh2, nullptr, Weff, nullptr, dh1, dbd, NM, Tout, T, V, stride, inv16, inv_per};
         const int Q = kTT + 2 * kHalf;
         const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
-        const int grid = grid_small(NM, T);
         if (nt == 1) {
             set_smem3(tcn2_small_conv_kernel<1, true>, smem);
-            tcn2_small_conv_kernel<1, true><<<grid, kThr, smem, (cudaStream_t)s>>>(p);
+            tcn2_small_conv_kernel<1, true><<<grid_small(tcn2_small_conv_kernel<1, true>, smem, NM, T), kThr, smem, (cudaStream_t)s>>>(p);
         } else {
             set_smem3(tcn2_small_conv_kernel<2, true>, smem);
-            tcn2_small_conv_kernel<2, true><<<grid, kThr, smem, (cudaStream_t)s>>>(p);
+            tcn2_small_conv_kernel<2, true><<<grid_small(tcn2_small_conv_kernel<2, true>, smem, NM, T), kThr, smem, (cudaStream_t)s>>>(p);
         }
         if (int e = finish_launch("tcn2_bwd_conv (data)")) return e;
     }
@@ -349,13 +356,12 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
         SmallP p{h1, dh2, Weff, nullptr, dWeff, nullptr, NM, T, Tout, V, stride, inv16, inv_per};
         const int Q = (kTT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)kTaps * bp * bp + (size_t)kTT * V * bp + (size_t)Q * V * bp);
-        const int grid = grid_small(NM, Tout);
         if (nt == 1) {
             set_smem3(tcn2_small_dw_kernel<1>, smem);
-            tcn2_small_dw_kernel<1><<<grid, kThr, smem, (cudaStream_t)s>>>(p);
+            tcn2_small_dw_kernel<1><<<grid_small(tcn2_small_dw_kernel<1>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
         } else {
             set_smem3(tcn2_small_dw_kernel<2>, smem);
-            tcn2_small_dw_kernel<2><<<grid, kThr, smem, (cudaStream_t)s>>>(p);
+            tcn2_small_dw_kernel<2><<<grid_small(tcn2_small_dw_kernel<2>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
         }
     }
     return finish_launch("tcn2_bwd_conv (weights)");
