@@ -74,7 +74,9 @@ __device__ __forceinline__ void stage_frames(float* __restrict__ dst, const floa
 }
 
 // ---------------------------------------------------------------------------- data kernel
-template <int NT, bool BWD>
+// VV = number of joints as a compile-time constant (25 NTU, 18 Kinetics; 0 = run-time): the tap
+// offsets of the fragment loads become immediates instead of one multiply-add per tap and row.
+template <int NT, bool BWD, int VV>
 __global__ void __launch_bounds__(kThr, 3) tcn2_small_conv_kernel(SmallP p) {
     constexpr int BP = NT * 8;
     extern __shared__ __align__(16) float smem[];
@@ -82,7 +84,7 @@ __global__ void __launch_bounds__(kThr, 3) tcn2_small_conv_kernel(SmallP p) {
     float* s_col = smem + kTaps * NT * NT * 64;                     // [BP] (+ padding to 16 floats)
     float* s_in = s_col + 16;                                       // [Q][V][BP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const int V = p.V, s = p.stride;
+    const int V = VV ? VV : p.V, s = p.stride;
     const int sq = BWD ? 1 : s;
     const int Q = BWD ? kTT + 2 * kHalf : (kTT - 1) * s + kTaps;
     for (int i = tid; i < kTaps * NT * NT * 32; i += kThr) {
@@ -201,11 +203,11 @@ __global__ void __launch_bounds__(kThr, 3) tcn2_small_conv_kernel(SmallP p) {
 // ---------------------------------------------------------------------------- weight kernel
 // m = ci, n = co, k = output rows.  Warps 0..3 take taps 0..7, warps 4..7 taps 8..14; inside a group
 // the four warps split the 16-row tiles of the staged (sample, 16-frame) tile.
-template <int NT>
+template <int NT, int VV>
 __global__ void __launch_bounds__(kThr, 2) tcn2_small_dw_kernel(SmallP p) {
     constexpr int BP = NT * 8;
     extern __shared__ __align__(16) float smem[];
-    const int V = p.V, s = p.stride;
+    const int V = VV ? VV : p.V, s = p.stride;
     const int Q = (kTT - 1) * s + kTaps;
     float* s_dW = smem;                                             // [15][BP][BP]
     float* s_d = s_dW + kTaps * BP * BP;                            // [kTT][V][BP]   dh2 tile
@@ -251,32 +253,55 @@ __global__ void __launch_bounds__(kThr, 2) tcn2_small_dw_kernel(SmallP p) {
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) b[nt][hh] = s_d[rl * BP + nt * 8 + g];
                 }
+                if (NT == 2) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int tap = tg * 8 + j;                      // warp-uniform
-                    if (tap < kTaps) {
-                        const float a[4] = {ap[0][tap * tapstep], NT == 2 ? ap[0][tap * tapstep + (NT - 1) * 8] : 0.f,
-                                            ap[1][tap * tapstep], NT == 2 ? ap[1][tap * tapstep + (NT - 1) * 8] : 0.f};
+                    for (int j = 0; j < 8; ++j) {
+                        const int tap = tg * 8 + j;                  // warp-uniform
+                        if (tap < kTaps) {
+                            const float a[4] = {ap[0][tap * tapstep], ap[0][tap * tapstep + 8],
+                                                ap[1][tap * tapstep], ap[1][tap * tapstep + 8]};
 #pragma unroll
-                        for (int nt = 0; nt < NT; ++nt) mma_f(acc[j][nt], a, b[nt][0], b[nt][1]);
+                            for (int nt = 0; nt < NT; ++nt) mma_f(acc[j][nt], a, b[nt][0], b[nt][1]);
+                        }
+                    }
+                } else {
+                    // bp = 8: the 16 rows of the A fragment hold TWO taps (m = g: tap 2j, m = g + 8:
+                    // tap 2j + 1), so 15 taps cost 8 MMAs instead of 15 half-empty ones
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int ta = tg * 8 + 2 * j, tb = ta + 1;
+                        const bool hb = tb < kTaps;
+                        const float a[4] = {ap[0][ta * tapstep], hb ? ap[0][(hb ? tb : ta) * tapstep] : 0.f,
+                                            ap[1][ta * tapstep], hb ? ap[1][(hb ? tb : ta) * tapstep] : 0.f};
+                        mma_f(acc[j][0], a, b[0][0], b[0][1]);
                     }
                 }
             }
         }
     }
     __syncthreads();
+    if (NT == 2) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int tap = tg * 8 + j;
-        if (tap < kTaps) {
+        for (int j = 0; j < 8; ++j) {
+            const int tap = tg * 8 + j;
+            if (tap < kTaps) {
 #pragma unroll
-            for (int nt = 0; nt < NT; ++nt)
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int ci = g + 8 * (i >> 1), co = nt * 8 + 2 * t + (i & 1);
-                    if (ci < BP) atomicAdd(&s_dW[(tap * BP + ci) * BP + co], acc[j][nt][i]);
-                }
+                    for (int i = 0; i < 4; ++i) {
+                        const int ci = g + 8 * (i >> 1), co = nt * 8 + 2 * t + (i & 1);
+                        atomicAdd(&s_dW[(tap * BP + ci) * BP + co], acc[j][nt][i]);
+                    }
+            }
         }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int tap = tg * 8 + 2 * j + (i >> 1), co = 2 * t + (i & 1);
+                if (tap < kTaps) atomicAdd(&s_dW[(tap * BP + g) * BP + co], acc[j][0][i]);
+            }
     }
     __syncthreads();
     for (int i = tid; i < kTaps * BP * BP; i += kThr) atomicAdd(&p.out[i], s_dW[i]);
@@ -310,6 +335,11 @@ int grid_small(K kern, size_t smem, int NM, int Tf) {
 
 using namespace istgcn;
 
+#define T2S_DISPATCH_V(LAUNCH)                  \
+    if (V == 25) { LAUNCH(25); }                \
+    else if (V == 18) { LAUNCH(18); }           \
+    else { LAUNCH(0); }
+
 ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float* beff, float* h2,
                                 int NM, int T, int V, int bp, int stride, istgcn_stream_t s) {
     ISTGCN_REQUIRE(h1 && Weff && beff && h2, ISTGCN_E_ARG, "tcn2_conv: null pointer");
@@ -320,13 +350,18 @@ ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float*
     SmallP p{h1, nullptr, Weff, beff, h2, nullptr, NM, T, Tout, V, stride, (65536 + V - 1) / V, inv_per};
     const int Q = (kTT - 1) * stride + kTaps;
     const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
-    if (nt == 1) {
-        set_smem3(tcn2_small_conv_kernel<1, false>, smem);
-        tcn2_small_conv_kernel<1, false><<<grid_small(tcn2_small_conv_kernel<1, false>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
-    } else {
-        set_smem3(tcn2_small_conv_kernel<2, false>, smem);
-        tcn2_small_conv_kernel<2, false><<<grid_small(tcn2_small_conv_kernel<2, false>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
+#define T2S_FWD(VV)                                                                                  \
+    if (nt == 1) {                                                                                    \
+        set_smem3(tcn2_small_conv_kernel<1, false, VV>, smem);                                        \
+        tcn2_small_conv_kernel<1, false, VV><<<grid_small(tcn2_small_conv_kernel<1, false, VV>, smem, NM, Tout), \
+                                               kThr, smem, (cudaStream_t)s>>>(p);                    \
+    } else {                                                                                          \
+        set_smem3(tcn2_small_conv_kernel<2, false, VV>, smem);                                        \
+        tcn2_small_conv_kernel<2, false, VV><<<grid_small(tcn2_small_conv_kernel<2, false, VV>, smem, NM, Tout), \
+                                               kThr, smem, (cudaStream_t)s>>>(p);                    \
     }
+    T2S_DISPATCH_V(T2S_FWD)
+#undef T2S_FWD
     return finish_launch("tcn2_conv");
 }
 
@@ -343,26 +378,36 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
         SmallP p{dh2, nullptr, Weff, nullptr, dh1, dbd, NM, Tout, T, V, stride, inv16, inv_per};
         const int Q = kTT + 2 * kHalf;
         const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
-        if (nt == 1) {
-            set_smem3(tcn2_small_conv_kernel<1, true>, smem);
-            tcn2_small_conv_kernel<1, true><<<grid_small(tcn2_small_conv_kernel<1, true>, smem, NM, T), kThr, smem, (cudaStream_t)s>>>(p);
-        } else {
-            set_smem3(tcn2_small_conv_kernel<2, true>, smem);
-            tcn2_small_conv_kernel<2, true><<<grid_small(tcn2_small_conv_kernel<2, true>, smem, NM, T), kThr, smem, (cudaStream_t)s>>>(p);
-        }
+#define T2S_BWD(VV)                                                                                  \
+    if (nt == 1) {                                                                                    \
+        set_smem3(tcn2_small_conv_kernel<1, true, VV>, smem);                                         \
+        tcn2_small_conv_kernel<1, true, VV><<<grid_small(tcn2_small_conv_kernel<1, true, VV>, smem, NM, T), \
+                                              kThr, smem, (cudaStream_t)s>>>(p);                     \
+    } else {                                                                                          \
+        set_smem3(tcn2_small_conv_kernel<2, true, VV>, smem);                                         \
+        tcn2_small_conv_kernel<2, true, VV><<<grid_small(tcn2_small_conv_kernel<2, true, VV>, smem, NM, T), \
+                                              kThr, smem, (cudaStream_t)s>>>(p);                     \
+    }
+        T2S_DISPATCH_V(T2S_BWD)
+#undef T2S_BWD
         if (int e = finish_launch("tcn2_bwd_conv (data)")) return e;
     }
     {   // dWeff
         SmallP p{h1, dh2, Weff, nullptr, dWeff, nullptr, NM, T, Tout, V, stride, inv16, inv_per};
         const int Q = (kTT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)kTaps * bp * bp + (size_t)kTT * V * bp + (size_t)Q * V * bp);
-        if (nt == 1) {
-            set_smem3(tcn2_small_dw_kernel<1>, smem);
-            tcn2_small_dw_kernel<1><<<grid_small(tcn2_small_dw_kernel<1>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
-        } else {
-            set_smem3(tcn2_small_dw_kernel<2>, smem);
-            tcn2_small_dw_kernel<2><<<grid_small(tcn2_small_dw_kernel<2>, smem, NM, Tout), kThr, smem, (cudaStream_t)s>>>(p);
-        }
+#define T2S_DW(VV)                                                                                   \
+    if (nt == 1) {                                                                                    \
+        set_smem3(tcn2_small_dw_kernel<1, VV>, smem);                                                 \
+        tcn2_small_dw_kernel<1, VV><<<grid_small(tcn2_small_dw_kernel<1, VV>, smem, NM, Tout), kThr, smem, \
+                                      (cudaStream_t)s>>>(p);                                         \
+    } else {                                                                                          \
+        set_smem3(tcn2_small_dw_kernel<2, VV>, smem);                                                 \
+        tcn2_small_dw_kernel<2, VV><<<grid_small(tcn2_small_dw_kernel<2, VV>, smem, NM, Tout), kThr, smem, \
+                                      (cudaStream_t)s>>>(p);                                         \
+    }
+        T2S_DISPATCH_V(T2S_DW)
+#undef T2S_DW
     }
     return finish_launch("tcn2_bwd_conv (weights)");
 }

@@ -77,10 +77,17 @@ def main():
             for _ in range(3):
                 fn()
             torch.cuda.synchronize()
+            # the launches are replayed from a CUDA graph: the small kernels run for 10-30 us, less
+            # than a Python -> ctypes -> launch round trip, so eager timing would measure the host
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(args.iters):
+                    fn()
+            graph.replay()
+            torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            for _ in range(args.iters):
-                fn()
+            graph.replay()
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
