@@ -334,6 +334,14 @@ int istgcn_sgd_step(float* p, const float* g, float* buf, long long n, const flo
                     float momentum, float weight_decay, int nesterov, float grad_scale,
                     istgcn_stream_t s);
 
+/* ---- input pipeline on the device (feeder/feeder.py:70-85, feeder/tools.py:32-102) ---------
+ * in (N, C, Tin, V, M) -> out (N, C, Tout, V, M):  out[:, :, t] = in[:, :, t + shift[n]] (zeros outside
+ * [0, Tin): random_choose's crop, auto_pading's offset; shift may be NULL) and then random_move on
+ * channels 0, 1 of every output frame: (x, y) <- (m0*x - m1*y + m2, m1*x + m0*y + m3) with
+ * move[n][t] = {cos(a)*s, sin(a)*s, t_x, t_y} drawn on the host (may be NULL).                */
+int istgcn_feeder_augment(const float* in, const int* shift, const float* move, float* out, int N,
+                          int C, int Tin, int Tout, int V, int M, istgcn_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,9 +43,60 @@ __global__ void __launch_bounds__(256) sgd_step_kernel(float* __restrict__ p,
     }
 }
 
+// Training-time augmentation of the reference's feeder on the device (feeder/feeder.py:70-85 ->
+// feeder/tools.py:32-102): temporal window (random_choose / auto_pading: out frame t reads input
+// frame t + shift[n], zeros outside) followed by random_move (x, y of EVERY frame of the window,
+// padding included, rotated / scaled / translated by the per-frame matrix the host drew with the
+// reference's own random calls: move[n][t] = {cos(a)*s, sin(a)*s, t_x, t_y}).
+__global__ void feeder_augment_kernel(const float* __restrict__ in, const int* __restrict__ shift,
+                                      const float* __restrict__ move, float* __restrict__ out,
+                                      int N, int C, int Tin, int Tout, int VM) {
+    const long long total = (long long)N * Tout * VM;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int vm = (int)(i % VM);
+        const long long nt = i / VM;
+        const int t = (int)(nt % Tout), n = (int)(nt / Tout);
+        const int ts = t + (shift ? shift[n] : 0);
+        const bool ok = ts >= 0 && ts < Tin;
+        float x = 0.f, y = 0.f;
+        const float* src = in + ((long long)n * C * Tin + ts) * VM + vm;
+        float* dst = out + ((long long)n * C * Tout + t) * VM + vm;
+        if (ok) {
+            x = src[0];
+            if (C > 1) y = src[(long long)Tin * VM];
+        }
+        if (move && C > 1) {
+            const float4 m = *reinterpret_cast<const float4*>(move + ((long long)n * Tout + t) * 4);
+            const float nx = m.x * x - m.y * y + m.z, ny = m.y * x + m.x * y + m.w;
+            x = nx;
+            y = ny;
+        }
+        dst[0] = x;
+        if (C > 1) dst[(long long)Tout * VM] = y;
+        for (int c = 2; c < C; ++c) dst[(long long)c * Tout * VM] = ok ? src[(long long)c * Tin * VM] : 0.f;
+    }
+}
+
 }  // namespace istgcn
 
 using namespace istgcn;
+
+ISTGCN_API int istgcn_feeder_augment(const float* in, const int* shift, const float* move, float* out,
+                                     int N, int C, int Tin, int Tout, int V, int M,
+                                     istgcn_stream_t s) {
+    ISTGCN_REQUIRE(in && out, ISTGCN_E_ARG, "feeder_augment: null pointer");
+    ISTGCN_REQUIRE(N >= 0 && C >= 1 && Tin >= 1 && Tout >= 1 && V >= 1 && M >= 1, ISTGCN_E_SHAPE,
+                   "feeder_augment: bad shape");
+    ISTGCN_REQUIRE(move == nullptr || (uintptr_t)move % 16 == 0, ISTGCN_E_ARG, "feeder_augment: move must be 16-byte aligned");
+    const long long total = (long long)N * Tout * V * M;
+    if (total == 0) return 0;
+    long long blocks = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    feeder_augment_kernel<<<(int)blocks, 256, 0, (cudaStream_t)s>>>(in, shift, move, out, N, C, Tin, Tout, V * M);
+    return finish_launch("feeder_augment");
+}
 
 ISTGCN_API int istgcn_sgd_step(float* p, const float* g, float* buf, long long n, const float* lr,
                                float momentum, float weight_decay, int nesterov, float grad_scale,

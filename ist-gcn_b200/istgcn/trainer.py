@@ -151,17 +151,20 @@ class Trainer(object):
         return out
 
     # ------------------------------------------------------------------ epoch driver
-    def train_epoch(self, loader, epoch=0, step=None, device=None):
-        """One pass of recognition.py:185-310 over ``loader`` (yields (data, label)): step LR
-        schedule, pinned non-blocking H2D, one ``step`` per batch.  The loss is read back once per
-        epoch, not once per iteration (the reference's per-iteration ``.item()`` is a host sync).
-        Returns the mean loss."""
+    def train_epoch(self, loader, epoch=0, step=None, device=None, augment=None):
+        """One pass of recognition.py:185-310 over ``loader`` (yields host (data, label) batches):
+        step LR schedule, pinned double-buffered H2D on a copy stream (istgcn.pipeline), one ``step``
+        per batch.  The loss is read back once per epoch, not once per iteration (the reference's
+        per-iteration ``.item()`` is a host sync).  Returns the mean loss."""
         device = device or next(self.model.parameters()).device
         self.set_lr(self.base_lr * (0.1 ** sum(1 for s in (step or []) if epoch >= s)))
         total, count = None, 0
-        for data, label in loader:
-            data = data.float().to(device, non_blocking=True)
-            label = label.long().to(device, non_blocking=True)
+        if torch.device(device).type == 'cuda':
+            from . import pipeline
+            batches = pipeline.DevicePrefetcher(loader, device, augment)
+        else:
+            batches = ((d.float().to(device), l.long().to(device)) for d, l in loader)
+        for data, label in batches:
             loss = self.step(data, label).detach()
             total = loss.clone() if total is None else total + loss
             count += 1
