@@ -81,6 +81,15 @@ __device__ __forceinline__ void load_small_a(uint32_t (&a)[NT][4], const float* 
 template <int NT>
 __device__ __forceinline__ int small_ch(int t, int kk) { return NT == 1 ? 2 * t : 4 * t + 2 * kk; }
 
+// Labelling of the OUTPUT columns of the products whose result is a wide activation tile (u, da):
+// column g of n-tile nt is channel 16*(nt/2) + 4*(g/2) + 2*(nt%2) + g%2 of the 64-wide slice, so the
+// accumulators a thread holds for n-tiles 2jj and 2jj+1 (columns 2t, 2t+1 of each) are the four
+// CONSECUTIVE channels 16jj + 4t .. +3: one 16-byte store / load per row instead of two 8-byte ones
+// (half the L1 wavefronts -- the 8-byte form kept the LSU data pipe at 65 %).
+__device__ __forceinline__ int out_col(int nt, int g) {
+    return 16 * (nt >> 1) + 4 * (g >> 1) + 2 * (nt & 1) + (g & 1);
+}
+
 // A fragments with the contraction over ROWS: the transposed [16 rows][BP] tile, m = channel j (g,
 // g + 8), k = row (t, t + 4) of the 8-row half `ks`.  Rows >= rows read as zero.
 template <int NT>
@@ -219,52 +228,59 @@ __global__ void __launch_bounds__(kT2Threads, 2) tcn2_up_kernel(UpP p) {
     for (int i = tid; i < S * 8 * NT * 32; i += kT2Threads) {
         const int l = i & 31, q = i >> 5;
         const int kk = q % NT, nt = (q / NT) & 7, sl = q / (NT * 8);
-        const int j = small_ch<NT>(l & 3, kk), c = sl * 64 + nt * 8 + (l >> 2);
+        const int j = small_ch<NT>(l & 3, kk), c = sl * 64 + out_col(nt, l >> 2);
         s_w[i] = make_float2(tff(p.Wu[j * C + c]), tff(p.Wu[(j + 1) * C + c]));
     }
     for (int i = tid; i < C; i += kT2Threads) { s_bu[i] = p.bu[i]; s_sum[i] = 0.f; s_sq[i] = 0.f; }
     __syncthreads();
     const int slice = warp % S, tsub = warp / S, tpc = 8 / S;
-    float st[8][4];
+    float st[4][8];                              // per 16-channel chunk jj: sums [0..3], squares [4..7]
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+    for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) st[nt][i] = 0.f;
+        for (int i = 0; i < 8; ++i) st[jj][i] = 0.f;
     const long long ntiles = (p.rows + 15) >> 4;
     for (long long tile = (long long)blockIdx.x * tpc + tsub; tile < ntiles; tile += (long long)gridDim.x * tpc) {
         const long long r0 = tile * 16 + g, r1 = r0 + 8;
         const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
         uint32_t a[NT][4];
         load_small_a<NT>(a, p.h2, r0 * BP, r1 * BP, ok0, ok1, t);
-        float* u0 = p.u + r0 * C + slice * 64 + 2 * t;
-        float* u1 = p.u + r1 * C + slice * 64 + 2 * t;
+        float* u0 = p.u + r0 * C + slice * 64 + 4 * t;
+        float* u1 = p.u + r1 * C + slice * 64 + 4 * t;
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float2 bb = *reinterpret_cast<const float2*>(s_bu + slice * 64 + nt * 8 + 2 * t);
-            float acc[4] = {bb.x, bb.y, bb.x, bb.y};
+        for (int jj = 0; jj < 4; ++jj) {
+            // n-tiles 2jj, 2jj+1 under the out_col labelling: this thread's accumulators are the four
+            // consecutive channels 16jj + 4t .. +3 of rows g (v0) and g + 8 (v1)
+            const float4 bb = *reinterpret_cast<const float4*>(s_bu + slice * 64 + jj * 16 + 4 * t);
+            float lo[4] = {bb.x, bb.y, bb.x, bb.y}, hi[4] = {bb.z, bb.w, bb.z, bb.w};
 #pragma unroll
-            for (int kk = 0; kk < NT; ++kk) mma(acc, a[kk], s_w[((slice * 8 + nt) * NT + kk) * 32 + lane]);
-            if (ok0) *reinterpret_cast<float2*>(u0 + nt * 8) = make_float2(acc[0], acc[1]);
-            else acc[0] = acc[1] = 0.f;
-            if (ok1) *reinterpret_cast<float2*>(u1 + nt * 8) = make_float2(acc[2], acc[3]);
-            else acc[2] = acc[3] = 0.f;
-            st[nt][0] += acc[0] + acc[2];
-            st[nt][1] += acc[1] + acc[3];
-            st[nt][2] = fmaf(acc[0], acc[0], fmaf(acc[2], acc[2], st[nt][2]));
-            st[nt][3] = fmaf(acc[1], acc[1], fmaf(acc[3], acc[3], st[nt][3]));
+            for (int kk = 0; kk < NT; ++kk) {
+                mma(lo, a[kk], s_w[((slice * 8 + 2 * jj) * NT + kk) * 32 + lane]);
+                mma(hi, a[kk], s_w[((slice * 8 + 2 * jj + 1) * NT + kk) * 32 + lane]);
+            }
+            float v0[4] = {lo[0], lo[1], hi[0], hi[1]}, v1[4] = {lo[2], lo[3], hi[2], hi[3]};
+            if (ok0) st4(u0 + jj * 16, make_float4(v0[0], v0[1], v0[2], v0[3]));
+            if (ok1) st4(u1 + jj * 16, make_float4(v1[0], v1[1], v1[2], v1[3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                if (!ok0) v0[e] = 0.f;
+                if (!ok1) v1[e] = 0.f;
+                st[jj][e] += v0[e] + v1[e];
+                st[jj][4 + e] = fmaf(v0[e], v0[e], fmaf(v1[e], v1[e], st[jj][4 + e]));
+            }
         }
     }
     if (p.ssum) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
+        for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) st[nt][i] = group_sum_g(st[nt][i]);
-            if (g == 0) {
-                const int c = slice * 64 + nt * 8 + 2 * t;
-                atomicAdd(&s_sum[c], st[nt][0]); atomicAdd(&s_sum[c + 1], st[nt][1]);
-                atomicAdd(&s_sq[c], st[nt][2]); atomicAdd(&s_sq[c + 1], st[nt][3]);
+            for (int e = 0; e < 4; ++e) {
+                const float sv = group_sum_g(st[jj][e]), qv = group_sum_g(st[jj][4 + e]);
+                if (g == 0) {
+                    atomicAdd(&s_sum[slice * 64 + jj * 16 + 4 * t + e], sv);
+                    atomicAdd(&s_sq[slice * 64 + jj * 16 + 4 * t + e], qv);
+                }
             }
-        }
         __syncthreads();
         for (int c = tid; c < C; c += kT2Threads) {
             atomicAdd(&p.ssum[c], (double)s_sum[c]);
@@ -498,56 +514,65 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_down_kernel(Bw
     for (int i = tid; i < S * 8 * NT * 32; i += NTHR) {
         const int l = i & 31, q = i >> 5;
         const int kk = q % NT, nt = (q / NT) & 7, sl = q / (NT * 8);
-        const int j = small_ch<NT>(l & 3, kk), c = sl * 64 + nt * 8 + (l >> 2);
+        const int j = small_ch<NT>(l & 3, kk), c = sl * 64 + out_col(nt, l >> 2);
         s_w[i] = make_float2(tff(p.Wd[c * BP + j]), tff(p.Wd[c * BP + j + 1]));
     }
     for (int i = tid; i < BP * C + 2 * C; i += NTHR) s_dW[i] = 0.f;
     __syncthreads();
     const int slice = warp % S, tsub = warp / S, tpc = W / S;
     float* tile_s = s_tile + warp * 16 * 64;
-    float accW[8][4], st[8][4];
+    float accW[8][4], st[4][8];                  // st: per 16-channel chunk, sum g1 [0..3], sum g1*zhat [4..7]
 #pragma unroll
     for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) accW[a][b] = st[a][b] = 0.f;
+        for (int b = 0; b < 4; ++b) accW[a][b] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) st[a][b] = 0.f;
     const long long ntiles = (p.rows + 15) >> 4;
     for (long long tile = (long long)blockIdx.x * tpc + tsub; tile < ntiles; tile += (long long)gridDim.x * tpc) {
         const long long r0 = tile * 16 + g, r1 = r0 + 8;
         const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
-        const long long o0 = (ok0 ? r0 : p.rows - 1) * C + slice * 64 + 2 * t;
-        const long long o1 = (ok1 ? r1 : p.rows - 1) * C + slice * 64 + 2 * t;
-        float2 z0[8], z1[8];
+        const long long o0 = (ok0 ? r0 : p.rows - 1) * C + slice * 64 + 4 * t;
+        const long long o1 = (ok1 ? r1 : p.rows - 1) * C + slice * 64 + 4 * t;
+        float4 z0[4], z1[4];
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { z0[nt] = lds2(p.z + o0 + nt * 8); z1[nt] = lds2(p.z + o1 + nt * 8); }
+        for (int jj = 0; jj < 4; ++jj) { z0[jj] = lds4(p.z + o0 + jj * 16); z1[jj] = lds4(p.z + o1 + jj * 16); }
         uint32_t a[NT][4];
         load_small_a<NT>(a, p.dh1, r0 * BP, r1 * BP, ok0, ok1, t);
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int jj = 0; jj < 4; ++jj) {
+            float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int kk = 0; kk < NT; ++kk) mma(acc, a[kk], s_w[((slice * 8 + nt) * NT + kk) * 32 + lane]);
-            const int c = slice * 64 + nt * 8 + 2 * t;
-            const float2 mu = *reinterpret_cast<const float2*>(s_c + c);
-            const float2 sc = *reinterpret_cast<const float2*>(s_c + C + c);
-            const float2 be = *reinterpret_cast<const float2*>(s_c + 2 * C + c);
-            const float2 rs = *reinterpret_cast<const float2*>(s_c + 3 * C + c);
-            float a00 = fmaxf(bn_apply(z0[nt].x, mu.x, sc.x, be.x), 0.f);
-            float a01 = fmaxf(bn_apply(z0[nt].y, mu.y, sc.y, be.y), 0.f);
-            float a10 = fmaxf(bn_apply(z1[nt].x, mu.x, sc.x, be.x), 0.f);
-            float a11 = fmaxf(bn_apply(z1[nt].y, mu.y, sc.y, be.y), 0.f);
-            if (!ok0) a00 = a01 = 0.f;
-            if (!ok1) a10 = a11 = 0.f;
-            const float g00 = a00 > 0.f ? acc[0] : 0.f, g01 = a01 > 0.f ? acc[1] : 0.f;
-            const float g10 = a10 > 0.f ? acc[2] : 0.f, g11 = a11 > 0.f ? acc[3] : 0.f;
-            if (ok0) *reinterpret_cast<float2*>(p.g1 + r0 * C + slice * 64 + nt * 8 + 2 * t) = make_float2(g00, g01);
-            if (ok1) *reinterpret_cast<float2*>(p.g1 + r1 * C + slice * 64 + nt * 8 + 2 * t) = make_float2(g10, g11);
-            st[nt][0] += g00 + g10;
-            st[nt][1] += g01 + g11;
-            st[nt][2] += (g00 * (z0[nt].x - mu.x) + g10 * (z1[nt].x - mu.x)) * rs.x;
-            st[nt][3] += (g01 * (z0[nt].y - mu.y) + g11 * (z1[nt].y - mu.y)) * rs.y;
-            const int pc = (nt * 8 + 2 * t) ^ swz(g);
-            *reinterpret_cast<float2*>(tile_s + g * 64 + pc) = make_float2(a00, a01);
-            *reinterpret_cast<float2*>(tile_s + (g + 8) * 64 + pc) = make_float2(a10, a11);
+            for (int kk = 0; kk < NT; ++kk) {
+                mma(lo, a[kk], s_w[((slice * 8 + 2 * jj) * NT + kk) * 32 + lane]);
+                mma(hi, a[kk], s_w[((slice * 8 + 2 * jj + 1) * NT + kk) * 32 + lane]);
+            }
+            const float d0[4] = {lo[0], lo[1], hi[0], hi[1]}, d1[4] = {lo[2], lo[3], hi[2], hi[3]};
+            const int c = slice * 64 + jj * 16 + 4 * t;
+            const float4 mu = *reinterpret_cast<const float4*>(s_c + c);
+            const float4 sc = *reinterpret_cast<const float4*>(s_c + C + c);
+            const float4 be = *reinterpret_cast<const float4*>(s_c + 2 * C + c);
+            const float4 rs = *reinterpret_cast<const float4*>(s_c + 3 * C + c);
+            const float zz0[4] = {z0[jj].x, z0[jj].y, z0[jj].z, z0[jj].w}, zz1[4] = {z1[jj].x, z1[jj].y, z1[jj].z, z1[jj].w};
+            const float mua[4] = {mu.x, mu.y, mu.z, mu.w}, sca[4] = {sc.x, sc.y, sc.z, sc.w};
+            const float bea[4] = {be.x, be.y, be.z, be.w}, rsa[4] = {rs.x, rs.y, rs.z, rs.w};
+            float a0[4], a1[4], g0[4], g1v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                a0[e] = ok0 ? fmaxf(bn_apply(zz0[e], mua[e], sca[e], bea[e]), 0.f) : 0.f;
+                a1[e] = ok1 ? fmaxf(bn_apply(zz1[e], mua[e], sca[e], bea[e]), 0.f) : 0.f;
+                g0[e] = a0[e] > 0.f ? d0[e] : 0.f;
+                g1v[e] = a1[e] > 0.f ? d1[e] : 0.f;
+                st[jj][e] += g0[e] + g1v[e];
+                st[jj][4 + e] += (g0[e] * (zz0[e] - mua[e]) + g1v[e] * (zz1[e] - mua[e])) * rsa[e];
+            }
+            if (ok0) st4(p.g1 + r0 * C + c, make_float4(g0[0], g0[1], g0[2], g0[3]));
+            if (ok1) st4(p.g1 + r1 * C + c, make_float4(g1v[0], g1v[1], g1v[2], g1v[3]));
+            const int pc = (jj * 16 + 4 * t) ^ swz(g);
+            st4(tile_s + g * 64 + pc, make_float4(a0[0], a0[1], a0[2], a0[3]));
+            st4(tile_s + (g + 8) * 64 + pc, make_float4(a1[0], a1[1], a1[2], a1[3]));
         }
         __syncwarp();
         // dWd[c][j] += a[rows][c] dh1[rows][j]   (m = j, n = c, k = rows)
@@ -560,19 +585,22 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_down_kernel(Bw
         __syncwarp();
     }
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
+    for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int j = g + 8 * (i >> 1), c = slice * 64 + nt * 8 + 2 * t + (i & 1);
             if (j < BP) atomicAdd(&s_dW[j * C + c], accW[nt][i]);
-            st[nt][i] = group_sum_g(st[nt][i]);
         }
-        if (g == 0) {
-            const int c = slice * 64 + nt * 8 + 2 * t;
-            atomicAdd(&s_sg[c], st[nt][0]); atomicAdd(&s_sg[c + 1], st[nt][1]);
-            atomicAdd(&s_sgx[c], st[nt][2]); atomicAdd(&s_sgx[c + 1], st[nt][3]);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float sv = group_sum_g(st[jj][e]), xv = group_sum_g(st[jj][4 + e]);
+            if (g == 0) {
+                atomicAdd(&s_sg[slice * 64 + jj * 16 + 4 * t + e], sv);
+                atomicAdd(&s_sgx[slice * 64 + jj * 16 + 4 * t + e], xv);
+            }
         }
-    }
     __syncthreads();
     for (int i = tid; i < BP * C; i += NTHR) {
         const int j = i / C, c = i - j * C;
