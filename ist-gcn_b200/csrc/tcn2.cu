@@ -57,7 +57,6 @@ __device__ __forceinline__ int swz(int row) { return ((row & 1) << 4) | (((row >
 __device__ __forceinline__ float2 ldg2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 lds4(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
-__device__ __forceinline__ float2 lds2(const float* p) { return __ldcs(reinterpret_cast<const float2*>(p)); }
 
 // A fragments of a 16-row tile of a [rows][BP] matrix (BP = 8 * NT), rows g / g + 8 of the tile,
 // under the channel re-labelling: NT = 1: one k-step, slots (t, t+4) = channels (2t, 2t+1);
@@ -342,6 +341,21 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
     const long long ntiles = (p.rows + 15) >> 4;
     const long long stride_t = (long long)gridDim.x * tpc;
     const long long iters = (ntiles - (long long)blockIdx.x * tpc + stride_t - 1) / stride_t;   // uniform per CTA
+    // Register prefetch: the (go, u) rows of the warp's NEXT tile are requested as soon as the
+    // current tile's du is formed -- before its weight-gradient MMAs and the cross-slice hand-over --
+    // so the HBM latency of tile i+1 hides behind the second half of tile i.
+    float4 g0[4], g1[4], u0[4], u1[4];
+    auto issue_loads = [&](long long tl) {
+        const long long r0 = tl * 16 + g, r1 = r0 + 8;
+        const long long o0 = (r0 < p.rows ? r0 : p.rows - 1) * C + slice * 64 + 4 * t;
+        const long long o1 = (r1 < p.rows ? r1 : p.rows - 1) * C + slice * 64 + 4 * t;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            g0[jj] = lds4(p.go + o0 + jj * 16); u0[jj] = lds4(p.u + o0 + jj * 16);
+            g1[jj] = lds4(p.go + o1 + jj * 16); u1[jj] = lds4(p.u + o1 + jj * 16);
+        }
+    };
+    if ((long long)blockIdx.x * tpc + tsub < ntiles) issue_loads((long long)blockIdx.x * tpc + tsub);
     for (long long it = 0; it < iters; ++it) {
         const long long tile = (long long)blockIdx.x * tpc + it * stride_t + tsub;
         const bool active = tile < ntiles;
@@ -355,12 +369,6 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
             const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
             const long long o0 = (ok0 ? r0 : p.rows - 1) * C + slice * 64 + 4 * t;
             const long long o1 = (ok1 ? r1 : p.rows - 1) * C + slice * 64 + 4 * t;
-            float4 g0[4], g1[4], u0[4], u1[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                g0[jj] = lds4(p.go + o0 + jj * 16); u0[jj] = lds4(p.u + o0 + jj * 16);
-                g1[jj] = lds4(p.go + o1 + jj * 16); u1[jj] = lds4(p.u + o1 + jj * 16);
-            }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int c = slice * 64 + jj * 16 + 4 * t;
@@ -408,6 +416,7 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
                 st4(tile_s + (g + 8) * 64 + pc, make_float4(db[0], db[1], db[2], db[3]));
             }
             __syncwarp();
+            if (tile + stride_t < ntiles) issue_loads(tile + stride_t);
             // dWu[j][c] += h2[rows][j] du[rows][c]
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
@@ -531,16 +540,23 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_down_kernel(Bw
 #pragma unroll
         for (int b = 0; b < 8; ++b) st[a][b] = 0.f;
     const long long ntiles = (p.rows + 15) >> 4;
-    for (long long tile = (long long)blockIdx.x * tpc + tsub; tile < ntiles; tile += (long long)gridDim.x * tpc) {
-        const long long r0 = tile * 16 + g, r1 = r0 + 8;
+    const long long stride_t = (long long)gridDim.x * tpc;
+    // register prefetch of the next tile's z rows and dh1 fragments (see tcn2_bwd_up_kernel)
+    float4 z0[4], z1[4];
+    uint32_t a[NT][4];
+    auto issue_loads = [&](long long tl) {
+        const long long r0 = tl * 16 + g, r1 = r0 + 8;
         const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
         const long long o0 = (ok0 ? r0 : p.rows - 1) * C + slice * 64 + 4 * t;
         const long long o1 = (ok1 ? r1 : p.rows - 1) * C + slice * 64 + 4 * t;
-        float4 z0[4], z1[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) { z0[jj] = lds4(p.z + o0 + jj * 16); z1[jj] = lds4(p.z + o1 + jj * 16); }
-        uint32_t a[NT][4];
         load_small_a<NT>(a, p.dh1, r0 * BP, r1 * BP, ok0, ok1, t);
+    };
+    if ((long long)blockIdx.x * tpc + tsub < ntiles) issue_loads((long long)blockIdx.x * tpc + tsub);
+    for (long long tile = (long long)blockIdx.x * tpc + tsub; tile < ntiles; tile += stride_t) {
+        const long long r0 = tile * 16 + g, r1 = r0 + 8;
+        const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             float lo[4] = {0.f, 0.f, 0.f, 0.f}, hi[4] = {0.f, 0.f, 0.f, 0.f};
@@ -575,6 +591,7 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_down_kernel(Bw
             st4(tile_s + (g + 8) * 64 + pc, make_float4(a1[0], a1[1], a1[2], a1[3]));
         }
         __syncwarp();
+        if (tile + stride_t < ntiles) issue_loads(tile + stride_t);
         // dWd[c][j] += a[rows][c] dh1[rows][j]   (m = j, n = c, k = rows)
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
