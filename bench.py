@@ -148,6 +148,24 @@ def algorithmic_bytes(kernel, batch, shape):
         elif kernel == 'gcn_bwd_w':
             if res == 2:
                 per_launch.append(4 * r_out * (2 * cout + cin))
+        elif kernel == 'tcn2_down':      # reads z, writes h1
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * r_in * (cout + bp))
+        elif kernel == 'tcn2_conv':      # reads h1, writes h2
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * (r_in + r_out) * bp)
+        elif kernel == 'tcn2_up':        # reads h2, writes u
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * r_out * (cout + bp))
+        elif kernel == 'tcn2_bwd_up':    # reads go, u, h2, writes dh2
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * r_out * (2 * cout + 2 * bp))
+        elif kernel == 'tcn2_bwd_conv':  # reads dh2, h1 (twice: data + weight kernel), writes dh1
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * (2 * r_in + 2 * r_out) * bp)
+        elif kernel == 'tcn2_bwd_down':  # reads z, dh1, writes g1
+            bp = 8 if int(cout ** 0.5) <= 8 else 16
+            per_launch.append(4 * r_in * (2 * cout + 2 * bp))
         elif kernel == 'tcn_fwd':        # reads z, writes u (+ h1, h2 write, h1 read)
             bp = 8 if int(cout ** 0.5) <= 8 else 16
             per_launch.append(4 * (r_in * (cout + 2 * bp) + r_out * (cout + bp)))
@@ -279,6 +297,19 @@ def run_istgcn(args):
                     avg_launch_ms=per_kernel[top] / n_launch)
     shares = {k: round(v / prof_steps / ms_per_step_, 4)
               for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1])}
+    # every entry point with a byte model: device time per step, algorithmic GB/s, fraction of peak
+    table = []
+    if args.arch == 'ist_gcn':
+        for k, v in sorted(per_kernel.items(), key=lambda kv: -kv[1]):
+            ab = algorithmic_bytes(k, B, w['shape'])
+            if k == 'gcn_tc':
+                ab = ab + algorithmic_bytes('gcn_tc_bwd', B, w['shape'])
+            if not ab:
+                continue
+            gbs = sum(ab) * prof_steps / (v / 1e3) / 1e9
+            table.append({'entry_point': k, 'ms_per_step': round(v / prof_steps, 4), 'launches_per_step': len(ab),
+                          'algorithmic_GB_per_step': round(sum(ab) / 1e9, 3), 'GBps': round(gbs, 1),
+                          'frac_of_hbm_peak': round(gbs / peak, 3)})
 
     # end to end through the public API from pinned HOST buffers: the input pipeline of the trainer
     # (istgcn.pipeline.DevicePrefetcher: copy stream, two slots -- the H2D copy of step i+1 overlaps
@@ -344,7 +375,8 @@ def run_istgcn(args):
         'e2e': {'value': e2e_value, 'unit': 'clips/s',
                 'h2d_bytes_per_step': h2d_per_step, 'd2h_bytes_per_step': 4,
                 'pipeline': 'pinned host batches -> copy stream (double buffer) -> Trainer.step -> loss.item()'},
-        'roofline': roof, 'kernel_shares': shares, 'fwd_clips_per_s': fwd, 'loss': final_loss,
+        'roofline': roof, 'kernel_shares': shares, 'per_entry_point': table, 'fwd_clips_per_s': fwd,
+        'loss': final_loss,
     }
     if replicas_ok is not None:
         line['replicas_equal_after_run'] = replicas_ok

@@ -341,21 +341,6 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
     const long long ntiles = (p.rows + 15) >> 4;
     const long long stride_t = (long long)gridDim.x * tpc;
     const long long iters = (ntiles - (long long)blockIdx.x * tpc + stride_t - 1) / stride_t;   // uniform per CTA
-    // Register prefetch: the (go, u) rows of the warp's NEXT tile are requested as soon as the
-    // current tile's du is formed -- before its weight-gradient MMAs and the cross-slice hand-over --
-    // so the HBM latency of tile i+1 hides behind the second half of tile i.
-    float4 g0[4], g1[4], u0[4], u1[4];
-    auto issue_loads = [&](long long tl) {
-        const long long r0 = tl * 16 + g, r1 = r0 + 8;
-        const long long o0 = (r0 < p.rows ? r0 : p.rows - 1) * C + slice * 64 + 4 * t;
-        const long long o1 = (r1 < p.rows ? r1 : p.rows - 1) * C + slice * 64 + 4 * t;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            g0[jj] = lds4(p.go + o0 + jj * 16); u0[jj] = lds4(p.u + o0 + jj * 16);
-            g1[jj] = lds4(p.go + o1 + jj * 16); u1[jj] = lds4(p.u + o1 + jj * 16);
-        }
-    };
-    if ((long long)blockIdx.x * tpc + tsub < ntiles) issue_loads((long long)blockIdx.x * tpc + tsub);
     for (long long it = 0; it < iters; ++it) {
         const long long tile = (long long)blockIdx.x * tpc + it * stride_t + tsub;
         const bool active = tile < ntiles;
@@ -369,6 +354,14 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
             const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
             const long long o0 = (ok0 ? r0 : p.rows - 1) * C + slice * 64 + 4 * t;
             const long long o1 = (ok1 ? r1 : p.rows - 1) * C + slice * 64 + 4 * t;
+            // (a register prefetch of the next tile here, as in tcn2_bwd_down_kernel, measured 10 % SLOWER:
+            // 64 more live registers during the weight-gradient MMAs at the 168-register cap)
+            float4 g0[4], g1[4], u0[4], u1[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                g0[jj] = lds4(p.go + o0 + jj * 16); u0[jj] = lds4(p.u + o0 + jj * 16);
+                g1[jj] = lds4(p.go + o1 + jj * 16); u1[jj] = lds4(p.u + o1 + jj * 16);
+            }
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int c = slice * 64 + jj * 16 + 4 * t;
@@ -416,7 +409,6 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
                 st4(tile_s + (g + 8) * 64 + pc, make_float4(db[0], db[1], db[2], db[3]));
             }
             __syncwarp();
-            if (tile + stride_t < ntiles) issue_loads(tile + stride_t);
             // dWu[j][c] += h2[rows][j] du[rows][c]
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
