@@ -423,11 +423,15 @@ def _dp_worker(rank, world, port, use_graph, out_path):
     for p in (os.path.join(root, 'ist-gcn_b200'), root):
         if p not in sys.path:
             sys.path.insert(0, p)
+    import datetime
+    import faulthandler
     import torch.distributed as dist
+    faulthandler.dump_traceback_later(100, exit=True)            # a hung collective must not eat the GPU budget
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank),
+                            timeout=datetime.timedelta(seconds=90))
     import istgcn
     from istgcn import dp, trainer
     istgcn.set_math('3xtf32')
@@ -457,6 +461,7 @@ def _dp_worker(rank, world, port, use_graph, out_path):
         torch.save({'grads': grads, 'losses': losses, 'equal': equal,
                     'params': {n: prm.detach().cpu() for n, prm in model.named_parameters()}}, out_path)
     dist.destroy_process_group()
+    faulthandler.cancel_dump_traceback_later()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
