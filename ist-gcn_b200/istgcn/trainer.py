@@ -41,14 +41,17 @@ class Trainer(object):
     """model + SGD(nesterov) + gradient buckets; ``step(x, label)`` is one iteration of
     recognition.py:249-298 (forward, loss, zero_grad, backward, optimizer step).
 
-    ``use_graph=True`` captures the WHOLE iteration -- forward, backward, the bucket all-reduces
-    (launched from the gradient hooks on NCCL's stream, so they overlap the rest of the backward
-    pass inside the graph too) and the optimiser kernel -- in one CUDA graph per input shape after
-    two eager warm-up steps at that shape, and replays it afterwards: a step is ~200 kernels plus
-    the parameter regrouping, which is launch-bound from Python at B200 speeds.  The learning
-    rate is read from device memory by the optimiser kernel, so the step schedule needs no
-    re-capture.  ``ISTGCN_GRAPH_COLLECTIVES=0`` keeps the collectives and the optimiser outside
-    the graph (replay forward + backward, then reduce and step eagerly)."""
+    ``use_graph=True`` captures the iteration in one CUDA graph per input shape after two eager
+    warm-up steps at that shape and replays it afterwards: a step is ~200 kernels plus the
+    parameter regrouping, which is launch-bound from Python at B200 speeds.  The learning rate is
+    read from device memory by the optimiser kernel, so the step schedule needs no re-capture.
+    One rank: the graph holds forward, backward and the optimiser kernel.  Several ranks: the
+    graph holds forward + backward; the bucket all-reduces (4.4 MB, latency-bound) and the
+    optimiser kernel run right after the replay.  ``ISTGCN_GRAPH_COLLECTIVES=1`` captures the
+    collectives as well (launched from the gradient hooks on NCCL's stream, overlapping the rest
+    of the backward pass inside the graph); a graph that holds NCCL kernels must be destroyed
+    BEFORE the process group -- call ``close()`` -- or ``destroy_process_group`` blocks forever
+    (observed on this pool, torch 2.11 / NCCL 2.28.9)."""
 
     def __init__(self, model, base_lr=0.1, weight_decay=1e-4, nesterov=True, momentum=0.9,
                  bucket_bytes=2 << 20, group=None, use_graph=False):
@@ -61,7 +64,7 @@ class Trainer(object):
         self.use_graph = use_graph
         self._graphs = {}           # (x.shape, label.shape) -> (graph, static x, static label, loss)
         self._eager_seen = {}
-        self.graph_collectives = os.environ.get('ISTGCN_GRAPH_COLLECTIVES', '1') != '0'
+        self.graph_collectives = os.environ.get('ISTGCN_GRAPH_COLLECTIVES', '0') == '1'
 
     # one iteration; ``with_optimizer`` False leaves the summed gradients in the buckets
     def _iteration(self, x, label, with_optimizer=True):
@@ -85,6 +88,19 @@ class Trainer(object):
     def invalidate_graph(self):
         """Drop every captured graph (e.g. after the model's structure or mode flags changed)."""
         self._graphs = {}
+
+    def close(self):
+        """Release the captured graphs (required before ``destroy_process_group`` when they hold
+        NCCL collectives) and the gradient hooks."""
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        self._graphs = {}
+        self._eval_graph = None
+        self.buckets.remove()
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
 
     def set_lr(self, lr):
         if hasattr(self.optimizer, 'set_lr'):

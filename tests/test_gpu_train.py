@@ -418,6 +418,8 @@ def _free_port():
 
 
 def _dp_worker(rank, world, port, use_graph, out_path):
+    os.environ['ISTGCN_GRAPH_COLLECTIVES'] = '1' if use_graph == 'collectives' else '0'
+    use_graph = bool(use_graph)
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (os.path.join(root, 'ist-gcn_b200'), root):
@@ -457,6 +459,7 @@ def _dp_worker(rank, world, port, use_graph, out_path):
     if use_graph:
         assert len(tr._graphs) == 1
     equal = dp.replicas_equal(model)
+    tr.close()                                                  # graphs with NCCL kernels go before the group
     if rank == 0:
         torch.save({'grads': grads, 'losses': losses, 'equal': equal,
                     'params': {n: prm.detach().cpu() for n, prm in model.named_parameters()}}, out_path)
@@ -468,12 +471,13 @@ def _dp_worker(rank, world, port, use_graph, out_path):
 def test_data_parallel_two_ranks_nccl(tmp_path):
     """Two NCCL ranks on the real net.ist_gcn: (1) the averaged gradient equals the mean of the
     per-shard oracle gradients (per-rank BatchNorm); (2) replicas stay
-    bit-equal over five steps in eager AND CUDA-graph mode (the graph holds the all-reduces);
-    (3) both modes end at the same parameters."""
+    bit-equal over five steps in eager mode, in CUDA-graph mode (graph = forward + backward, the
+    all-reduces follow the replay) and with the all-reduces captured inside the graph
+    (ISTGCN_GRAPH_COLLECTIVES=1); (3) all modes end at the same parameters."""
     import torch.multiprocessing as mp
     res = {}
-    for use_graph in (False, True):
-        out = str(tmp_path / ('dp_%d.pt' % use_graph))
+    for use_graph in (False, True, 'collectives'):
+        out = str(tmp_path / ('dp_%s.pt' % use_graph))
         mp.spawn(_dp_worker, args=(2, _free_port(), use_graph, out), nprocs=2, join=True)
         res[use_graph] = torch.load(out)
         assert res[use_graph]['equal'], 'replicas diverged (graph=%s)' % use_graph
@@ -492,7 +496,8 @@ def test_data_parallel_two_ranks_nccl(tmp_path):
     ref = torch.cat([g.cpu().reshape(-1) for g in acc])
     assert rel_l2(mine, ref) < 2e-2, rel_l2(mine, ref)
     pe = torch.cat([v.double().reshape(-1) for v in res[False]['params'].values()])
-    pg = torch.cat([v.double().reshape(-1) for v in res[True]['params'].values()])
-    assert rel_l2(pg, pe) < 1e-3
-    # (five steps at lr 0.05 amplify the atomics-order noise between the two runs)
-    assert max(abs(a - b) / abs(a) for a, b in zip(res[False]['losses'], res[True]['losses'])) < 5e-3
+    for mode in (True, 'collectives'):
+        pg = torch.cat([v.double().reshape(-1) for v in res[mode]['params'].values()])
+        assert rel_l2(pg, pe) < 1e-3, mode
+        # (five steps at lr 0.05 amplify the atomics-order noise between the runs)
+        assert max(abs(a - b) / abs(a) for a, b in zip(res[False]['losses'], res[mode]['losses'])) < 5e-3, mode
