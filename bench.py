@@ -286,7 +286,7 @@ def run_istgcn(args):
     roof = {'kernel': top, 'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
             'launches': n_launch, 'share_of_step': per_kernel[top] / prof_steps / ms_per_step_,
             'traffic': None, 'timed_in': 'eager pass of %d steps (%.1f ms/step)' % (prof_steps, eager_ms / prof_steps)}
-    tpath = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+    tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.isfile(tpath) and args.arch == 'ist_gcn':
         with open(tpath) as f:          # DRAM bytes per launch from the committed ncu capture
             tr_rec = json.load(f).get(top)

@@ -334,6 +334,36 @@ int istgcn_sgd_step(float* p, const float* g, float* buf, long long n, const flo
                     float momentum, float weight_decay, int nesterov, float grad_scale,
                     istgcn_stream_t s);
 
+/* ---- parameter regrouping of one IST-GCN block, one kernel each way ------------------------
+ * reference-layout parameters (tgcn.py:51-58 / inceptionv2_gcn.py:22-29 conv weight [K*Cout][Cin] + bias,
+ * A / A2 / A3 buffers and edge_importance* [K][V][V] (st_gcn_msgcn.py:112-117; A2 = A3 = NULL: single
+ * adjacency; imp_i = NULL: importance 1), conv_1x1_start [b][C], tcn_1/2/3 [b][b][3|9|15] with
+ * mstcn_importance[3], conv_1x1_end [C][b] (st_gcn_mstcn_1x1.py:190-224), residual conv [Cout][Cin])
+ * -> the kernel operands documented above: vals[nnz], colsum[K][V], Wc[K*Cin][Cout], biasterm[V][Cout],
+ * Wd[C][bp], bd[bp], Weff[15][bp][bp], beff[bp], Wu[bp][C], Wr[Cin][Cout], btr[V][Cout].
+ * flat_idx[nnz] (index of every pattern entry in the [K][V][V] stack), dst_ptr / dst_id as above.
+ * bwd: gradients of those operands -> gradients of the reference-layout parameters (written, not
+ * accumulated); inv_idx[K*V*V] = id of the pattern entry or -1, id_kw[nnz] = k*V + w of entry id.    */
+int istgcn_block_prep_fwd(const float* W, const float* bias, const float* A1, const float* imp1,
+                          const float* A2, const float* imp2, const float* A3, const float* imp3,
+                          const long long* flat_idx, const int* dst_ptr, const int* dst_id, int nnz,
+                          float* vals, float* colsum, float* Wc, float* biasterm, const float* Ws,
+                          const float* bs, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const float* W3, const float* b3, const float* We, const float* m_imp, float* Wd,
+                          float* bd, float* Weff, float* beff, float* Wu, const float* Wres, const float* bres,
+                          float* Wr, float* btr, int K, int V, int Cin, int Cout, int b, int bp,
+                          istgcn_stream_t s);
+int istgcn_block_prep_bwd(const float* dvals, const float* dWc, const float* dbt, const float* dWd,
+                          const float* dbd, const float* dWeff, const float* dbeff, const float* dWu,
+                          const float* dWr, const float* dbtr, const float* bias, const float* colsum,
+                          const float* A1, const float* A2, const float* A3, const int* inv_idx,
+                          const int* id_kw, const float* W1, const float* b1, const float* W2, const float* b2,
+                          const float* W3, const float* b3, const float* m_imp, float* dW, float* dbias,
+                          float* dimp1, float* dimp2, float* dimp3, float* dWs, float* dbs, float* dW1,
+                          float* db1, float* dW2, float* db2, float* dW3, float* db3, float* dWe, float* dm_imp,
+                          float* dWres, float* dbres, int K, int V, int Cin, int Cout, int b, int bp,
+                          istgcn_stream_t s);
+
 /* ---- input pipeline on the device (feeder/feeder.py:70-85, feeder/tools.py:32-102) ---------
  * in (N, C, Tin, V, M) -> out (N, C, Tout, V, M):  out[:, :, t] = in[:, :, t + shift[n]] (zeros outside
  * [0, Tin): random_choose's crop, auto_pading's offset; shift may be NULL) and then random_move on

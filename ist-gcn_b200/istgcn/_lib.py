@@ -25,7 +25,7 @@ SYMBOLS = (
     'istgcn_tconv_dw_tc',
     'istgcn_block_tail_fwd', 'istgcn_block_tail_bwd', 'istgcn_dropout_mask',
     'istgcn_pool_fwd', 'istgcn_pool_bwd',
-    'istgcn_sgd_step', 'istgcn_feeder_augment',
+    'istgcn_sgd_step', 'istgcn_feeder_augment', 'istgcn_block_prep_fwd', 'istgcn_block_prep_bwd',
 )
 
 

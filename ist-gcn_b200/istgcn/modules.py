@@ -92,6 +92,77 @@ def bottleneck_tcn_operands(conv_start, tcn_1, tcn_2, tcn_3, conv_end, m_imp):
     return wd, bd, weff, beff, wu, conv_end.bias
 
 
+class BlockPrep(torch.autograd.Function):
+    """graph_conv_operands + bottleneck_tcn_operands (+ the residual conv regrouping) of one block as
+    ONE kernel forward and ONE backward (istgcn_block_prep_fwd / _bwd, csrc/train.cu) instead of
+    ~50 tiny ATen launches each way.  Inputs are the reference-layout parameters themselves."""
+
+    @staticmethod
+    def forward(ctx, W, bias, imp1, imp2, imp3, Ws, bs, W1, b1, W2, b2, W3, b3, We, m_imp, Wres, bres,
+                bufs, pattern, dims):
+        from ._lib import call
+        K, V, Cin, Cout, b, bp = dims
+        dev = W.device
+        A1, A2, A3 = bufs
+        new = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.float32)          # noqa: E731
+        vals, colsum, Wc, biasterm = new(pattern.nnz), new(K, V), new(K * Cin, Cout), new(V, Cout)
+        Wd, bd, Weff, beff, Wu = new(Cout, bp), new(bp), new(15, bp, bp), new(bp), new(bp, Cout)
+        Wr = btr = None
+        if Wres is not None:
+            Wr, btr = new(Cin, Cout), new(V, Cout)
+        c = lambda t: None if t is None else t.contiguous()                           # noqa: E731
+        call('block_prep_fwd', c(W), c(bias), A1, c(imp1), A2, c(imp2), A3, c(imp3), pattern.flat_idx,
+             pattern.dst_ptr, pattern.dst_id, pattern.nnz, vals, colsum, Wc, biasterm, c(Ws), c(bs), c(W1),
+             c(b1), c(W2), c(b2), c(W3), c(b3), c(We), c(m_imp), Wd, bd, Weff, beff, Wu, c(Wres), c(bres), Wr,
+             btr, K, V, Cin, Cout, b, bp)
+        ctx.dims, ctx.bufs, ctx.pattern = dims, bufs, pattern
+        ctx.has = (bias is not None, imp1 is not None, imp2 is not None, imp3 is not None, Wres is not None)
+        ctx.save_for_backward(bias, colsum, W1, b1, W2, b2, W3, b3, m_imp)
+        ctx.mark_non_differentiable(colsum)
+        if Wres is None:
+            Wr, btr = W.new_zeros(0), W.new_zeros(0)
+            ctx.mark_non_differentiable(Wr, btr)
+        return vals, Wc, biasterm, colsum, Wd, bd, Weff, beff, Wu, Wr, btr
+
+    @staticmethod
+    def backward(ctx, dvals, dWc, dbt, _dcolsum, dWd, dbd, dWeff, dbeff, dWu, dWr, dbtr):
+        from ._lib import call
+        bias, colsum, W1, b1, W2, b2, W3, b3, m_imp = ctx.saved_tensors
+        K, V, Cin, Cout, b, bp = ctx.dims
+        A1, A2, A3 = ctx.bufs
+        pat = ctx.pattern
+        has_bias, h1, h2, h3, has_res = ctx.has
+        dev = colsum.device
+        z = lambda g, *sh: torch.zeros(*sh, device=dev) if g is None else g.contiguous()     # noqa: E731
+        dvals, dWc, dbt = z(dvals, pat.nnz), z(dWc, K * Cin, Cout), z(dbt, V, Cout)
+        dWd, dbd, dWeff, dbeff, dWu = z(dWd, Cout, bp), z(dbd, bp), z(dWeff, 15, bp, bp), z(dbeff, bp), z(dWu, bp, Cout)
+        new = lambda *sh: torch.empty(*sh, device=dev, dtype=torch.float32)          # noqa: E731
+        dW = new(K * Cout, Cin, 1, 1)
+        dbias = new(K * Cout) if has_bias else None
+        dimp = [new(K, V, V) if h else None for h in (h1, h2, h3)]
+        dWs, dbs, dWe, dm = new(b, Cout, 1, 1), new(b), new(Cout, b, 1, 1), new(3)
+        dWt = [new(b, b, kt, 1) for kt in (3, 9, 15)]
+        dbt3 = [new(b) for _ in range(3)]
+        dWres = dbres = None
+        if has_res:
+            dWr, dbtr = z(dWr, Cin, Cout), z(dbtr, V, Cout)
+            dWres, dbres = new(Cout, Cin, 1, 1), new(Cout)
+        else:
+            dWr = dbtr = None
+        call('block_prep_bwd', dvals, dWc, dbt, dWd, dbd, dWeff, dbeff, dWu, dWr, dbtr, bias if has_bias else None,
+             colsum, A1, A2, A3, pat.inv_idx, pat.id_kw, W1.contiguous(), b1.contiguous(), W2.contiguous(),
+             b2.contiguous(), W3.contiguous(), b3.contiguous(), m_imp.contiguous(), dW, dbias, dimp[0], dimp[1],
+             dimp[2], dWs, dbs, dWt[0], dbt3[0], dWt[1], dbt3[1], dWt[2], dbt3[2], dWe, dm, dWres, dbres, K, V,
+             Cin, Cout, b, bp)
+        return (dW, dbias, dimp[0], dimp[1], dimp[2], dWs, dbs, dWt[0], dbt3[0], dWt[1], dbt3[1], dWt[2],
+                dbt3[2], dWe, dm, dWres, dbres, None, None, None)
+
+
+def _prep_kernel_enabled():
+    import os
+    return os.environ.get('ISTGCN_PREP_KERNEL', '1') != '0'
+
+
 class FusedBlockMixin(object):
     """Drives ops.STBlock for a block whose sub-modules follow the reference's names:
     ``gcn`` (ConvTemporalGraphical or Inception2), ``tcn_start``, ``conv_1x1_start``, ``tcn_1``,
@@ -148,6 +219,33 @@ class FusedBlockMixin(object):
         return (vals.contiguous(), wc.contiguous(), biasterm.contiguous(), w2, wd.contiguous(),
                 bd.contiguous(), weff.contiguous(), beff.contiguous(), wu.contiguous(), bu.contiguous(),
                 wr, btr)
+
+    def prepare_operands_fused(self, bufs, imps, m_imp, pattern):
+        """The same operands from the RAW adjacency buffers (A, A2, A3 or A alone) and importance
+        parameters through BlockPrep: one kernel forward, one backward."""
+        conv = self._gcn_conv()
+        kc, cin = conv.weight.shape[0], conv.weight.shape[1]
+        K, V = pattern.K, pattern.V
+        cout = kc // K
+        b = self.conv_1x1_start.weight.shape[0]
+        bp = padded_bottleneck(b)
+        bufs = tuple(bufs) + (None,) * (3 - len(bufs))
+        imps = [i if torch.is_tensor(i) else None for i in imps] + [None] * (3 - len(imps))
+        wres = bres = None
+        if self._res_mode == 2:
+            wres, bres = self.residual[0].weight, self.residual[0].bias
+        vals, wc, biasterm, colsum, wd, bd, weff, beff, wu, wr, btr = BlockPrep.apply(
+            conv.weight, conv.bias, imps[0], imps[1], imps[2], self.conv_1x1_start.weight,
+            self.conv_1x1_start.bias, self.tcn_1.weight, self.tcn_1.bias, self.tcn_2.weight, self.tcn_2.bias,
+            self.tcn_3.weight, self.tcn_3.bias, self.conv_1x1_end.weight, m_imp, wres, bres, bufs, pattern,
+            (K, V, cin, cout, b, bp))
+        w2 = conv.weight.detach().view(kc, cin)
+        if cin % 32:
+            w2 = F.pad(w2, (0, 32 - cin % 32))
+        tc_ops = (w2, None, None) if conv.bias is None else (w2, conv.bias.detach().view(K, cout), colsum)
+        if self._res_mode != 2:
+            wr = btr = None
+        return (vals, wc, biasterm, tc_ops, wd, bd, weff, beff, wu, self.conv_1x1_end.bias, wr, btr)
 
     def forward_cl(self, x, adjs, m_imp, pattern, operands=None):
         """x (N*M, T, V, Cin) channels-last -> (N*M, T/stride, V, Cout)."""
@@ -337,6 +435,16 @@ class FusedModelMixin(object):
             return adjs
 
         blocks = list(self.st_gcn_networks)
+        fused_prep = _prep_kernel_enabled() and not hasattr(self, '_block_adjs') and m_imp is not None and \
+            all(hasattr(b, 'prepare_operands_fused') for b in blocks)
+
+        def operands_of(i, blk):
+            if fused_prep:      # one kernel: raw buffers + importance parameters
+                bufs = (self.A,) if imp2 is None else (self.A, self.A2, self.A3)
+                imps = (imp1[i],) if imp2 is None else (imp1[i], imp2[i], imp3[i])
+                return blk.prepare_operands_fused(bufs, imps, m_imp[i], pattern)
+            return blk.prepare_operands(adjs_of(i), m_imp[i] if m_imp is not None else None, pattern)
+
         if _side_stream_enabled() and all(hasattr(b, 'prepare_operands') for b in blocks):
             # parameter regrouping of every block on a side stream, one event per block: block i
             # waits for ITS operands only, blocks i+1.. are regrouped while block i computes
@@ -346,8 +454,7 @@ class FusedModelMixin(object):
             prepared = []
             with torch.cuda.stream(side):
                 for i, blk in enumerate(blocks):
-                    opnds = blk.prepare_operands(adjs_of(i), m_imp[i] if m_imp is not None else None,
-                                                 pattern)
+                    opnds = operands_of(i, blk)
                     for t in _flatten(opnds):
                         t.record_stream(main)
                     ev = torch.cuda.Event()
@@ -358,7 +465,10 @@ class FusedModelMixin(object):
                 x = blk.forward_cl(x, None, None, pattern, operands=opnds)
             return x
         for i, blk in enumerate(blocks):
-            x = blk.forward_cl(x, adjs_of(i), m_imp[i] if m_imp is not None else None, pattern)
+            if fused_prep:
+                x = blk.forward_cl(x, None, None, pattern, operands=operands_of(i, blk))
+            else:
+                x = blk.forward_cl(x, adjs_of(i), m_imp[i] if m_imp is not None else None, pattern)
         return x
 
     def forward(self, x):

@@ -34,6 +34,10 @@ class SparsePattern(object):
         def dev(a, dt=torch.int32):
             return torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(device)
         self.flat_idx = dev(k * V * V + v * V + w, torch.int64)
+        inv = np.full(K * V * V, -1, dtype=np.int64)
+        inv[k * V * V + v * V + w] = ids
+        self.inv_idx = dev(inv)                         # [K*V*V] -> canonical id of the entry, or -1
+        self.id_kw = dev(k * V + w)                     # [nnz] -> k*V + w (destination column) of entry id
         self.dst_ptr, self.dst_src, self.dst_id = dev(dst_ptr), dev(v[order_d]), dev(ids[order_d])
         # transposed adjacency for the input gradient: grouped by (k, v), "source" = w
         order_t = np.lexsort((w, v, k))                 # by k, then v, then w

@@ -1,7 +1,7 @@
 """Aggregate an `ncu --metrics gpu__time_duration.sum[,dram__bytes_read.sum,dram__bytes_write.sum]
 --csv` launch list by kernel name (markdown table on stdout).
 
-usage: summarize_launches.py launches.csv [traffic.json]
+usage: summarize_launches.py launches.csv [traffic.json [round-tag]]
 With a second argument, DRAM bytes per launch of the C-ABI entry points are written as JSON
 (bench.py reads profiles/r1_traffic.json for `roofline.traffic`)."""
 import csv, collections, json, re, sys
@@ -13,6 +13,10 @@ UNIT_B = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 ENTRY = (('tc::gcn_tc2_kernel', 'gcn_tc'), ('tc::gcn_tc_kernel', 'gcn_tc'), ('tc::gcn_tc_dw', 'gcn_tc_dw'),
          ('tc::frame_colsum', 'gcn_tc_dw'), ('tc::gcn_tc_da', 'gcn_tc_dvals'),
          ('istgcn::tcn_bwd', 'tcn_bwd'), ('istgcn::tcn_down', 'tcn_fwd'), ('istgcn::tcn_up', 'tcn_fwd'),
+         ('tcn2_down_kernel', 'tcn2_down'), ('tcn2_up_kernel', 'tcn2_up'), ('tcn2_bwd_up_kernel', 'tcn2_bwd_up'),
+         ('tcn2_bwd_down_kernel', 'tcn2_bwd_down'), ('tcn2_small_conv_kernel<1, 0', 'tcn2_conv'),
+         ('tcn2_small_conv_kernel<2, 0', 'tcn2_conv'), ('tcn2_small_conv_kernel<1, 1', 'tcn2_bwd_conv'),
+         ('tcn2_small_conv_kernel<2, 1', 'tcn2_bwd_conv'), ('tcn2_small_dw_kernel', 'tcn2_bwd_conv'),
          ('istgcn::block_tail_fwd', 'block_tail_fwd'), ('istgcn::block_tail_bwd', 'block_tail_bwd'),
          ('istgcn::bn_back_apply', 'bn_back_apply'), ('istgcn::bn_back_colsum', 'bn_back_colsum'), ('istgcn::gcn_small_fwd', 'gcn_small_fwd'),
          ('istgcn::gcn_small_bwd', 'gcn_small_bwd'))
@@ -49,11 +53,11 @@ if len(sys.argv) > 2:
     ent = {}
     for name, (n, t, rd, wr) in rows.items():
         for prefix, key in ENTRY:
-            if name.startswith(prefix):
+            if prefix in name:
                 e = ent.setdefault(key, [0, 0.0, 0.0])
                 e[0] += n; e[1] += rd + wr; e[2] += t
                 break
-    per_call = {'tcn_bwd': 3, 'tcn_fwd': 2}       # kernels per C-ABI call
+    per_call = {'tcn_bwd': 3, 'tcn_fwd': 2, 'tcn2_bwd_conv': 2}       # kernels per C-ABI call
     out = {}
     for key, (n, b, t) in ent.items():
         calls = n / per_call.get(key, 1)
@@ -61,6 +65,6 @@ if len(sys.argv) > 2:
             calls = sum(v[0] for k2, v in rows.items() if k2.startswith('tc::gcn_tc_dw'))
         out[key] = {'dram_bytes_per_launch': b / calls, 'launches': int(calls), 'ms_per_launch': t / calls,
                     'workload': 'ntu', 'clips_per_gpu': 64,
-                    'source': 'profiles/r1_launches_dram.md (ncu dram__bytes_read.sum + dram__bytes_write.sum)'}
+                    'source': 'profiles/%s_launches_dram.md (ncu dram__bytes_read.sum + dram__bytes_write.sum)' % (sys.argv[3] if len(sys.argv) > 3 else 'r1')}
     with open(sys.argv[2], 'w') as f:
         json.dump(out, f, indent=1)
