@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(256) block_prep_fwd_kernel(PrepP p) {
         p.colsum[i] = s;
     }
     for (int i = gid; i < K * Cin * Cout; i += gsz) {                 // Wc[k*Cin+ci][c] = W[k*Cout+c][ci]
-        const int c = i % Cout, ci = (i / Cout) % Cin, k = i / (Cout * Cin);
-        p.Wc[i] = p.W[((long long)k * Cout + c) * Cin + ci];
+        const int ci = i % Cin, c = (i / Cin) % Cout, k = i / (Cout * Cin);      // coalesced reads, strided writes
+        p.Wc[((long long)k * Cin + ci) * Cout + c] = p.W[i];
     }
     for (int i = gid; i < V * Cout; i += gsz) {                       // biasterm[w][c]
         const int c = i % Cout, w = i / Cout;
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(256) block_prep_fwd_kernel(PrepP p) {
     }
     if (p.Wres) {
         for (int i = gid; i < Cin * Cout; i += gsz) {                 // Wr[ci][co] = Wres[co][ci]
-            const int co = i % Cout, ci = i / Cout;
-            p.Wr[i] = p.Wres[co * Cin + ci];
+            const int ci = i % Cin, co = i / Cin;
+            p.Wr[ci * Cout + co] = p.Wres[i];
         }
         for (int i = gid; i < V * Cout; i += gsz) p.btr[i] = p.bres[i % Cout];
     }
@@ -174,24 +174,25 @@ __global__ void __launch_bounds__(256) block_prep_bwd_kernel(PrepBwdP p) {
     const int gsz = gridDim.x * blockDim.x, gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int K = p.K, V = p.V, Cin = p.Cin, Cout = p.Cout, b = p.b, bp = p.bp;
     // importances: d imp_i[k][v][w] = A_i * (dvals[id] + sum_c bias[k][c] dbt[w][c]) on the pattern, 0 elsewhere
-    for (int i = gid; i < K * V * V; i += gsz) {
+    // (one WARP per stack element: the lanes share the dot product over the channels)
+    const int lane = threadIdx.x & 31, gwarp = gid >> 5, nwarp = gsz >> 5;
+    for (int i = gwarp; i < K * V * V; i += nwarp) {
         const int id = p.inv_idx[i];
         float gsum = 0.f;
         if (id >= 0) {
-            gsum = p.dvals[id];
             if (p.bias) {
                 const int kw = p.id_kw[id], k = kw / V, w = kw - k * V;
                 float q = 0.f;
-                for (int c = 0; c < Cout; ++c) q = fmaf(p.bias[k * Cout + c], p.dbt[w * Cout + c], q);
-                gsum += q;
+                for (int c = lane; c < Cout; c += 32) q = fmaf(p.bias[k * Cout + c], p.dbt[w * Cout + c], q);
+                gsum = warp_sum(q);
             }
+            gsum += p.dvals[id];
         }
-        for (int s = 0; s < p.ns; ++s)
-            if (p.dimp[s]) p.dimp[s][i] = id >= 0 ? p.A[s][i] * gsum : 0.f;
+        if (lane < p.ns && p.dimp[lane]) p.dimp[lane][i] = id >= 0 ? p.A[lane][i] * gsum : 0.f;
     }
     for (int i = gid; i < K * Cout * Cin; i += gsz) {                 // dW[k*Cout+c][ci] = dWc[k*Cin+ci][c]
-        const int ci = i % Cin, c = (i / Cin) % Cout, k = i / (Cin * Cout);
-        p.dW[i] = p.dWc[((long long)k * Cin + ci) * Cout + c];
+        const int c = i % Cout, ci = (i / Cout) % Cin, k = i / (Cin * Cout);     // coalesced reads, strided writes
+        p.dW[((long long)k * Cout + c) * Cin + ci] = p.dWc[i];
     }
     if (p.dbias)
         for (int i = gid; i < K * Cout; i += gsz) {                   // dbias[k][c] = sum_w colsum[k][w] dbt[w][c]
@@ -217,8 +218,8 @@ __global__ void __launch_bounds__(256) block_prep_bwd_kernel(PrepBwdP p) {
         }
     if (p.dWres) {
         for (int i = gid; i < Cout * Cin; i += gsz) {                 // dWres[co][ci] = dWr[ci][co]
-            const int ci = i % Cin, co = i / Cin;
-            p.dWres[i] = p.dWr[ci * Cout + co];
+            const int co = i % Cout, ci = i / Cout;
+            p.dWres[co * Cin + ci] = p.dWr[i];
         }
         for (int i = gid; i < Cout; i += gsz) {
             float s = 0.f;
@@ -226,17 +227,24 @@ __global__ void __launch_bounds__(256) block_prep_bwd_kernel(PrepBwdP p) {
             p.dbres[i] = s;
         }
     }
-    // d m_imp[q] = <W_q, dWeff window> + <b_q, dbeff>: one warp of block 0 per branch
-    if (blockIdx.x == 0 && threadIdx.x < 96) {
-        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // d m_imp[q] = <W_q, dWeff window> + <b_q, dbeff>: blocks 0..2 take one branch each
+    if (blockIdx.x < 3) {
+        __shared__ float red[8];
+        const int q = blockIdx.x;
         float s = 0.f;
-        for (int i = lane; i < b * b * kt[q]; i += 32) {
+        for (int i = threadIdx.x; i < b * b * kt[q]; i += blockDim.x) {
             const int kk = i % kt[q], ci = (i / kt[q]) % b, co = i / (kt[q] * b);
             s = fmaf(p.Wt[q][i], p.dWeff[((kk + (15 - kt[q]) / 2) * bp + ci) * bp + co], s);
         }
-        for (int i = lane; i < b; i += 32) s = fmaf(p.bt[q][i], p.dbeff[i], s);
+        for (int i = threadIdx.x; i < b; i += blockDim.x) s = fmaf(p.bt[q][i], p.dbeff[i], s);
         s = warp_sum(s);
-        if (lane == 0) p.dm_imp[q] = s;
+        if (lane == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) t += red[wq];
+            p.dm_imp[q] = t;
+        }
     }
 }
 
