@@ -147,6 +147,20 @@ int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const fl
                   int CinPad, int Cout, int t_in, int t_out, int t_stride, int t_offset, int map_side,
                   istgcn_stream_t s);
 
+/* weight AND adjacency gradient from one pass over (dz, x) (csrc/gcn_pair_tc.cu; replaces the two calls
+ * above in the fast mode): P[(v,w)][ci][c] = sum_f x[(f,v)][ci] dz[(f,w)][c] for every joint pair of the
+ * non-zero pattern on the tensor core (both operands by TMA as they lie in HBM), then
+ *   dWc[k*Cin+ci][c] += sum_(v,w) vals[(k,v,w)] P[(v,w)][ci][c],   dvals[(k,v,w)] += <Wc[k], P[(v,w)]>.
+ * v_list[npairs]: source joints grouped by destination joint; items[nitems][4] = {w, first index into
+ * v_list, count, first output column}: at most 512/nb * 128/Cin pairs and nb (<= 128) columns each;
+ * entry_pair[nnz]: pair index of every canonical entry; k_ptr[K+1]: entries of partition k (canonical
+ * order is sorted by k).  P_ws [npairs][Cin][Cout] caller-zeroed scratch; Cin, Cout multiples of 32.   */
+int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, const float* Wc,
+                          const int* items, int nitems, const int* v_list, int npairs,
+                          const int* entry_pair, const int* k_ptr, int nnz, float* P_ws, float* dWc,
+                          float* dvals, int frames, int V, int K, int Cin, int Cout, int nb,
+                          istgcn_stream_t s);
+
 /* ---- first block (in_channels <= 4: net/st_gcnold.py:46 `st_gcn(in_channels, 64, ...)`, the
  * graph convolution of tgcn.py:76-89 on a 3-channel input) on CUDA cores in full fp32
  * (csrc/gcn_small.cu): 12 B in / 256 B out per row, so no tensor-core slice padding.

@@ -1,0 +1,259 @@
+// Weight AND adjacency gradient of the fused graph convolution from ONE pass over (dz, x)
+// (reference: autograd of net/utils/tgcn.py:79-86 / net/utils/inceptionv2_gcn.py:69-88):
+//
+//   P[(v,w)][ci][c] = sum_f x[(f,v)][ci] * dz[(f,w)][c]           for every joint pair (v, w) that is
+//                                                                 non-zero in some partition
+//   dWc[k*Cin+ci][c] += sum_{(v,w)} A_eff[k][v][w] * P[(v,w)][ci][c]
+//   dvals[(k,v,w)]   += sum_{ci,c} Wc[k*Cin+ci][c] * P[(v,w)][ci][c]
+//
+// i.e. the adjacency is folded OUT of the big contraction: the tensor-core kernel is a batch of plain
+// "rows-contracted" products with both operands fed by TMA exactly as they lie in HBM -- no
+// aggregation MMA (whose block-diagonal structure wastes 3/4 of every M=128 instruction in
+// gcn_tc_dw2 / gcn_tc_da2), no lane masks, no TMEM->smem converter warps -- and the two small
+// reductions that bring the partitions back in run on the CUDA cores over the pair matrices
+// (195 pairs x Cin x Cout: 3 ... 51 MB).  Replaces istgcn_gcn_tc_dw + istgcn_gcn_tc_dvals.
+//
+// Kernel structure = csrc/tconv_dw_tc.cu (MN-major operands, 32-byte-atom 128B swizzle): a K-tile is
+// 64 consecutive frames of ONE joint (3-D tensor map (C, V, frames), box 32 x 1 x 64); a work item
+// is one destination joint w with up to G of its source joints (stacked rows R = vi*Cin + ci, M-blocks
+// of 128 rows, accumulators resident in tensor memory) and one N-chunk of <= 128 output channels;
+// the dz atoms of (w, K-tile) are shared by all M-blocks of the item.
+//   warp 0      TMA producer        warp 1      MMA issuer (kind::tf32, M=128, N=nb, K=8 frames)
+//   warps 4-7   final epilogue: TMEM -> fp32 atomics into P
+#include "tc_common.cuh"
+
+namespace istgcn {
+namespace tc {
+
+constexpr int kThreadsGP = 256;
+constexpr int kGPRows = 64;                       // frames of a K-tile atom
+constexpr int kGPBytes = kGPRows * 128;           // [64 frames][32 channels]
+constexpr int kGPAst = 3;                         // ring of M-block stages (4 atoms each)
+
+struct PairParams {
+    float* P;                                     // [npairs][Cin][Cout]
+    const int4* items;                            // {w, v0, nv, col0}
+    const int* v_list;                            // [npairs] source joints, grouped by destination w
+    int frames, V, Cin, Cout, nb, ktiles;
+};
+
+struct SmemGP {
+    static constexpr int a_off = 0;                                   // kGPAst x 4 atoms
+    static constexpr int b_off = a_off + kGPAst * 4 * kGPBytes;       // 2 x (nb/32 <= 4) atoms
+    static constexpr int bar_off = b_off + 2 * 4 * kGPBytes;
+    static constexpr int kNumBars = 2 * kGPAst + 4 + 1;
+    static constexpr int total = bar_off + kNumBars * 8 + 16;
+};
+
+__global__ void __launch_bounds__(kThreadsGP, 1)
+gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap dmap,
+                   PairParams p) {
+    using L = SmemGP;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* As = smem + L::a_off;
+    uint8_t* Bs = smem + L::b_off;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + kGPAst;
+    uint64_t* b_full = a_empty + kGPAst;
+    uint64_t* b_empty = b_full + 2;
+    uint64_t* done = b_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::kNumBars);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int4 item = p.items[blockIdx.y];
+    const int w = item.x, v0 = item.y, nv = item.z, col0 = item.w;
+    const int nb = p.nb, natom = nb / 32;
+    const int rows_total = nv * p.Cin;
+    const int nmb = (rows_total + 127) / 128;
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < (uint32_t)(nmb * nb)) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int i = 0; i < kGPAst; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) { tma_prefetch_desc(&xmap); tma_prefetch_desc(&dmap); }
+    if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        uint32_t ita = 0, itb = 0;
+        for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
+            const int f0 = kt_i * kGPRows;
+            const int bb = itb & 1;
+            mbar_wait(&b_empty[bb], ((itb >> 1) & 1) ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&b_full[bb], (uint32_t)kGPBytes * natom);
+                for (int j = 0; j < natom; ++j)
+                    tma_load_3d(Bs + (bb * 4 + j) * kGPBytes, &dmap, &b_full[bb], col0 + 32 * j, w, f0);
+            }
+            __syncwarp();
+            for (int mb = 0; mb < nmb; ++mb, ++ita) {
+                const int sa = ita % kGPAst;
+                mbar_wait(&a_empty[sa], ((ita / kGPAst) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(&a_full[sa], (uint32_t)kGPBytes * 4);
+                    for (int j = 0; j < 4; ++j) {
+                        const int R = mb * 128 + 32 * j;                 // first stacked row of the atom
+                        const int vi = R / p.Cin, ci0 = R - vi * p.Cin;
+                        const bool ok = R < rows_total;
+                        // atoms past the end of the item: a box outside the tensor reads as zeros
+                        tma_load_3d(As + (sa * 4 + j) * kGPBytes, &xmap, &a_full[sa], ok ? ci0 : 0,
+                                    ok ? p.v_list[v0 + vi] : 0, ok ? f0 : -(1 << 20));
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc(128, nb, true, true);
+        uint32_t ita = 0, itb = 0;
+        bool first = true;
+        for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
+            const int bb = itb & 1;
+            mbar_wait(&b_full[bb], (itb >> 1) & 1);
+            const uint32_t b_addr = smem_u32(Bs + bb * 4 * kGPBytes);
+            for (int mb = 0; mb < nmb; ++mb, ++ita) {
+                const int sa = ita % kGPAst;
+                mbar_wait(&a_full[sa], (ita / kGPAst) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a_addr = smem_u32(As + sa * 4 * kGPBytes);
+                    const uint32_t d_tmem = tmem_base + mb * nb;
+#pragma unroll
+                    for (int ks = 0; ks < kGPRows / 8; ++ks)
+                        tc_mma_tf32(d_tmem, make_desc(a_addr + ks * 1024, kGPBytes, 512, 1),
+                                    make_desc(b_addr + ks * 1024, kGPBytes, 512, 1), idesc,
+                                    (first && ks == 0) ? 0u : 1u);
+                    tc_commit(&a_empty[sa]);
+                    if (mb == nmb - 1) tc_commit(&b_empty[bb]);
+                }
+                __syncwarp();
+            }
+            first = false;
+        }
+        if (elect_one()) tc_commit(done);
+        __syncwarp();
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
+        const int m = ew * 32 + lane;
+        mbar_wait(done, 0);
+        tc_fence_after();
+        if ((int)blockIdx.x < p.ktiles) {
+            for (int mb = 0; mb < nmb; ++mb) {
+                const int R = mb * 128 + m;
+                const int vi = R / p.Cin, ci = R - vi * p.Cin;
+                for (int c0 = 0; c0 < nb; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + mb * nb + c0, v);
+                    if (R < rows_total) {
+                        float* dst = p.P + ((size_t)(v0 + vi) * p.Cin + ci) * p.Cout + col0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// dWc[k*Cin+ci][c] += sum over the entries (k, v, w) of partition k of vals * P[pair][ci][c]
+__global__ void __launch_bounds__(256) pair_reduce_dw_kernel(const float* __restrict__ P,
+                                                             const float* __restrict__ vals,
+                                                             const int* __restrict__ entry_pair,
+                                                             const int* __restrict__ k_ptr,
+                                                             float* __restrict__ dWc, int K, int CC) {
+    const long long total = (long long)K * CC;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i / CC), r = (int)(i - (long long)k * CC);
+        float s = 0.f;
+        for (int e = k_ptr[k]; e < k_ptr[k + 1]; ++e) s = fmaf(vals[e], P[(size_t)entry_pair[e] * CC + r], s);
+        dWc[i] += s;
+    }
+}
+
+// dvals[e] += <Wc[k(e)], P[pair(e)]>: one CTA per entry
+__global__ void __launch_bounds__(256) pair_reduce_da_kernel(const float* __restrict__ P,
+                                                             const float* __restrict__ Wc,
+                                                             const int* __restrict__ entry_pair,
+                                                             const int* __restrict__ k_ptr,
+                                                             float* __restrict__ dvals, int K, int CC) {
+    __shared__ float red[8];
+    const int e = blockIdx.x;
+    int k = 0;
+    while (k + 1 < K && e >= k_ptr[k + 1]) ++k;
+    const float4* p4 = reinterpret_cast<const float4*>(P + (size_t)entry_pair[e] * CC);
+    const float4* w4 = reinterpret_cast<const float4*>(Wc + (size_t)k * CC);
+    float s = 0.f;
+    for (int i = threadIdx.x; i < CC / 4; i += blockDim.x) {
+        const float4 a = p4[i], b = w4[i];
+        s = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, fmaf(a.w, b.w, s))));
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        dvals[e] += t;
+    }
+}
+
+}  // namespace tc
+}  // namespace istgcn
+
+using namespace istgcn;
+
+ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, const float* Wc,
+                                     const int* items, int nitems, const int* v_list, int npairs,
+                                     const int* entry_pair, const int* k_ptr, int nnz, float* P_ws,
+                                     float* dWc, float* dvals, int frames, int V, int K, int Cin, int Cout,
+                                     int nb, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(dz && x && vals && Wc && items && v_list && entry_pair && k_ptr && P_ws && dWc && dvals,
+                   ISTGCN_E_ARG, "gcn_pair_grads: null pointer");
+    ISTGCN_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && V >= 1 && V <= 64 && K >= 1,
+                   ISTGCN_E_SHAPE, "gcn_pair_grads: Cin=%d Cout=%d V=%d unsupported", Cin, Cout, V);
+    ISTGCN_REQUIRE(nb >= 32 && nb <= 128 && nb % 32 == 0 && Cout % nb == 0, ISTGCN_E_SHAPE,
+                   "gcn_pair_grads: N-chunk %d must divide Cout=%d (32..128)", nb, Cout);
+    ISTGCN_REQUIRE(((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(x) |
+                     reinterpret_cast<uintptr_t>(P_ws) | reinterpret_cast<uintptr_t>(Wc)) & 15) == 0,
+                   ISTGCN_E_ARG, "gcn_pair_grads: pointers must be 16-byte aligned");
+    if (frames == 0 || nitems == 0 || nnz == 0) return 0;
+    cudaStream_t st = (cudaStream_t)s;
+    tc::PairParams p{};
+    p.P = P_ws; p.items = reinterpret_cast<const int4*>(items); p.v_list = v_list;
+    p.frames = frames; p.V = V; p.Cin = Cin; p.Cout = Cout; p.nb = nb;
+    p.ktiles = (frames + tc::kGPRows - 1) / tc::kGPRows;
+    CUtensorMap xmap, dmap;
+    if (int e = tc::encode_joint_frames_map(&xmap, x, frames, V, Cin, tc::kGPRows)) return e;
+    if (int e = tc::encode_joint_frames_map(&dmap, dz, frames, V, Cout, tc::kGPRows)) return e;
+    cudaFuncSetAttribute(tc::gcn_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         tc::SmemGP::total);
+    int nx = num_sms() / nitems;
+    if (nx < 1) nx = 1;
+    if (nx > p.ktiles) nx = p.ktiles;
+    tc::gcn_pair_tc_kernel<<<dim3(nx, nitems), tc::kThreadsGP, tc::SmemGP::total, st>>>(xmap, dmap, p);
+    if (int e = finish_launch("gcn_pair_tc")) return e;
+    const int CC = Cin * Cout;
+    long long blocks = ((long long)K * CC + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    tc::pair_reduce_dw_kernel<<<(int)blocks, 256, 0, st>>>(P_ws, vals, entry_pair, k_ptr, dWc, K, CC);
+    if (int e = finish_launch("pair_reduce_dw")) return e;
+    tc::pair_reduce_da_kernel<<<nnz, 256, 0, st>>>(P_ws, Wc, entry_pair, k_ptr, dvals, K, CC);
+    return finish_launch("pair_reduce_da");
+}

@@ -523,6 +523,24 @@ int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V,
     return 0;
 }
 
+int encode_joint_frames_map(CUtensorMap* map, const float* base, long long frames, int V, int C,
+                            int box_frames) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return ISTGCN_E_ARCH;
+    cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)V, (cuuint64_t)frames};
+    cuuint64_t strides[2] = {(cuuint64_t)C * 4, (cuuint64_t)V * C * 4};
+    cuuint32_t box[3] = {32u, 1u, (cuuint32_t)box_frames};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for joint-frames map [%lld x %d x %d]", (int)r, frames, V, C);
+        return ISTGCN_E_ARG;
+    }
+    return 0;
+}
+
 template <int NCOLS>
 static int launch_tc(const CUtensorMap& map, const CUtensorMap& omap, const CUtensorMap& omap_last,
                      const GcnTcParams& p, cudaStream_t s) {

@@ -357,6 +357,10 @@ int encode_frames_map(CUtensorMap* map, const float* base, int NM, int T, int V,
 // 3-D (C, V, frames) view of a channels-last activation: box = 32 channels x V joints x 1 frame,
 // 32-byte-atom 128B swizzle (gcn_tc2.cu)
 int encode_frame_slices(CUtensorMap* map, const float* base, long long frames, int V, int C);
+// 3-D (C, V, frames) view: box = 32 channels x ONE joint x box_frames consecutive frames, 32-byte-atom
+// 128B swizzle: the rows-contracted (MN-major) operand of gcn_pair_tc.cu
+int encode_joint_frames_map(CUtensorMap* map, const float* base, long long frames, int V, int C,
+                            int box_frames);
 // second-generation graph-convolution engine (gcn_tc2.cu)
 bool gcn_tc2_eligible(int V, int K, int Cin, int Cout, const float* in, const float* out);
 int launch_gcn_tc2(const float* in, const float* w_rows, const float* vals, const int* lptr,

@@ -16,7 +16,7 @@ SYMBOLS = (
     'istgcn_last_error', 'istgcn_version', 'istgcn_check_device',
     'istgcn_data_bn_stats', 'istgcn_data_bn_apply', 'istgcn_data_bn_bwd',
     'istgcn_bn_finalize', 'istgcn_bn_eval_coeffs', 'istgcn_bn_bwd_coeffs',
-    'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw',
+    'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw', 'istgcn_gcn_pair_grads',
     'istgcn_gcn_small_fwd', 'istgcn_gcn_small_bwd',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
     'istgcn_tcn2_down', 'istgcn_tcn2_conv', 'istgcn_tcn2_up', 'istgcn_tcn2_bwd_up', 'istgcn_tcn2_bwd_conv',
@@ -72,7 +72,7 @@ def _conv(a):
 
 # kernels launched per C-ABI call (tcn_fwd = down + up, tcn_bwd = up + temporal + down,
 # pool_fwd = kernel behind a memset) -- used for the ``gpu_launches`` count of bench.py
-KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2, 'tconv_dw_tc': 2, 'tcn2_bwd_conv': 2}
+KERNELS_PER_CALL = {'tcn_fwd': 2, 'tcn_bwd': 3, 'gcn_tc_dw': 2, 'tconv_dw_tc': 2, 'tcn2_bwd_conv': 2, 'gcn_pair_grads': 3}
 launch_count = 0          # kernels launched through this binding since import
 timing = None             # set to a dict by bench.py: name -> list of (start_event, end_event)
 

@@ -132,6 +132,18 @@ def _gcn_tc2_ok(cin, cout):
         os.environ.get('ISTGCN_GCN_TC_V1') is None
 
 
+def _gcn_pair_ok(cin, cout):
+    """Shapes the one-pass weight + adjacency gradient takes (csrc/gcn_pair_tc.cu)."""
+    return cin % 32 == 0 and cout % 32 == 0 and cin <= 512 and os.environ.get('ISTGCN_GCN_PAIR_OFF') is None
+
+
+def gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout):
+    items, nb = pat.pair_items(Cin, Cout)
+    ws = torch.zeros(pat.npairs, Cin, Cout, device=dz.device, dtype=torch.float32)
+    call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], pat.pair_v, pat.npairs, pat.entry_pair,
+         pat.k_ptr, pat.nnz, ws, dWc, dvals, frames, V, K, Cin, Cout, nb)
+
+
 def _gcn_small_ok(cin, cout):
     """The first block's narrow-input graph convolution (csrc/gcn_small.cu)."""
     # fast mode only: the fp32-grade parity mode keeps one arithmetic (the 3xTF32 engine) for every
@@ -306,7 +318,7 @@ class STBlock(Function):
             call('tconv_tc', dyr, Wr.contiguous(), None, gin, None, None, NM, T, Tout, V, Cout, Cin, 1, s, -1)
             add_in = gin
         small = _gcn_small_ok(Cin, Cout) and cfg.res_mode == 0
-        dbt_done = False
+        dbt_done = pair = False
         if small:
             # first block: dz, dx, dvals, dWc and dbt in one CUDA-core kernel
             call('gcn_small_bwd', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.dst_ptr, pat.dst_src,
@@ -329,12 +341,18 @@ class STBlock(Function):
                 call('gcn_tc', g1, z, p1, m11, c1, mean1, Wc, vals, pat.t_ptr, pat.t_src, pat.t_id,
                      pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin,
                      0, 0, 1, 0, 0)
-            call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
-                 NM * T, V, K, Cin, Cout)
+            pair = dbt_done and _gcn_pair_ok(Cin, Cout)
+            if pair:      # weight AND adjacency gradient from one pass over (dz, x)
+                gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, NM * T, V, K, Cin, Cout)
+            else:
+                call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
+                     NM * T, V, K, Cin, Cout)
         else:
             call('gcn_bwd_x', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.src_ptr, pat.src_kw,
                  pat.src_id, pat.nnz, add_in, gin, dvals, NM * T, V, K, Cin, Cout, 0, 0, 1, 0, math)
         if small:
+            pass
+        elif use_tc() and pair:
             pass
         elif use_tc():
             call('gcn_tc_dw', dz, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dWc,

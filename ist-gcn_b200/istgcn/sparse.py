@@ -47,6 +47,35 @@ class SparsePattern(object):
         self.src_ptr = dev(src_ptr)
         self.src_kw = dev(k[order_s] * V + w[order_s])
         self.src_id = dev(ids[order_s])
+        # joint pairs (v, w) that are non-zero in SOME partition, grouped by destination w
+        # (csrc/gcn_pair_tc.cu): pair id = position in the (w, v)-sorted list
+        key = w.astype(np.int64) * V + v
+        uniq, inverse = np.unique(key, return_inverse=True)
+        self.npairs = int(uniq.size)
+        self._pair_w = (uniq // V).astype(np.int64)
+        self.pair_v = dev(uniq % V)                      # [npairs] source joint of every pair
+        self.entry_pair = dev(inverse)                   # [nnz] canonical entry -> pair id
+        self.k_ptr = dev(np.concatenate([[0], np.cumsum(np.bincount(k, minlength=K))]))
+        self._device = device
+        self._pair_items = {}
+
+    def pair_items(self, cin, cout):
+        """Work items of istgcn_gcn_pair_grads for this channel pair: (items int32 [n][4] =
+        {w, first pair, pairs, first column}, N-chunk width)."""
+        hit = self._pair_items.get((cin, cout))
+        if hit is None:
+            nb = next(c for c in (128, 96, 64, 32) if cout % c == 0)
+            per_item = max(1, (512 // nb) * 128 // cin)
+            rows = []
+            bounds = np.concatenate([[0], np.cumsum(np.bincount(self._pair_w, minlength=self.V))])
+            for w_ in range(self.V):
+                lo, hi = int(bounds[w_]), int(bounds[w_ + 1])
+                for first in range(lo, hi, per_item):
+                    for col0 in range(0, cout, nb):
+                        rows.append((w_, first, min(per_item, hi - first), col0))
+            items = torch.as_tensor(np.asarray(rows, dtype=np.int32).reshape(-1, 4)).to(self._device)
+            hit = self._pair_items[(cin, cout)] = (items, nb)
+        return hit
 
     @classmethod
     def identity(cls, V, device):

@@ -282,6 +282,12 @@ def test_tensor_core_graph_conv_entry_points_vs_fp64(env, layout, strategy, cin,
     call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals, frames, V, K, cin, cout)
     dA = torch.einsum('fvc,kfwc->kvw', x.view(frames, V, cin).double(), G)
     assert rel(dvals, dA.reshape(-1)[pat.flat_idx]) < 5e-3
+    # both of them from one pass over (dz, x): csrc/gcn_pair_tc.cu (accumulates onto its outputs)
+    from istgcn import ops
+    dW2, dvals2 = torch.ones(K * cin, cout, device=dev), torch.ones(pat.nnz, device=dev)
+    ops.gcn_pair_grads(dz, x, vals, Wc, pat, dW2, dvals2, frames, V, K, cin, cout)
+    assert rel(dW2 - 1, dW_ref) < 5e-3
+    assert rel(dvals2 - 1, dA.reshape(-1)[pat.flat_idx]) < 5e-3
 
 
 
