@@ -153,10 +153,13 @@ int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const fl
  *   dWc[k*Cin+ci][c] += sum_(v,w) vals[(k,v,w)] P[(v,w)][ci][c],   dvals[(k,v,w)] += <Wc[k], P[(v,w)]>.
  * v_list[npairs]: source joints grouped by destination joint; items[nitems][4] = {w, first index into
  * v_list, count, first output column}: at most 512/nb * 128/Cin pairs and nb (<= 128) columns each;
+ * ctas[nctas][4] = {item, first 64-frame K-tile, K-tile stride, 0}: one thread block each (the caller
+ * gives an item thread blocks in proportion to its pairs so that all blocks finish together);
  * entry_pair[nnz]: pair index of every canonical entry; k_ptr[K+1]: entries of partition k (canonical
  * order is sorted by k).  P_ws [npairs][Cin][Cout] caller-zeroed scratch; Cin, Cout multiples of 32.   */
 int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, const float* Wc,
-                          const int* items, int nitems, const int* v_list, int npairs,
+                          const int* items, int nitems, const int* ctas, int nctas,
+                          const int* v_list, int npairs,
                           const int* entry_pair, const int* k_ptr, int nnz, float* P_ws, float* dWc,
                           float* dvals, int frames, int V, int K, int Cin, int Cout, int nb,
                           istgcn_stream_t s);

@@ -28,11 +28,12 @@ namespace tc {
 constexpr int kThreadsGP = 256;
 constexpr int kGPRows = 64;                       // frames of a K-tile atom
 constexpr int kGPBytes = kGPRows * 128;           // [64 frames][32 channels]
-constexpr int kGPAst = 3;                         // ring of M-block stages (4 atoms each)
+constexpr int kGPAst = 4;                         // ring of M-block stages (4 atoms each)
 
 struct PairParams {
     float* P;                                     // [npairs][Cin][Cout]
     const int4* items;                            // {w, v0, nv, col0}
+    const int4* ctas;                             // per CTA: {item, first K-tile, K-tile stride, 0}
     const int* v_list;                            // [npairs] source joints, grouped by destination w
     int frames, V, Cin, Cout, nb, ktiles;
 };
@@ -61,7 +62,12 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + L::kNumBars);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int4 item = p.items[blockIdx.y];
+    // Work split: every CTA walks the K-tiles first, first + stride, ... of ONE item; the host gives an
+    // item CTAs in proportion to its M-blocks, so all CTAs advance through the frames at the same
+    // pace (the x / dz K-tiles they share stay in L2) and finish together.
+    const int4 cta = p.ctas[blockIdx.x];
+    const int4 item = p.items[cta.x];
+    const int kt_first = cta.y, kt_step = cta.z;
     const int w = item.x, v0 = item.y, nv = item.z, col0 = item.w;
     const int nb = p.nb, natom = nb / 32;
     const int rows_total = nv * p.Cin;
@@ -85,7 +91,7 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
 
     if (warp == 0) {
         uint32_t ita = 0, itb = 0;
-        for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
+        for (int kt_i = kt_first; kt_i < p.ktiles; kt_i += kt_step, ++itb) {
             const int f0 = kt_i * kGPRows;
             const int bb = itb & 1;
             mbar_wait(&b_empty[bb], ((itb >> 1) & 1) ^ 1);
@@ -116,7 +122,7 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         const uint32_t idesc = make_idesc(128, nb, true, true);
         uint32_t ita = 0, itb = 0;
         bool first = true;
-        for (int kt_i = blockIdx.x; kt_i < p.ktiles; kt_i += gridDim.x, ++itb) {
+        for (int kt_i = kt_first; kt_i < p.ktiles; kt_i += kt_step, ++itb) {
             const int bb = itb & 1;
             mbar_wait(&b_full[bb], (itb >> 1) & 1);
             const uint32_t b_addr = smem_u32(Bs + bb * 4 * kGPBytes);
@@ -146,7 +152,7 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         const int m = ew * 32 + lane;
         mbar_wait(done, 0);
         tc_fence_after();
-        if ((int)blockIdx.x < p.ktiles) {
+        if (kt_first < p.ktiles) {
             for (int mb = 0; mb < nmb; ++mb) {
                 const int R = mb * 128 + m;
                 const int vi = R / p.Cin, ci = R - vi * p.Cin;
@@ -220,11 +226,12 @@ __global__ void __launch_bounds__(256) pair_reduce_da_kernel(const float* __rest
 using namespace istgcn;
 
 ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, const float* Wc,
-                                     const int* items, int nitems, const int* v_list, int npairs,
+                                     const int* items, int nitems, const int* ctas, int nctas,
+                                     const int* v_list, int npairs,
                                      const int* entry_pair, const int* k_ptr, int nnz, float* P_ws,
                                      float* dWc, float* dvals, int frames, int V, int K, int Cin, int Cout,
                                      int nb, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(dz && x && vals && Wc && items && v_list && entry_pair && k_ptr && P_ws && dWc && dvals,
+    ISTGCN_REQUIRE(dz && x && vals && Wc && items && ctas && v_list && entry_pair && k_ptr && P_ws && dWc && dvals,
                    ISTGCN_E_ARG, "gcn_pair_grads: null pointer");
     ISTGCN_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && V >= 1 && V <= 64 && K >= 1,
                    ISTGCN_E_SHAPE, "gcn_pair_grads: Cin=%d Cout=%d V=%d unsupported", Cin, Cout, V);
@@ -233,10 +240,11 @@ ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const floa
     ISTGCN_REQUIRE(((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(x) |
                      reinterpret_cast<uintptr_t>(P_ws) | reinterpret_cast<uintptr_t>(Wc)) & 15) == 0,
                    ISTGCN_E_ARG, "gcn_pair_grads: pointers must be 16-byte aligned");
-    if (frames == 0 || nitems == 0 || nnz == 0) return 0;
+    if (frames == 0 || nitems == 0 || nctas == 0 || nnz == 0) return 0;
     cudaStream_t st = (cudaStream_t)s;
     tc::PairParams p{};
-    p.P = P_ws; p.items = reinterpret_cast<const int4*>(items); p.v_list = v_list;
+    p.P = P_ws; p.items = reinterpret_cast<const int4*>(items); p.ctas = reinterpret_cast<const int4*>(ctas);
+    p.v_list = v_list;
     p.frames = frames; p.V = V; p.Cin = Cin; p.Cout = Cout; p.nb = nb;
     p.ktiles = (frames + tc::kGPRows - 1) / tc::kGPRows;
     CUtensorMap xmap, dmap;
@@ -244,10 +252,7 @@ ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const floa
     if (int e = tc::encode_joint_frames_map(&dmap, dz, frames, V, Cout, tc::kGPRows)) return e;
     cudaFuncSetAttribute(tc::gcn_pair_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          tc::SmemGP::total);
-    int nx = num_sms() / nitems;
-    if (nx < 1) nx = 1;
-    if (nx > p.ktiles) nx = p.ktiles;
-    tc::gcn_pair_tc_kernel<<<dim3(nx, nitems), tc::kThreadsGP, tc::SmemGP::total, st>>>(xmap, dmap, p);
+    tc::gcn_pair_tc_kernel<<<nctas, tc::kThreadsGP, tc::SmemGP::total, st>>>(xmap, dmap, p);
     if (int e = finish_launch("gcn_pair_tc")) return e;
     const int CC = Cin * Cout;
     long long blocks = ((long long)K * CC + 255) / 256;

@@ -138,9 +138,9 @@ def _gcn_pair_ok(cin, cout):
 
 
 def gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout):
-    items, nb = pat.pair_items(Cin, Cout)
+    items, nb, ctas = pat.pair_items(Cin, Cout)
     ws = torch.zeros(pat.npairs, Cin, Cout, device=dz.device, dtype=torch.float32)
-    call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], pat.pair_v, pat.npairs, pat.entry_pair,
+    call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], ctas, ctas.shape[0], pat.pair_v, pat.npairs, pat.entry_pair,
          pat.k_ptr, pat.nnz, ws, dWc, dvals, frames, V, K, Cin, Cout, nb)
 
 

@@ -74,7 +74,17 @@ class SparsePattern(object):
                     for col0 in range(0, cout, nb):
                         rows.append((w_, first, min(per_item, hi - first), col0))
             items = torch.as_tensor(np.asarray(rows, dtype=np.int32).reshape(-1, 4)).to(self._device)
-            hit = self._pair_items[(cin, cout)] = (items, nb)
+            # thread blocks per item in proportion to its cost (M-blocks of 128 stacked rows + the
+            # shared dz atoms), about one block per SM in total; block j of an item with s blocks
+            # takes the K-tiles j, j + s, j + 2s, ...
+            sms = torch.cuda.get_device_properties(self._device).multi_processor_count \
+                if torch.cuda.is_available() else 148
+            cost = np.array([(r[2] * cin + 127) // 128 + 0.5 for r in rows])
+            waves = max(1, -(-2 * len(rows) // sms))        # many items: a few short waves instead of 1.x long ones
+            share = np.maximum(1, np.floor(cost / cost.sum() * sms * waves)).astype(int)
+            ctas = [(i, j, int(s_), 0) for i, s_ in enumerate(share) for j in range(int(s_))]
+            ctas = torch.as_tensor(np.asarray(ctas, dtype=np.int32).reshape(-1, 4)).to(self._device)
+            hit = self._pair_items[(cin, cout)] = (items, nb, ctas)
         return hit
 
     @classmethod
