@@ -80,8 +80,14 @@ class SparsePattern(object):
             sms = torch.cuda.get_device_properties(self._device).multi_processor_count \
                 if torch.cuda.is_available() else 148
             cost = np.array([(r[2] * cin + 127) // 128 + 0.5 for r in rows])
-            waves = max(1, -(-2 * len(rows) // sms))        # many items: a few short waves instead of 1.x long ones
-            share = np.maximum(1, np.floor(cost / cost.sum() * sms * waves)).astype(int)
+            # greedy apportionment (the next block goes to the slowest item) over 1 .. 4 waves of
+            # thread blocks: the fewest waves whose slowest block is within 20 % of the mean
+            for waves in range(max(1, -(-len(rows) // sms)), 5):
+                share = np.ones(len(rows), dtype=int)
+                for _ in range(max(0, sms * waves - len(rows))):
+                    share[int(np.argmax(cost / share))] += 1
+                if (cost / share).max() <= 1.2 * cost.sum() / share.sum():
+                    break
             ctas = [(i, j, int(s_), 0) for i, s_ in enumerate(share) for j in range(int(s_))]
             ctas = torch.as_tensor(np.asarray(ctas, dtype=np.int32).reshape(-1, 4)).to(self._device)
             hit = self._pair_items[(cin, cout)] = (items, nb, ctas)
