@@ -91,6 +91,18 @@ class AugmentSpec(object):
         return shift, move, t_out
 
 
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    """One copy stream per device for the whole process: the caching allocator pools memory per
+    stream, so a fresh stream per epoch would pay cudaMalloc for its staging tensors again."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
 class DevicePrefetcher(object):
     """Iterate a host loader of (data (N, C, T, V, M), label (N,)) batches as device tensors.
 
@@ -102,7 +114,7 @@ class DevicePrefetcher(object):
     def __init__(self, loader, device, augment=None):
         self.loader, self.device = loader, torch.device(device)
         self.augment = augment if augment is not None and augment.active else None
-        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream = _copy_stream(self.device)
         self.slots = [dict(), dict()]
         self.h2d_bytes = 0
 
