@@ -133,6 +133,9 @@ def algorithmic_bytes(kernel, batch, shape):
         elif kernel == 'bn_back_apply':   # residual branch of the two strided blocks: reads go, rres, writes dyr
             if res == 2:
                 per_launch.append(4 * r_out * 3 * cout)
+        elif kernel == 'gcn_pair_grads':  # weight + adjacency gradient in one pass: reads dz, x
+            if cin >= 32:
+                per_launch.append(4 * r_in * (cout + cin))
         elif kernel == 'gcn_tc_dvals':   # reads dz, x
             if cin >= 32:
                 per_launch.append(4 * r_in * (cout + cin))
