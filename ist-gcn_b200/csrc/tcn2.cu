@@ -488,164 +488,6 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
     for (int i = tid; i < BP; i += NTHR) atomicAdd(&p.dbeff[i], s_dbe[i]);
 }
 
-// ---- the same stage for C > 64: a warp walks ALL 64-channel slices of its 16 rows, so dh2 needs no
-// cross-warp hand-over (the slice-per-warp form above pays one __syncthreads per tile for it and ran
-// at 0.53-0.61 of the HBM peak against 0.76 at C = 64).  Per-slice state cannot stay in registers
-// over the slices, so the weight-gradient fragments of every (tile, slice) go to shared memory with
-// conflict-free reductions (plane / pair layout below) and dbu comes from column sums of the
-// staged du tile.
-template <int NT>
-__global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_wide_kernel(BwdUpP p) {
-    constexpr int BP = NT * 8, W = kT2HeavyWarps, NTHR = W * 32;
-    extern __shared__ __align__(16) float smem[];
-    const int C = p.C, S = C >> 6;
-    float* s_p = smem;                                              // p2, m12, c2, mean2: [4][C]
-    float2* s_w = reinterpret_cast<float2*>(smem + 4 * C);          // [S][4 jj][2 h][NT][32]
-    float* s_tile = smem + 4 * C + S * 8 * NT * 64;                 // [W warps][16][64]
-    float* s_dW = s_tile + W * 16 * 64;                             // [2*NT planes (e, j>>3)][C/2][8]
-    float* s_dbu = s_dW + BP * C;                                   // [C]
-    float* s_dbe = s_dbu + C;                                       // [BP]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    for (int i = tid; i < C; i += NTHR) {
-        s_p[i] = p.p2[i]; s_p[C + i] = p.m12[i]; s_p[2 * C + i] = p.c2[i]; s_p[3 * C + i] = p.mean2[i];
-    }
-    for (int i = tid; i < S * 8 * NT * 32; i += NTHR) {
-        const int l = i & 31, q = i >> 5;
-        const int nt = q % NT, h = (q / NT) & 1, jj = (q / (NT * 2)) & 3, sl = q / (NT * 8);
-        const int j = nt * 8 + (l >> 2), c0 = sl * 64 + jj * 16 + 4 * (l & 3) + 2 * h;
-        s_w[i] = make_float2(tff(p.Wu[j * C + c0]), tff(p.Wu[j * C + c0 + 1]));
-    }
-    for (int i = tid; i < BP * C + C + BP; i += NTHR) s_dW[i] = 0.f;
-    __syncthreads();
-    float* tile_s = s_tile + warp * 16 * 64;
-    const uint64_t eseed = effective_seed(p.seed, p.step);
-    float dbe[NT][2];
-#pragma unroll
-    for (int a = 0; a < NT; ++a) dbe[a][0] = dbe[a][1] = 0.f;
-    const int plane_sz = (C >> 1) * 8;
-    const long long ntiles = (p.rows + 15) >> 4;
-    for (long long tile = (long long)blockIdx.x * W + warp; tile < ntiles; tile += (long long)gridDim.x * W) {
-        const long long r0 = tile * 16 + g, r1 = r0 + 8;
-        const bool ok0 = r0 < p.rows, ok1 = r1 < p.rows;
-        float acch[NT][4];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acch[nt][i] = 0.f;
-        for (int sl = 0; sl < S; ++sl) {
-            const long long o0 = (ok0 ? r0 : p.rows - 1) * C + sl * 64 + 4 * t;
-            const long long o1 = (ok1 ? r1 : p.rows - 1) * C + sl * 64 + 4 * t;
-            float4 g0[4], g1[4], u0[4], u1[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                g0[jj] = lds4(p.go + o0 + jj * 16); u0[jj] = lds4(p.u + o0 + jj * 16);
-                g1[jj] = lds4(p.go + o1 + jj * 16); u1[jj] = lds4(p.u + o1 + jj * 16);
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int c = sl * 64 + jj * 16 + 4 * t;
-                const float4 pv = *reinterpret_cast<const float4*>(s_p + c);
-                const float4 mv = *reinterpret_cast<const float4*>(s_p + C + c);
-                const float4 cv = *reinterpret_cast<const float4*>(s_p + 2 * C + c);
-                const float4 nv = *reinterpret_cast<const float4*>(s_p + 3 * C + c);
-                float ga[4] = {g0[jj].x, g0[jj].y, g0[jj].z, g0[jj].w};
-                float gb[4] = {g1[jj].x, g1[jj].y, g1[jj].z, g1[jj].w};
-                if (p.drop_p > 0.f) {
-                    bool ka[4], kb[4];
-                    dropout_keep4(eseed, (uint64_t)((o0 + jj * 16) >> 2), p.drop_p, ka);
-                    dropout_keep4(eseed, (uint64_t)((o1 + jj * 16) >> 2), p.drop_p, kb);
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        ga[e] = ka[e] ? ga[e] * p.keep_scale : 0.f;
-                        gb[e] = kb[e] ? gb[e] * p.keep_scale : 0.f;
-                    }
-                }
-                float da[4], db[4];
-                da[0] = bn_back(ga[0], u0[jj].x, pv.x, mv.x, cv.x, nv.x);
-                da[1] = bn_back(ga[1], u0[jj].y, pv.y, mv.y, cv.y, nv.y);
-                da[2] = bn_back(ga[2], u0[jj].z, pv.z, mv.z, cv.z, nv.z);
-                da[3] = bn_back(ga[3], u0[jj].w, pv.w, mv.w, cv.w, nv.w);
-                db[0] = bn_back(gb[0], u1[jj].x, pv.x, mv.x, cv.x, nv.x);
-                db[1] = bn_back(gb[1], u1[jj].y, pv.y, mv.y, cv.y, nv.y);
-                db[2] = bn_back(gb[2], u1[jj].z, pv.z, mv.z, cv.z, nv.z);
-                db[3] = bn_back(gb[3], u1[jj].w, pv.w, mv.w, cv.w, nv.w);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (!ok0) da[e] = 0.f;
-                    if (!ok1) db[e] = 0.f;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t a[4] = {tf(da[2 * h]), tf(db[2 * h]), tf(da[2 * h + 1]), tf(db[2 * h + 1])};
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        mma(acch[nt], a, s_w[(((sl * 4 + jj) * 2 + h) * NT + nt) * 32 + lane]);
-                }
-                const int pc = (jj * 16 + 4 * t) ^ swz(g);
-                st4(tile_s + g * 64 + pc, make_float4(da[0], da[1], da[2], da[3]));
-                st4(tile_s + (g + 8) * 64 + pc, make_float4(db[0], db[1], db[2], db[3]));
-            }
-            __syncwarp();
-            // dWu[j][c] += h2[rows][j] du[rows][c] for this slice: fresh fragments, flushed to shared memory
-            float accW[8][4];
-#pragma unroll
-            for (int a = 0; a < 8; ++a)
-#pragma unroll
-                for (int b = 0; b < 4; ++b) accW[a][b] = 0.f;
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-                uint32_t a[4];
-                load_small_at<NT>(a, p.h2, tile * 16, p.rows, ks, g, t);
-                rows_mma(accW, a, tile_s, ks, g, t);
-            }
-            // element (j = g + 8*(i>>1), c = sl*64 + 8nt + 2t + (i&1)) -> plane (i&1, i>>1), pair index c>>1,
-            // slot g: the 32 lanes of one reduction hit 32 different banks (8t + g)
-#pragma unroll
-            for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-                for (int i = 0; i < (NT == 2 ? 4 : 2); ++i)
-                    atomicAdd(&s_dW[((i & 1) * NT + (i >> 1)) * plane_sz + (sl * 32 + nt * 4 + t) * 8 + g], accW[nt][i]);
-            // dbu[c] += column sums of the staged tile (lane = column, both halves of the slice)
-            {
-                float c0s = 0.f, c1s = 0.f;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) {
-                    c0s += tile_s[r * 64 + (lane ^ swz(r))];
-                    c1s += tile_s[r * 64 + ((lane + 32) ^ swz(r))];
-                }
-                atomicAdd(&s_dbu[sl * 64 + lane], c0s);
-                atomicAdd(&s_dbu[sl * 64 + 32 + lane], c1s);
-            }
-            __syncwarp();
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const int c = nt * 8 + 2 * t;
-            if (ok0)
-                *reinterpret_cast<float2*>(p.dh2 + r0 * BP + c) = make_float2(rnd_tf32(acch[nt][0]), rnd_tf32(acch[nt][1]));
-            if (ok1)
-                *reinterpret_cast<float2*>(p.dh2 + r1 * BP + c) = make_float2(rnd_tf32(acch[nt][2]), rnd_tf32(acch[nt][3]));
-            dbe[nt][0] += acch[nt][0] + acch[nt][2];
-            dbe[nt][1] += acch[nt][1] + acch[nt][3];
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const float v = group_sum_g(dbe[nt][e]);
-            if (g == 0) atomicAdd(&s_dbe[nt * 8 + 2 * t + e], v);
-        }
-    __syncthreads();
-    for (int i = tid; i < BP * C; i += NTHR) {                      // plane / pair layout -> dWu[j][c]
-        const int slot = i & 7, pair = (i >> 3) % (C >> 1), plane = i / plane_sz;
-        const int j = slot + 8 * (plane % NT), c = 2 * pair + plane / NT;
-        atomicAdd(&p.dWu[j * C + c], s_dW[i]);
-    }
-    for (int i = tid; i < C; i += NTHR) atomicAdd(&p.dbu[i], s_dbu[i]);
-    for (int i = tid; i < BP; i += NTHR) atomicAdd(&p.dbeff[i], s_dbe[i]);
-}
-
 // ============================================================================ backward: down
 struct BwdDownP {
     const float *dh1, *z, *mean, *scale, *beta, *rstd, *Wd;
@@ -860,17 +702,7 @@ ISTGCN_API int istgcn_tcn2_bwd_up(const float* go, const float* u, const float* 
     const size_t smem = sizeof(float) * (4 * C + S * 8 * nt * 64 + W * 16 * 64 + 2 * W * 32 * nt * 4 +
                                          bp * C + C + bp);
     const int grid = grid2(((rows + 15) / 16 + W / S - 1) / (W / S), 3);
-    if (S > 1) {        // a warp walks all slices of its rows: no cross-warp hand-over
-        const size_t smem_w = sizeof(float) * (4 * C + S * 8 * nt * 64 + W * 16 * 64 + bp * C + C + bp);
-        const int grid_w = grid2(((rows + 15) / 16 + W - 1) / W, 3);
-        if (nt == 1) {
-            set_smem2(tcn2_bwd_up_wide_kernel<1>, smem_w);
-            tcn2_bwd_up_wide_kernel<1><<<grid_w, W * 32, smem_w, (cudaStream_t)s>>>(p);
-        } else {
-            set_smem2(tcn2_bwd_up_wide_kernel<2>, smem_w);
-            tcn2_bwd_up_wide_kernel<2><<<grid_w, W * 32, smem_w, (cudaStream_t)s>>>(p);
-        }
-    } else if (nt == 1) {
+    if (nt == 1) {
         set_smem2(tcn2_bwd_up_kernel<1>, smem);
         tcn2_bwd_up_kernel<1><<<grid, W * 32, smem, (cudaStream_t)s>>>(p);
     } else {
