@@ -180,11 +180,20 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
                                       uint64_t seed0, const unsigned long long* step) {
     const uint64_t seed = effective_seed(seed0, step);
     const int c4 = C >> 2;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % c4) * 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // The grid stride is a multiple of C/4 (the launcher sees to it), so a thread stays on ONE group
+    // of four channels: the BatchNorm coefficients live in registers and no 64-bit modulo sits in the
+    // loop (the per-iteration `i % c4` + six coefficient loads made this kernel issue-bound at 0.78 of
+    // the HBM peak).
+    const int c = (int)(i % c4) * 4;
+    const float4 mu = ld4(mean2 + c), sc = ld4(scale2 + c), be = ld4(beta2 + c);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), a = m, b = m;
+    if (mode == 2) { m = ld4(mean_r + c); a = ld4(scale_r + c); b = ld4(beta_r + c); }
+    for (; i < n4; i += stride) {
         const float4 uu = ld4(u + i * 4);
-        const float4 mu = ld4(mean2 + c), sc = ld4(scale2 + c), be = ld4(beta2 + c);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mode != 0) r = ld4(res + i * 4);
         float y[4] = {bn_apply(uu.x, mu.x, sc.x, be.x), bn_apply(uu.y, mu.y, sc.y, be.y),
                       bn_apply(uu.z, mu.z, sc.z, be.z), bn_apply(uu.w, mu.w, sc.w, be.w)};
         if (drop_p > 0.f) {
@@ -194,11 +203,8 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
             for (int j = 0; j < 4; ++j) y[j] = keep[j] ? y[j] * keep_scale : 0.f;
         }
         if (mode == 1) {
-            const float4 r = ld4(res + i * 4);
             y[0] += r.x; y[1] += r.y; y[2] += r.z; y[3] += r.w;
         } else if (mode == 2) {
-            const float4 r = ld4(res + i * 4);
-            const float4 m = ld4(mean_r + c), a = ld4(scale_r + c), b = ld4(beta_r + c);
             y[0] += bn_apply(r.x, m.x, a.x, b.x); y[1] += bn_apply(r.y, m.y, a.y, b.y);
             y[2] += bn_apply(r.z, m.z, a.z, b.z); y[3] += bn_apply(r.w, m.w, a.w, b.w);
         }
@@ -452,7 +458,12 @@ ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const f
     const int mode = res == nullptr ? 0 : (scale_r == nullptr ? 1 : 2);
     const long long n4 = rows * C / 4;
     if (n4 == 0) return 0;
-    block_tail_fwd_kernel<<<ew_grid(n4, 256), 256, 0, (cudaStream_t)s>>>(
+    // grid stride = blocks * threads must be a multiple of C/4: a thread then keeps its channel group
+    const int c4 = C / 4;
+    int threads = 256;
+    while (threads % c4 != 0 && threads < 1024) threads += 32;
+    ISTGCN_REQUIRE(threads % c4 == 0, ISTGCN_E_SHAPE, "block_tail_fwd: C=%d has no block size that is a multiple of C/4", C);
+    block_tail_fwd_kernel<<<ew_grid(n4, threads), threads, 0, (cudaStream_t)s>>>(
         u, mean2, scale2, beta2, res, mean_r, scale_r, beta_r, out, n4, C, mode, drop_p,
         1.f / (1.f - drop_p), drop_seed, drop_step);
     return finish_launch("block_tail_fwd");

@@ -277,9 +277,12 @@ def _tf32_torch(flag):
     return old
 
 
-@pytest.mark.parametrize('cin,cout,stride,t', [
-    (64, 64, 1, 300), (64, 128, 2, 300), (128, 128, 1, 150), (128, 256, 2, 150), (256, 256, 1, 75)])
-def test_block_at_baseline_shape_tf32(env, cin, cout, stride, t):
+@pytest.mark.parametrize('cin,cout,stride,t,layout,nm', [
+    (64, 64, 1, 300, 'ntu-rgb+d_sym', 128), (64, 128, 2, 300, 'ntu-rgb+d_sym', 128),
+    (128, 128, 1, 150, 'ntu-rgb+d_sym', 128), (128, 256, 2, 150, 'ntu-rgb+d_sym', 128),
+    (256, 256, 1, 75, 'ntu-rgb+d_sym', 128),
+    (128, 128, 1, 150, 'openpose_sym', 512)])       # BASELINE cfg 3: Kinetics-skeleton, batch 256, V = 18
+def test_block_at_baseline_shape_tf32(env, cin, cout, stride, t, layout, nm):
     """One IST-GCN block at the BASELINE.json cfg-2 layer shape (batch 64 -> NM = 128 person
     sequences, V = 25: 38 400 / 19 200 / 9 600 frames, every persistent CTA walks many tiles) in
     the benchmarked 'tf32' mode vs the oracle in fp64 ON THE GPU; gradients calibrated against
@@ -289,8 +292,8 @@ def test_block_at_baseline_shape_tf32(env, cin, cout, stride, t):
     from oracle import model_ref
     dev = torch.device('cuda')
     gen = torch.Generator().manual_seed(cin + cout + stride)
-    g = Graph('ntu-rgb+d_sym', 'spatial_3_sym')
-    K, V, nm = 4, 25, 128
+    g = Graph(layout, 'spatial_3_sym')
+    K, V = 4, g.A.shape[1]
     blk = st_gcn(cin, cout, (9, K), stride, residual=True)
     with torch.no_grad():
         for m in blk.modules():
