@@ -602,10 +602,13 @@ ISTGCN_API int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_
     static const bool force_v1 = getenv("ISTGCN_GCN_TC_V1") != nullptr;
     if (!force_v1 && bn_p == nullptr && in_out == nullptr && map_side == 0 && CinPad == Cin &&
         (add_rows == nullptr || (add_rows == out && stat_sum == nullptr)) &&
-        tc::gcn_tc2_eligible(V, K, Cin, Cout, in, out))
-        return tc::launch_gcn_tc2(in, w_rows, vals, lptr, lsrc, lid, bias_k, colsum, out,
-                                  add_rows != nullptr, stat_sum, stat_sumsq, frames, V, K, Cin, Cout,
-                                  (cudaStream_t)s);
+        tc::gcn_tc2_eligible(V, K, Cin, Cout, in, out)) {
+        // ISTGCN_GCN_TC_V2=1 keeps the lane-mask form of the aggregation (gcn_tc2.cu)
+        static const bool force_v2 = getenv("ISTGCN_GCN_TC_V2") != nullptr;
+        auto launch = force_v2 ? tc::launch_gcn_tc2 : tc::launch_gcn_tc3;
+        return launch(in, w_rows, vals, lptr, lsrc, lid, bias_k, colsum, out, add_rows != nullptr, stat_sum,
+                      stat_sumsq, frames, V, K, Cin, Cout, (cudaStream_t)s);
+    }
     tc::GcnTcParams p{in, in2, {bn_p, bn_m1, bn_c, bn_mu}, vals, lptr, lsrc, lid, bias_k, colsum,
                       add_rows, out, in_out, stat_sum, stat_sumsq, frames, V, K, Cin, CinPad, Cout,
                       nnz, 0, {0, 0, 1, 0}, {0, 0, 1, 0}, 0};

@@ -367,6 +367,11 @@ int launch_gcn_tc2(const float* in, const float* w_rows, const float* vals, cons
                    const int* lsrc, const int* lid, const float* bias_k, const float* colsum, float* out,
                    int reduce, double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
                    int Cout, cudaStream_t st);
+// third-generation engine (gcn_tc3.cu): partitions on the lanes + block exchange
+int launch_gcn_tc3(const float* in, const float* w_rows, const float* vals, const int* lptr,
+                   const int* lsrc, const int* lid, const float* bias_k, const float* colsum, float* out,
+                   int reduce, double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
+                   int Cout, cudaStream_t st);
 // second-generation weight-gradient kernel (gcn_tc_dw2.cu)
 bool gcn_tc_dw2_eligible(int V, int K, int Cin, int Cout);
 int launch_gcn_tc_dw2(const float* dz, const float* x, const float* vals, const int* lptr,
