@@ -90,7 +90,9 @@ struct GcnTc3Params {
     const float *bias_k, *colsum;
     double *stat_sum, *stat_sumsq;
     int frames, V, K, Cin, Cout, tiles, reduce;
-    int variant;        // timing experiments only (ISTGCN_TC3_VARIANT, results are wrong when != 0)
+    int variant;        // 0 except in ISTGCN_TC3_PROF builds: ablation bits for timing experiments (1 exchange
+                        // without shared-memory traffic, 2 no MMA 1, 4 no epilogue work, 8 no exchange,
+                        // 16 no weight reloads, 32 / 64 / 128 no sums / bias / stores; results are wrong)
 };
 
 __device__ __forceinline__ void named_bar(int id, int threads) {
@@ -243,6 +245,8 @@ gcn_tc3_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
     const int nchunk = p.Cin / 32;
     const int nbox = K * NU;                            // weight boxes per slice (partition, column half)
     const int ngrp = (nbox + GW - 1) / GW;              // weight stages per slice
+    // the whole weight set fits the ring exactly (Cin = Cout = 64): load it once, never release it
+    const bool w_resident = nchunk * ngrp == NW;
     const int my_tiles = p.tiles > (int)blockIdx.x
                              ? (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -310,6 +314,7 @@ gcn_tc3_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                 for (int g = 0; g < ngrp; ++g, ++it) {
                     const int sb = it % NW;
                     const int bn = min(GW, nbox - g * GW);
+                    if (w_resident && t > 0) continue;
                     mbar_wait(&b_empty[sb], ((it / NW) & 1) ^ 1);
                     if ((p.variant & 16) && it >= (uint32_t)NW) {
                         if (elect_one()) mbar_arrive(&b_full[sb]);
@@ -413,7 +418,7 @@ gcn_tc3_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
 #pragma unroll
                 for (int g = 0; g < 4 * NU / GW; ++g) {
                     if (g >= ngrp) break;
-                    {
+                    if (!w_resident || t == 0) {
                         PROF_T0();
                         mbar_wait(&b_full[wsb], wph);
                         PROF_ADD(w_b);
@@ -433,7 +438,7 @@ gcn_tc3_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
                                                    (k | ks) ? 1u : (ch ? 1u : 0u));
                             }
                         }
-                        tc_commit(&b_empty[wsb]);
+                        if (!w_resident) tc_commit(&b_empty[wsb]);
                         if (ch == (uint32_t)nchunk - 1 && g == ngrp - 1) tc_commit(&t_full[buf]);
                     }
                     __syncwarp();
@@ -474,6 +479,19 @@ gcn_tc3_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             for (int k = 0; k < 4; ++k)
                 if (k < K) cs[k] = p.colsum[k * V + w];
         }
+        // one column block per warp (Cout <= 64): its bias term sum_k colsum[k][w] * bias_k[n] stays in
+        // registers for the whole kernel; otherwise it is rebuilt per block from shared memory
+        float bt[NB == 1 ? 32 : 1];
+        if (NB == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                float a = 0.f;
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (p.bias_k && k < K) a = fmaf(cs[k], s_bias[k * NCOLS + half * 32 + j], a);
+                bt[NB == 1 ? j : 0] = a;
+            }
+        }
         // column `lane` of staging row r sits at srow[r & 7] + (r >> 3) * 1024
         const uint8_t* srow[8];
 #pragma unroll
@@ -495,7 +513,10 @@ gcn_tc3_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__
             // one 32-column block: bias term, staging tile, TMA store / reduce-add, BatchNorm sums
             auto finish_block = [&](float (&v)[32], int c0, int ib) {
                 if (p.variant & 4) return;
-                if (p.bias_k && !(p.variant & 64)) {
+                if (NB == 1) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] += bt[NB == 1 ? j : 0];
+                } else if (p.bias_k && !(p.variant & 64)) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         if (k >= K) break;
@@ -627,8 +648,10 @@ int launch_gcn_tc3(const float* in, const float* w_rows, const float* vals, cons
                    int Cout, cudaStream_t st) {
     GcnTc3Params p{vals, lptr, lsrc, lid, bias_k, colsum, stat_sum, stat_sumsq, frames, V, K, Cin, Cout,
                    (frames + kFr3 - 1) / kFr3, reduce, 0};
+#if ISTGCN_TC3_PROF
     static const char* var_env = getenv("ISTGCN_TC3_VARIANT");
     if (var_env) p.variant = atoi(var_env);
+#endif
     const int ncols = Cout > 128 ? 256 : (Cout > 64 ? 128 : 64);
     CUtensorMap xmap, wmap, omap;
     if (int e = encode_frame_slices(&xmap, in, frames, V, Cin)) return e;
