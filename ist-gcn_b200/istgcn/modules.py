@@ -127,6 +127,7 @@ class BlockPrep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dvals, dWc, dbt, _dcolsum, dWd, dbd, dWeff, dbeff, dWu, dWr, dbtr):
         from ._lib import call
+        ops.wait_pair_grads(dWc)          # the block's weight / adjacency gradient ran on its own stream
         bias, colsum, W1, b1, W2, b2, W3, b3, m_imp = ctx.saved_tensors
         K, V, Cin, Cout, b, bp = ctx.dims
         A1, A2, A3 = ctx.bufs
@@ -205,6 +206,7 @@ class FusedBlockMixin(object):
         ALL blocks on a side stream ahead of the block kernels (FusedModelMixin._trunk); autograd
         runs their backward on that stream too, off the critical path."""
         conv = self._gcn_conv()
+        self._prep_fused = False
         vals, wc, biasterm, w2 = graph_conv_operands(conv.weight, conv.bias, adjs, pattern)
         wd, bd, weff, beff, wu, bu = bottleneck_tcn_operands(
             self.conv_1x1_start, self.tcn_1, self.tcn_2, self.tcn_3, self.conv_1x1_end, m_imp)
@@ -245,6 +247,7 @@ class FusedBlockMixin(object):
         tc_ops = (w2, None, None) if conv.bias is None else (w2, conv.bias.detach().view(K, cout), colsum)
         if self._res_mode != 2:
             wr = btr = None
+        self._prep_fused = True           # BlockPrep.backward joins the asynchronous pair-gradient kernel
         return (vals, wc, biasterm, tc_ops, wd, bd, weff, beff, wu, self.conv_1x1_end.bias, wr, btr)
 
     def forward_cl(self, x, adjs, m_imp, pattern, operands=None):
@@ -254,6 +257,7 @@ class FusedBlockMixin(object):
         cfg.seed = next(_seed_counter) * 0x9E3779B1 + torch.initial_seed()
         if operands is None:
             operands = self.prepare_operands(adjs, m_imp, pattern)
+        cfg.pair_async = getattr(self, '_prep_fused', False)
         vals, wc, biasterm, w2, wd, bd, weff, beff, wu, bu, wr, btr = operands
         bn1, bn2 = self.tcn_start[0], self.tcn_end[0]
         bnr_w = bnr_b = None

@@ -144,6 +144,52 @@ def gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout):
          pat.k_ptr, pat.nnz, ws, dWc, dvals, frames, V, K, Cin, Cout, nb)
 
 
+# The weight / adjacency gradient of a block is needed only by the parameter-regrouping backward
+# (modules.BlockPrep.backward) at the very end of the backward pass, and its kernel is bound by the
+# tensor pipe and L2 while the kernels that follow it on the main stream (the next block's
+# element-wise and temporal backward) are bound by HBM: it runs on its own stream, and the consumer
+# waits for the event registered under the gradient's address.
+_pair_streams = {}
+_pair_events = {}
+
+
+def _pair_async_enabled():
+    return os.environ.get('ISTGCN_PAIR_ASYNC', '1') != '0'
+
+
+def _pair_stream(device):
+    key = (device.type, device.index)
+    if key not in _pair_streams:
+        _pair_streams[key] = torch.cuda.Stream(device=device)
+    return _pair_streams[key]
+
+
+def gcn_pair_grads_async(dz, x, vals, Wc, pat, dWc, dvals, owner, frames, V, K, Cin, Cout):
+    """gcn_pair_grads on the pair stream, ordered after everything already on the current stream.
+    `owner` is the allocation dWc / dvals are views of.  wait_pair_grads(dWc) joins."""
+    main = torch.cuda.current_stream(dz.device)
+    ps = _pair_stream(dz.device)
+    ev0 = torch.cuda.Event()
+    ev0.record(main)
+    ps.wait_event(ev0)
+    with torch.cuda.stream(ps):
+        gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout)
+        ev1 = torch.cuda.Event()
+        ev1.record(ps)
+    for t in (dz, x, vals, Wc, owner):
+        t.record_stream(ps)
+    _pair_events[dWc.data_ptr()] = ev1
+
+
+def wait_pair_grads(dWc):
+    """The current stream waits for the pair kernel that writes ``dWc`` (no-op if there is none)."""
+    if dWc is None:
+        return
+    ev = _pair_events.pop(dWc.data_ptr(), None)
+    if ev is not None:
+        torch.cuda.current_stream(dWc.device).wait_event(ev)
+
+
 def _gcn_small_ok(cin, cout):
     """The first block's narrow-input graph convolution (csrc/gcn_small.cu)."""
     # fast mode only: the fp32-grade parity mode keeps one arithmetic (the 3xTF32 engine) for every
@@ -342,7 +388,9 @@ class STBlock(Function):
                      pat.nnz, None, None, add_in, gin, dz, None, None, NM * T, V, K, Cout, Cout, Cin,
                      0, 0, 1, 0, 0)
             pair = dbt_done and _gcn_pair_ok(Cin, Cout)
-            if pair:      # weight AND adjacency gradient from one pass over (dz, x)
+            if pair and getattr(cfg, 'pair_async', False) and _pair_async_enabled():
+                gcn_pair_grads_async(dz, x, vals, Wc, pat, dWc, dvals, flat, NM * T, V, K, Cin, Cout)
+            elif pair:    # weight AND adjacency gradient from one pass over (dz, x)
                 gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, NM * T, V, K, Cin, Cout)
             else:
                 call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dvals,
