@@ -152,7 +152,7 @@ int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const fl
  * non-zero pattern on the tensor core (both operands by TMA as they lie in HBM), then
  *   dWc[k*Cin+ci][c] += sum_(v,w) vals[(k,v,w)] P[(v,w)][ci][c],   dvals[(k,v,w)] += <Wc[k], P[(v,w)]>.
  * v_list[npairs]: source joints grouped by destination joint; items[nitems][4] = {w, first index into
- * v_list, count, first output column}: at most 512/nb * 128/Cin pairs and nb (<= 128) columns each;
+ * v_list, count, first output column}: at most 512/nb * 128/Cin pairs and nb (<= 128, or 256) columns each;
  * ctas[nctas][4] = {item, first 64-frame K-tile, K-tile stride, 0}: one thread block each (the caller
  * gives an item thread blocks in proportion to its pairs so that all blocks finish together);
  * entry_pair[nnz]: pair index of every canonical entry; k_ptr[K+1]: entries of partition k (canonical

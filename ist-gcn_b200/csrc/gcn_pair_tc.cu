@@ -28,7 +28,7 @@ namespace tc {
 constexpr int kThreadsGP = 256;
 constexpr int kGPRows = 64;                       // frames of a K-tile atom
 constexpr int kGPBytes = kGPRows * 128;           // [64 frames][32 channels]
-constexpr int kGPAst = 4;                         // ring of M-block stages (4 atoms each)
+constexpr int kGPAst = 4;                         // ring of M-block stages (4 atoms each); 3 at N = 256
 
 struct PairParams {
     float* P;                                     // [npairs][Cin][Cout]
@@ -39,9 +39,10 @@ struct PairParams {
 };
 
 struct SmemGP {
-    static constexpr int a_off = 0;                                   // kGPAst x 4 atoms
-    static constexpr int b_off = a_off + kGPAst * 4 * kGPBytes;       // 2 x (nb/32 <= 4) atoms
-    static constexpr int bar_off = b_off + 2 * 4 * kGPBytes;
+    // N-chunk <= 128: 4 M-block stages (128 KB) + 2 x 4 dz atoms (64 KB); N-chunk 256: 3 stages
+    // (96 KB) + 2 x 8 dz atoms (128 KB); the dz buffers start right behind the ring
+    static constexpr int a_off = 0;
+    static constexpr int bar_off = 3 * 4 * kGPBytes + 2 * 8 * kGPBytes;
     static constexpr int kNumBars = 2 * kGPAst + 4 + 1;
     static constexpr int total = bar_off + kNumBars * 8 + 16;
 };
@@ -52,7 +53,8 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     using L = SmemGP;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* As = smem + L::a_off;
-    uint8_t* Bs = smem + L::b_off;
+    const int ast = p.nb > 128 ? 3 : kGPAst;
+    uint8_t* Bs = smem + L::a_off + ast * 4 * kGPBytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + kGPAst;
@@ -98,12 +100,12 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[bb], (uint32_t)kGPBytes * natom);
                 for (int j = 0; j < natom; ++j)
-                    tma_load_3d(Bs + (bb * 4 + j) * kGPBytes, &dmap, &b_full[bb], col0 + 32 * j, w, f0);
+                    tma_load_3d(Bs + (bb * natom + j) * kGPBytes, &dmap, &b_full[bb], col0 + 32 * j, w, f0);
             }
             __syncwarp();
             for (int mb = 0; mb < nmb; ++mb, ++ita) {
-                const int sa = ita % kGPAst;
-                mbar_wait(&a_empty[sa], ((ita / kGPAst) & 1) ^ 1);
+                const int sa = ita % ast;
+                mbar_wait(&a_empty[sa], ((ita / ast) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&a_full[sa], (uint32_t)kGPBytes * 4);
                     for (int j = 0; j < 4; ++j) {
@@ -125,10 +127,10 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
         for (int kt_i = kt_first; kt_i < p.ktiles; kt_i += kt_step, ++itb) {
             const int bb = itb & 1;
             mbar_wait(&b_full[bb], (itb >> 1) & 1);
-            const uint32_t b_addr = smem_u32(Bs + bb * 4 * kGPBytes);
+            const uint32_t b_addr = smem_u32(Bs + bb * natom * kGPBytes);
             for (int mb = 0; mb < nmb; ++mb, ++ita) {
-                const int sa = ita % kGPAst;
-                mbar_wait(&a_full[sa], (ita / kGPAst) & 1);
+                const int sa = ita % ast;
+                mbar_wait(&a_full[sa], (ita / ast) & 1);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a_addr = smem_u32(As + sa * 4 * kGPBytes);
@@ -235,8 +237,8 @@ ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const floa
                    ISTGCN_E_ARG, "gcn_pair_grads: null pointer");
     ISTGCN_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && V >= 1 && V <= 64 && K >= 1,
                    ISTGCN_E_SHAPE, "gcn_pair_grads: Cin=%d Cout=%d V=%d unsupported", Cin, Cout, V);
-    ISTGCN_REQUIRE(nb >= 32 && nb <= 128 && nb % 32 == 0 && Cout % nb == 0, ISTGCN_E_SHAPE,
-                   "gcn_pair_grads: N-chunk %d must divide Cout=%d (32..128)", nb, Cout);
+    ISTGCN_REQUIRE(nb >= 32 && nb <= 256 && nb % 32 == 0 && (nb <= 128 || nb == 256) && Cout % nb == 0,
+                   ISTGCN_E_SHAPE, "gcn_pair_grads: N-chunk %d must divide Cout=%d (32..128 or 256)", nb, Cout);
     ISTGCN_REQUIRE(((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(x) |
                      reinterpret_cast<uintptr_t>(P_ws) | reinterpret_cast<uintptr_t>(Wc)) & 15) == 0,
                    ISTGCN_E_ARG, "gcn_pair_grads: pointers must be 16-byte aligned");

@@ -64,7 +64,11 @@ class SparsePattern(object):
         {w, first pair, pairs, first column}, N-chunk width)."""
         hit = self._pair_items.get((cin, cout))
         if hit is None:
-            nb = next(c for c in (128, 96, 64, 32) if cout % c == 0)
+            import os
+            # the widest N-chunk reads the fewest operand bytes per MAC (the kernel is bound by the
+            # L2 -> shared-memory operand stream): rows + columns per K-tile for rows x columns MACs
+            widths = (256, 128, 96, 64, 32) if os.environ.get('ISTGCN_PAIR_NB_MAX') != '128' else (128, 96, 64, 32)
+            nb = next(c for c in widths if cout % c == 0)
             per_item = max(1, (512 // nb) * 128 // cin)
             rows = []
             bounds = np.concatenate([[0], np.cumsum(np.bincount(self._pair_w, minlength=self.V))])
