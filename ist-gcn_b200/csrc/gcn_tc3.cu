@@ -60,8 +60,8 @@ struct Cfg3 {
     static constexpr int GW = NCOLS == 64 ? 4 : 1;                // weight boxes per stage (one barrier)
     static constexpr int WBYTES = WU * 128;
     static constexpr int WSTAGE = GW * WBYTES;                    // 32 / 16 / 16 KB
-    static constexpr int NW = NCOLS == 64 ? 2 : 4;
-    static constexpr int NX = NCOLS == 64 ? 5 : 3;
+    static constexpr int NW = NCOLS == 64 ? 2 : 5;                // weights arrive with L2 latency: deep ring
+    static constexpr int NX = NCOLS == 64 ? 5 : (NCOLS == 128 ? 3 : 2);
     static constexpr int NSB = 2;                                 // exchange buffers in tensor memory
     static constexpr int ND2 = NCOLS == 64 ? 2 : 1;
     // Cout >= 128: the accumulators (2 x 128 or 1 x 256 columns) + 2 x 128 exchange columns are all of
