@@ -151,18 +151,21 @@ int istgcn_gcn_tc(const float* in, const float* in2, const float* bn_p, const fl
  * above in the fast mode): P[(v,w)][ci][c] = sum_f x[(f,v)][ci] dz[(f,w)][c] for every joint pair of the
  * non-zero pattern on the tensor core (both operands by TMA as they lie in HBM), then
  *   dWc[k*Cin+ci][c] += sum_(v,w) vals[(k,v,w)] P[(v,w)][ci][c],   dvals[(k,v,w)] += <Wc[k], P[(v,w)]>.
- * v_list[npairs]: source joints grouped by destination joint; items[nitems][4] = {w, first index into
- * v_list, count, first output column}: at most 512/nb * 128/Cin pairs and nb (<= 128, or 256) columns each;
- * ctas[nctas][4] = {item, first 64-frame K-tile, K-tile stride, 0}: one thread block each (the caller
- * gives an item thread blocks in proportion to its pairs so that all blocks finish together);
+ * A work item is a BLOCK of the joint-pair pattern: ns source joints x nd destination joints x ncw
+ * output channels of each (the kernel is bound by the L2 -> shared-memory operand stream: rows + columns
+ * per K-tile for rows x columns MACs, so blocks should be as square as tensor memory allows):
+ * items[nitems][8] = {d0, nd, s0, ns, first output column, ncw, owned-cell mask (bit vi*nd + j), 0} with
+ * d0 / s0 indexing joints[]; ceil(ns*Cin/128) * nd*ncw <= 512, nd*ncw <= 256, ncw % 32 == 0, ns*nd <= 32;
+ * every pattern pair x column range must be owned by exactly one item.  pair_of[V*V]: (v*V + w) -> pair
+ * index or -1.  ctas[nctas][4] = {item, first 64-frame K-tile, K-tile stride, 0}: one thread block each
+ * (the caller gives an item thread blocks in proportion to its cost so that all blocks finish together);
  * entry_pair[nnz]: pair index of every canonical entry; k_ptr[K+1]: entries of partition k (canonical
  * order is sorted by k).  P_ws [npairs][Cin][Cout] caller-zeroed scratch; Cin, Cout multiples of 32.   */
 int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, const float* Wc,
-                          const int* items, int nitems, const int* ctas, int nctas,
-                          const int* v_list, int npairs,
-                          const int* entry_pair, const int* k_ptr, int nnz, float* P_ws, float* dWc,
-                          float* dvals, int frames, int V, int K, int Cin, int Cout, int nb,
-                          istgcn_stream_t s);
+                          const int* items, int nitems, const int* ctas, int nctas, const int* joints,
+                          const int* pair_of, int npairs, const int* entry_pair, const int* k_ptr, int nnz,
+                          float* P_ws, float* dWc, float* dvals, int frames, int V, int K, int Cin,
+                          int Cout, istgcn_stream_t s);
 
 /* ---- first block (in_channels <= 4: net/st_gcnold.py:46 `st_gcn(in_channels, 64, ...)`, the
  * graph convolution of tgcn.py:76-89 on a 3-channel input) on CUDA cores in full fp32
@@ -245,6 +248,7 @@ int istgcn_tcn_bwd(const float* go, const float* u, const float* p2, const float
  *   tcn2_bwd_up    du = p2*((gy - m12) - c2*(u - mean2)); dh2 = du Wu^T (written);
  *                  dWu += h2^T du, dbu += sum du, dbeff += sum dh2
  *   tcn2_bwd_conv  dh1 = transposed temporal conv of dh2 (written); dWeff += ..., dbd += sum dh1
+ *                  (two independent kernels: dh1 == NULL -> dWeff only, dWeff == NULL -> dh1 + dbd only)
  *   tcn2_bwd_down  g1 = (dh1 Wd^T) where relu(BN1(z)) > 0 (written); sg1 += sum g1,
  *                  sg1x += sum g1*zhat (double[C]); dWd += a^T dh1                              */
 int istgcn_tcn2_down(const float* z, const float* mean1, const float* scale1, const float* beta1,

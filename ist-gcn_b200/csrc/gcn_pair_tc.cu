@@ -14,10 +14,14 @@
 // (195 pairs x Cin x Cout: 3 ... 51 MB).  Replaces istgcn_gcn_tc_dw + istgcn_gcn_tc_dvals.
 //
 // Kernel structure = csrc/tconv_dw_tc.cu (MN-major operands, 32-byte-atom 128B swizzle): a K-tile is
-// 64 consecutive frames of ONE joint (3-D tensor map (C, V, frames), box 32 x 1 x 64); a work item
-// is one destination joint w with up to G of its source joints (stacked rows R = vi*Cin + ci, M-blocks
-// of 128 rows, accumulators resident in tensor memory) and one N-chunk of <= 128 output channels;
-// the dz atoms of (w, K-tile) are shared by all M-blocks of the item.
+// 64 consecutive frames of ONE joint (3-D tensor map (C, V, frames), box 32 x 1 x 64).  A work item is a
+// BLOCK of the joint-pair pattern: ns source joints (stacked rows R = vi*Cin + ci, M-blocks of 128 rows)
+// x nd destination joints (columns n = j*ncw + c, ncw channels of each), accumulators resident in tensor
+// memory (M-blocks x nd*ncw <= 512 columns).  The kernel is bound by the L2 -> shared-memory operand
+// stream, i.e. by (rows + columns) per K-tile for rows x columns MACs, so the host covers the pattern
+// with blocks as square as tensor memory allows (the skeleton's pattern is block-structured: 8 x 2 or
+// 4 x 4 blocks at Cin = 64 are ~90 % full) and marks the cells each block owns; cells of a block that
+// are not in the pattern (or belong to another block) are computed and dropped.
 //   warp 0      TMA producer        warp 1      MMA issuer (kind::tf32, M=128, N=nb, K=8 frames)
 //   warps 4-7   final epilogue: TMEM -> fp32 atomics into P
 #include "tc_common.cuh"
@@ -32,10 +36,11 @@ constexpr int kGPAst = 4;                         // ring of M-block stages (4 a
 
 struct PairParams {
     float* P;                                     // [npairs][Cin][Cout]
-    const int4* items;                            // {w, v0, nv, col0}
+    const int4* items;                            // two per item: {d0, nd, s0, ns}, {col0, ncw, owned-cell mask, 0}
     const int4* ctas;                             // per CTA: {item, first K-tile, K-tile stride, 0}
-    const int* v_list;                            // [npairs] source joints, grouped by destination w
-    int frames, V, Cin, Cout, nb, ktiles;
+    const int* joints;                            // destination / source joints of the items (d0 / s0 index it)
+    const int* pair_of;                           // [V*V] (v*V + w) -> pair index, -1 outside the pattern
+    int frames, V, Cin, Cout, ktiles;
 };
 
 struct SmemGP {
@@ -53,8 +58,7 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     using L = SmemGP;
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* As = smem + L::a_off;
-    const int ast = p.nb > 128 ? 3 : kGPAst;
-    uint8_t* Bs = smem + L::a_off + ast * 4 * kGPBytes;
+
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::bar_off);
     uint64_t* a_full = bars;
     uint64_t* a_empty = a_full + kGPAst;
@@ -68,11 +72,15 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
     // item CTAs in proportion to its M-blocks, so all CTAs advance through the frames at the same
     // pace (the x / dz K-tiles they share stay in L2) and finish together.
     const int4 cta = p.ctas[blockIdx.x];
-    const int4 item = p.items[cta.x];
+    const int4 item = p.items[2 * cta.x], item2 = p.items[2 * cta.x + 1];
     const int kt_first = cta.y, kt_step = cta.z;
-    const int w = item.x, v0 = item.y, nv = item.z, col0 = item.w;
-    const int nb = p.nb, natom = nb / 32;
-    const int rows_total = nv * p.Cin;
+    const int d0 = item.x, nd = item.y, s0 = item.z, ns = item.w;
+    const int col0 = item2.x, ncw = item2.y;
+    const uint32_t owned = (uint32_t)item2.z;       // bit vi*nd + j: cell (source vi, destination j) is this item's
+    const int nb = nd * ncw, natom = nb / 32;
+    const int ast = nb > 128 ? 3 : kGPAst;
+    uint8_t* Bs = smem + L::a_off + ast * 4 * kGPBytes;
+    const int rows_total = ns * p.Cin;
     const int nmb = (rows_total + 127) / 128;
     uint32_t tmem_cols = 32;
     while (tmem_cols < (uint32_t)(nmb * nb)) tmem_cols <<= 1;
@@ -99,8 +107,10 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             mbar_wait(&b_empty[bb], ((itb >> 1) & 1) ^ 1);
             if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[bb], (uint32_t)kGPBytes * natom);
-                for (int j = 0; j < natom; ++j)
-                    tma_load_3d(Bs + (bb * natom + j) * kGPBytes, &dmap, &b_full[bb], col0 + 32 * j, w, f0);
+                for (int j = 0; j < natom; ++j) {
+                    const int jd = (32 * j) / ncw, c = 32 * j - jd * ncw;
+                    tma_load_3d(Bs + (bb * natom + j) * kGPBytes, &dmap, &b_full[bb], col0 + c, p.joints[d0 + jd], f0);
+                }
             }
             __syncwarp();
             for (int mb = 0; mb < nmb; ++mb, ++ita) {
@@ -114,7 +124,7 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
                         const bool ok = R < rows_total;
                         // atoms past the end of the item: a box outside the tensor reads as zeros
                         tma_load_3d(As + (sa * 4 + j) * kGPBytes, &xmap, &a_full[sa], ok ? ci0 : 0,
-                                    ok ? p.v_list[v0 + vi] : 0, ok ? f0 : -(1 << 20));
+                                    ok ? p.joints[s0 + vi] : 0, ok ? f0 : -(1 << 20));
                     }
                 }
                 __syncwarp();
@@ -158,11 +168,18 @@ gcn_pair_tc_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_consta
             for (int mb = 0; mb < nmb; ++mb) {
                 const int R = mb * 128 + m;
                 const int vi = R / p.Cin, ci = R - vi * p.Cin;
+                const bool row_ok = R < rows_total;
+                const int vsrc = row_ok ? p.joints[s0 + vi] : 0;
                 for (int c0 = 0; c0 < nb; c0 += 32) {
+                    const int jd = c0 / ncw, c = c0 - jd * ncw;
+                    // a warp's 32 rows belong to one source joint (Cin is a multiple of 32): uniform skip
+                    const bool mine = row_ok && ((owned >> (vi * nd + jd)) & 1u);
+                    if (!__any_sync(0xffffffffu, mine)) continue;
                     float v[32];
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + mb * nb + c0, v);
-                    if (R < rows_total) {
-                        float* dst = p.P + ((size_t)(v0 + vi) * p.Cin + ci) * p.Cout + col0 + c0;
+                    if (mine) {
+                        const int pid = p.pair_of[vsrc * p.V + p.joints[d0 + jd]];
+                        float* dst = p.P + ((size_t)pid * p.Cin + ci) * p.Cout + col0 + c;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
                     }
@@ -229,16 +246,15 @@ using namespace istgcn;
 
 ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, const float* Wc,
                                      const int* items, int nitems, const int* ctas, int nctas,
-                                     const int* v_list, int npairs,
+                                     const int* joints, const int* pair_of, int npairs,
                                      const int* entry_pair, const int* k_ptr, int nnz, float* P_ws,
                                      float* dWc, float* dvals, int frames, int V, int K, int Cin, int Cout,
-                                     int nb, istgcn_stream_t s) {
-    ISTGCN_REQUIRE(dz && x && vals && Wc && items && ctas && v_list && entry_pair && k_ptr && P_ws && dWc && dvals,
+                                     istgcn_stream_t s) {
+    ISTGCN_REQUIRE(dz && x && vals && Wc && items && ctas && joints && pair_of && entry_pair && k_ptr && P_ws &&
+                       dWc && dvals,
                    ISTGCN_E_ARG, "gcn_pair_grads: null pointer");
     ISTGCN_REQUIRE(Cin % 32 == 0 && Cout % 32 == 0 && Cin >= 32 && Cout >= 32 && V >= 1 && V <= 64 && K >= 1,
                    ISTGCN_E_SHAPE, "gcn_pair_grads: Cin=%d Cout=%d V=%d unsupported", Cin, Cout, V);
-    ISTGCN_REQUIRE(nb >= 32 && nb <= 256 && nb % 32 == 0 && (nb <= 128 || nb == 256) && Cout % nb == 0,
-                   ISTGCN_E_SHAPE, "gcn_pair_grads: N-chunk %d must divide Cout=%d (32..128 or 256)", nb, Cout);
     ISTGCN_REQUIRE(((reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(x) |
                      reinterpret_cast<uintptr_t>(P_ws) | reinterpret_cast<uintptr_t>(Wc)) & 15) == 0,
                    ISTGCN_E_ARG, "gcn_pair_grads: pointers must be 16-byte aligned");
@@ -246,8 +262,8 @@ ISTGCN_API int istgcn_gcn_pair_grads(const float* dz, const float* x, const floa
     cudaStream_t st = (cudaStream_t)s;
     tc::PairParams p{};
     p.P = P_ws; p.items = reinterpret_cast<const int4*>(items); p.ctas = reinterpret_cast<const int4*>(ctas);
-    p.v_list = v_list;
-    p.frames = frames; p.V = V; p.Cin = Cin; p.Cout = Cout; p.nb = nb;
+    p.joints = joints; p.pair_of = pair_of;
+    p.frames = frames; p.V = V; p.Cin = Cin; p.Cout = Cout;
     p.ktiles = (frames + tc::kGPRows - 1) / tc::kGPRows;
     CUtensorMap xmap, dmap;
     if (int e = tc::encode_joint_frames_map(&xmap, x, frames, V, Cin, tc::kGPRows)) return e;

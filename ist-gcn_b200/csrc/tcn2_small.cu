@@ -368,13 +368,16 @@ ISTGCN_API int istgcn_tcn2_conv(const float* h1, const float* Weff, const float*
 ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const float* Weff, float* dh1,
                                     float* dWeff, float* dbd, int NM, int T, int V, int bp, int stride,
                                     istgcn_stream_t s) {
-    ISTGCN_REQUIRE(dh2 && h1 && Weff && dh1 && dWeff && dbd, ISTGCN_E_ARG, "tcn2_bwd_conv: null pointer");
+    // dh1 == NULL: weight gradient only; dWeff == NULL: input gradient (+ dbd) only -- the two kernels are
+    // independent, a caller may put the weight gradient on another stream
+    ISTGCN_REQUIRE(dh2 && h1 && Weff && (dh1 || dWeff) && (dh1 == nullptr || dbd), ISTGCN_E_ARG,
+                   "tcn2_bwd_conv: null pointer");
     if (int e = check_small("tcn2_bwd_conv", NM, T, V, bp, stride)) return e;
     if (NM == 0) return 0;
     const int Tout = (T - 1) / stride + 1, nt = bp / 8;
     const int inv16 = (65536 + V - 1) / V;
     const unsigned inv_per = (unsigned)(((1ull << 32) + (unsigned)(V * bp / 4) - 1) / (unsigned)(V * bp / 4));
-    {   // dh1 (frames of the output = T) from the zero-upsampled dh2, column sums -> dbd
+    if (dh1) {   // dh1 (frames of the output = T) from the zero-upsampled dh2, column sums -> dbd
         SmallP p{dh2, nullptr, Weff, nullptr, dh1, dbd, NM, Tout, T, V, stride, inv16, inv_per};
         const int Q = kTT + 2 * kHalf;
         const size_t smem = sizeof(float) * ((size_t)kTaps * nt * nt * 64 + 16 + (size_t)Q * V * bp);
@@ -392,7 +395,7 @@ ISTGCN_API int istgcn_tcn2_bwd_conv(const float* dh2, const float* h1, const flo
 #undef T2S_BWD
         if (int e = finish_launch("tcn2_bwd_conv (data)")) return e;
     }
-    {   // dWeff
+    if (dWeff) {
         SmallP p{h1, dh2, Weff, nullptr, dWeff, nullptr, NM, T, Tout, V, stride, inv16, inv_per};
         const int Q = (kTT - 1) * stride + kTaps;
         const size_t smem = sizeof(float) * ((size_t)kTaps * bp * bp + (size_t)kTT * V * bp + (size_t)Q * V * bp);

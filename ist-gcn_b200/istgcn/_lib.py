@@ -94,6 +94,8 @@ def call(name, *args):
     launch_count += KERNELS_PER_CALL.get(name, 1)
     if name == 'gcn_tc_dw' and args[8] is None:        # no bias-term column sums: one kernel
         launch_count -= 1
+    if name == 'tcn2_bwd_conv' and (args[3] is None or args[4] is None):   # one of its two kernels
+        launch_count -= 1
     if timing is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -138,10 +138,10 @@ def _gcn_pair_ok(cin, cout):
 
 
 def gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout):
-    items, nb, ctas = pat.pair_items(Cin, Cout)
+    items, ctas, joints = pat.pair_items(Cin, Cout)
     ws = torch.zeros(pat.npairs, Cin, Cout, device=dz.device, dtype=torch.float32)
-    call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], ctas, ctas.shape[0], pat.pair_v, pat.npairs, pat.entry_pair,
-         pat.k_ptr, pat.nnz, ws, dWc, dvals, frames, V, K, Cin, Cout, nb)
+    call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], ctas, ctas.shape[0], joints, pat.pair_of, pat.npairs,
+         pat.entry_pair, pat.k_ptr, pat.nnz, ws, dWc, dvals, frames, V, K, Cin, Cout)
 
 
 # The weight / adjacency gradient of a block is needed only by the parameter-regrouping backward
@@ -164,29 +164,39 @@ def _pair_stream(device):
     return _pair_streams[key]
 
 
-def gcn_pair_grads_async(dz, x, vals, Wc, pat, dWc, dvals, owner, frames, V, K, Cin, Cout):
-    """gcn_pair_grads on the pair stream, ordered after everything already on the current stream.
-    `owner` is the allocation dWc / dvals are views of.  wait_pair_grads(dWc) joins."""
-    main = torch.cuda.current_stream(dz.device)
-    ps = _pair_stream(dz.device)
+def run_on_grad_stream(key, tensors, fn):
+    """Run ``fn()`` (weight-gradient kernels nobody on the main stream waits for) on the gradient
+    stream, ordered after everything already on the current stream.  ``tensors`` = everything fn
+    touches that was allocated on another stream; ``key`` = the gradient tensor whose consumer calls
+    wait_pair_grads(key)."""
+    dev = key.device
+    main = torch.cuda.current_stream(dev)
+    ps = _pair_stream(dev)
     ev0 = torch.cuda.Event()
     ev0.record(main)
     ps.wait_event(ev0)
     with torch.cuda.stream(ps):
-        gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout)
+        fn()
         ev1 = torch.cuda.Event()
         ev1.record(ps)
-    for t in (dz, x, vals, Wc, owner):
-        t.record_stream(ps)
-    _pair_events[dWc.data_ptr()] = ev1
+    for t in tensors:
+        if t is not None:
+            t.record_stream(ps)
+    _pair_events.setdefault(key.data_ptr(), []).append(ev1)
+
+
+def gcn_pair_grads_async(dz, x, vals, Wc, pat, dWc, dvals, owner, frames, V, K, Cin, Cout):
+    """gcn_pair_grads on the gradient stream.  `owner` is the allocation dWc / dvals are views of."""
+    run_on_grad_stream(dWc, (dz, x, vals, Wc, owner),
+                       lambda: gcn_pair_grads(dz, x, vals, Wc, pat, dWc, dvals, frames, V, K, Cin, Cout))
 
 
 def wait_pair_grads(dWc):
-    """The current stream waits for the pair kernel that writes ``dWc`` (no-op if there is none)."""
+    """The current stream waits for every gradient-stream kernel registered under ``dWc`` (no-op if
+    there is none)."""
     if dWc is None:
         return
-    ev = _pair_events.pop(dWc.data_ptr(), None)
-    if ev is not None:
+    for ev in _pair_events.pop(dWc.data_ptr(), ()):
         torch.cuda.current_stream(dWc.device).wait_event(ev)
 
 
@@ -334,7 +344,14 @@ class STBlock(Function):
         if ctx.tcn2:
             call('tcn2_bwd_up', go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, i64(R_out), Cout,
                  bp, float(drop_p), u64(seed), step_counter(dev))
-            call('tcn2_bwd_conv', dh2, h1, Weff, dh1, dWeff, dbd, NM, T, V, bp, s)
+            if getattr(cfg, 'pair_async', False) and _pair_async_enabled() and \
+                    os.environ.get('ISTGCN_DW_ASYNC', '1') != '0':
+                # the tap-weight gradient is needed by BlockPrep.backward only: gradient stream
+                call('tcn2_bwd_conv', dh2, h1, Weff, dh1, None, dbd, NM, T, V, bp, s)
+                run_on_grad_stream(dWc, (dh2, h1, Weff, flat),
+                                   lambda: call('tcn2_bwd_conv', dh2, h1, Weff, None, dWeff, None, NM, T, V, bp, s))
+            else:
+                call('tcn2_bwd_conv', dh2, h1, Weff, dh1, dWeff, dbd, NM, T, V, bp, s)
             call('tcn2_bwd_down', dh1, z, mean1, scale1, beta1, rstd1, Wd, g1, dWd, sums[4], sums[5],
                  i64(R_in), Cout, bp)
         else:

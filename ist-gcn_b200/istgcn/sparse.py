@@ -53,37 +53,89 @@ class SparsePattern(object):
         uniq, inverse = np.unique(key, return_inverse=True)
         self.npairs = int(uniq.size)
         self._pair_w = (uniq // V).astype(np.int64)
+        self._pair_v_host = (uniq % V).astype(np.int64)
         self.pair_v = dev(uniq % V)                      # [npairs] source joint of every pair
+        pair_of = np.full(V * V, -1, dtype=np.int64)
+        pair_of[self._pair_v_host * V + self._pair_w] = np.arange(uniq.size)
+        self.pair_of = dev(pair_of)                      # [V*V] (v*V + w) -> pair id, -1 outside the pattern
         self.entry_pair = dev(inverse)                   # [nnz] canonical entry -> pair id
         self.k_ptr = dev(np.concatenate([[0], np.cumsum(np.bincount(k, minlength=K))]))
         self._device = device
         self._pair_items = {}
 
+    def _cover(self, nd_max, ns_max):
+        """Greedy cover of the joint-pair pattern by (sources x destinations) blocks of at most
+        ns_max x nd_max joints: [(sources, destinations, owned-cell mask)], every pattern pair owned by
+        exactly one block.  The skeleton patterns are block-structured (limbs), so the blocks fill up."""
+        V = self.V
+        rem = np.zeros((V, V), dtype=bool)                 # [v][w]
+        rem[np.asarray(self._pair_v_host), np.asarray(self._pair_w)] = True
+        blocks = []
+        while rem.any():
+            D = [int(rem.sum(0).argmax())]
+            while len(D) < nd_max:                         # destinations sharing the most sources with D
+                share = [(int((rem[:, w] & rem[:, D].any(1)).sum()), -w) for w in range(V) if w not in D]
+                c, w = max(share)
+                if c == 0:
+                    break
+                D.append(-w)
+            cnt = rem[:, D].sum(1)
+            S = [int(v) for v in np.argsort(-cnt, kind='stable')[:ns_max] if cnt[v] > 0]
+            mask = 0
+            for vi, v in enumerate(S):
+                for jd, w in enumerate(D):
+                    if rem[v, w]:
+                        mask |= 1 << (vi * len(D) + jd)
+                        rem[v, w] = False
+            blocks.append((S, D, mask))
+        return blocks
+
     def pair_items(self, cin, cout):
-        """Work items of istgcn_gcn_pair_grads for this channel pair: (items int32 [n][4] =
-        {w, first pair, pairs, first column}, N-chunk width)."""
+        """Work items of istgcn_gcn_pair_grads for this channel pair -> (items int32 [n][8], ctas int32
+        [m][4], joints int32 [...]): blocks of the pair pattern x column chunks, and the thread blocks
+        dealt to them (include/istgcn_b200.h)."""
         hit = self._pair_items.get((cin, cout))
         if hit is None:
             import os
-            # the widest N-chunk reads the fewest operand bytes per MAC (the kernel is bound by the
-            # L2 -> shared-memory operand stream): rows + columns per K-tile for rows x columns MACs
-            widths = (256, 128, 96, 64, 32) if os.environ.get('ISTGCN_PAIR_NB_MAX') != '128' else (128, 96, 64, 32)
-            nb = next(c for c in widths if cout % c == 0)
-            per_item = max(1, (512 // nb) * 128 // cin)
-            rows = []
-            bounds = np.concatenate([[0], np.cumsum(np.bincount(self._pair_w, minlength=self.V))])
-            for w_ in range(self.V):
-                lo, hi = int(bounds[w_]), int(bounds[w_ + 1])
-                for first in range(lo, hi, per_item):
-                    for col0 in range(0, cout, nb):
-                        rows.append((w_, first, min(per_item, hi - first), col0))
-            items = torch.as_tensor(np.asarray(rows, dtype=np.int32).reshape(-1, 4)).to(self._device)
-            # thread blocks per item in proportion to its cost (M-blocks of 128 stacked rows + the
-            # shared dz atoms), about one block per SM in total; block j of an item with s blocks
-            # takes the K-tiles j, j + s, j + 2s, ...
+            # several destinations per item pay off when an M-block is one whole source joint
+            # (cin >= 128: 128 -> 128 at 2 x 2 joints: 371 -> 317 us); with half-block sources the cover
+            # wastes too many cells of its blocks (64 -> 64 at 4 x 4: 0.63x the operand bytes, 1.9x the
+            # MMAs, measured 284 -> 296 us).  ISTGCN_PAIR_BLOCKS=0 / 1 forces one / several destinations.
+            env = os.environ.get('ISTGCN_PAIR_BLOCKS')
+            single = env == '0' or (env != '1' and cin < 128)
+            # candidates: ncw output channels of nd destinations side by side (N = nd * ncw <= 256), ns
+            # sources stacked (M-blocks * N <= 512 columns of tensor memory); cost = operand rows loaded
+            # per K-tile = ns * cin + nd * ncw per block and column chunk (the kernel is L2-stream bound)
+            best = None
+            for ncw in sorted({c for c in (256, 128, 96, 64, 32) if cout % c == 0}, reverse=True):
+                for nd in (1, 2, 3, 4):
+                    n = nd * ncw
+                    if n > 256 or (single and nd > 1):
+                        continue
+                    ns = min(16, (512 // n) * 128 // cin, 32 // nd)
+                    if ns < 1:
+                        continue
+                    blocks = self._cover(nd, ns)
+                    cost = sum(len(S) * cin + len(D) * ncw for S, D, _ in blocks) * (cout // ncw)
+                    if best is None or cost < best[0]:
+                        best = (cost, ncw, blocks)
+            _, ncw, blocks = best
+            joints, rows, costs = [], [], []
+            for S, D, mask in blocks:
+                d0 = len(joints)
+                joints += D
+                s0 = len(joints)
+                joints += S
+                for col0 in range(0, cout, ncw):
+                    rows.append((d0, len(D), s0, len(S), col0, ncw, mask, 0))
+                    costs.append(len(S) * cin + len(D) * ncw)
+            items = torch.as_tensor(np.asarray(rows, dtype=np.int64).astype(np.int32).reshape(-1, 8)).to(self._device)
+            joints_t = torch.as_tensor(np.asarray(joints, dtype=np.int32)).to(self._device)
+            # thread blocks per item in proportion to its cost, about one block per SM in total; block j
+            # of an item with s blocks takes the K-tiles j, j + s, j + 2s, ...
             sms = torch.cuda.get_device_properties(self._device).multi_processor_count \
                 if torch.cuda.is_available() else 148
-            cost = np.array([(r[2] * cin + 127) // 128 + 0.5 for r in rows])
+            cost = np.asarray(costs, dtype=np.float64)
             # greedy apportionment (the next block goes to the slowest item) over 1 .. 4 waves of
             # thread blocks: the fewest waves whose slowest block is within 20 % of the mean
             for waves in range(max(1, -(-len(rows) // sms)), 5):
@@ -94,7 +146,7 @@ class SparsePattern(object):
                     break
             ctas = [(i, j, int(s_), 0) for i, s_ in enumerate(share) for j in range(int(s_))]
             ctas = torch.as_tensor(np.asarray(ctas, dtype=np.int32).reshape(-1, 4)).to(self._device)
-            hit = self._pair_items[(cin, cout)] = (items, nb, ctas)
+            hit = self._pair_items[(cin, cout)] = (items, ctas, joints_t)
         return hit
 
     @classmethod

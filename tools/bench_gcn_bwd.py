@@ -53,13 +53,14 @@ def main():
         dz = torch.randn(frames * V, cout, device=dev)
         Wc = torch.randn(K * cin, cout, device=dev) * 0.05
         dW, dv = torch.zeros(K * cin, cout, device=dev), torch.zeros(pat.nnz, device=dev)
-        items, nb, ctas = pat.pair_items(cin, cout)
+        items, ctas, joints = pat.pair_items(cin, cout)
+        nb = int(items[0, 1] * items[0, 5])
         ws = torch.zeros(pat.npairs, cin, cout, device=dev)
 
         def pair():
             ws.zero_()
-            call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], ctas, ctas.shape[0], pat.pair_v, pat.npairs,
-                 pat.entry_pair, pat.k_ptr, pat.nnz, ws, dW, dv, frames, V, K, cin, cout, nb)
+            call('gcn_pair_grads', dz, x, vals, Wc, items, items.shape[0], ctas, ctas.shape[0], joints, pat.pair_of,
+                 pat.npairs, pat.entry_pair, pat.k_ptr, pat.nnz, ws, dW, dv, frames, V, K, cin, cout)
 
         def old():
             call('gcn_tc_dvals', dz, x, Wc, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, dv, frames, V, K, cin, cout)
