@@ -258,14 +258,24 @@ def run_istgcn(args):
     launches = launches_per_step * args.steps
     # per-kernel device time: CUDA events around every launch of an eager pass of the same step
     # (events cannot be recorded inside a graph replay)
+    # In this pass the weight-gradient kernels run on the main stream like everything else
+    # (ISTGCN_PAIR_ASYNC=0): a kernel timed while another stream's kernel shares the SMs would be
+    # charged for both.
     _lib.timing = {}
     prof_steps = min(3, args.steps)
+    async_env = os.environ.get('ISTGCN_PAIR_ASYNC')
+    os.environ['ISTGCN_PAIR_ASYNC'] = '0'
+    torch.cuda.synchronize()
     ep0, ep1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ep0.record()
     for _ in range(prof_steps):
         tr._iteration(x, y, True)
     ep1.record()
     barrier()
+    if async_env is None:
+        os.environ.pop('ISTGCN_PAIR_ASYNC', None)
+    else:
+        os.environ['ISTGCN_PAIR_ASYNC'] = async_env
     timing, _lib.timing = _lib.timing, None
     eager_ms = ep0.elapsed_time(ep1)
     t_ms = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -288,7 +298,8 @@ def run_istgcn(args):
     alg_total = sum(alg) * prof_steps if alg else None
     roof = {'kernel': top, 'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src,
             'launches': n_launch, 'share_of_step': per_kernel[top] / prof_steps / ms_per_step_,
-            'traffic': None, 'timed_in': 'eager pass of %d steps (%.1f ms/step)' % (prof_steps, eager_ms / prof_steps)}
+            'traffic': None,
+            'timed_in': 'eager pass of %d steps, every kernel on the main stream (%.1f ms/step)' % (prof_steps, eager_ms / prof_steps)}
     tpath = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
     if os.path.isfile(tpath) and args.arch == 'ist_gcn':
         with open(tpath) as f:          # DRAM bytes per launch from the committed ncu capture
@@ -560,6 +571,27 @@ def twostream_sweep(args, dev, batches, world=1, rank=0, chunk=512, reps=5):
     return points
 
 
+def tf32_gemm_peak(dev, n=8192, iters=10):
+    """cuBLAS TF32 GEMM n^3 on this GPU (TFLOP/s): the library's tensor-pipe rate for the arithmetic
+    the tcgen05 kernels use (tools/microbench/mma_rate.cu measures the instruction rate itself)."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        for _ in range(2):
+            a @ b
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        return iters * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def run_extras(args, dev):
     """Driver-visible datapoints beside the headline (N = 1 only): the <= 1e-4 parity mode's
     throughput, BASELINE.json configs[2] (Kinetics-skeleton, batch 256), the stock-PyTorch-eager
@@ -572,6 +604,7 @@ def run_extras(args, dev):
     if args.workload == 'ntu' and args.arch == 'ist_gcn':
         out['kinetics_b256'] = _timed_training('kinetics', args.arch, args.math, 256, dev, steps)
     out['gpu_eager'] = gpu_eager_reference(args, dev)
+    out['tf32_gemm_tflops'] = tf32_gemm_peak(dev)
     ts_args = copy.copy(args)
     out['twostream_inference'] = {'stream_arch': args.ts_arch,
                                   'points': twostream_sweep(ts_args, dev, [1, 64, 1024])}

@@ -10,16 +10,17 @@ UNIT_MS = {'ns': 1e-6, 'nsecond': 1e-6, 'us': 1e-3, 'usecond': 1e-3, 'ms': 1.0, 
            'second': 1e3}
 UNIT_B = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 # kernel-name prefix -> C-ABI entry point (bench.py kernel_shares key)
-ENTRY = (('tc::gcn_tc2_kernel', 'gcn_tc'), ('tc::gcn_tc_kernel', 'gcn_tc'), ('tc::gcn_tc_dw', 'gcn_tc_dw'),
-         ('tc::frame_colsum', 'gcn_tc_dw'), ('tc::gcn_tc_da', 'gcn_tc_dvals'),
-         ('istgcn::tcn_bwd', 'tcn_bwd'), ('istgcn::tcn_down', 'tcn_fwd'), ('istgcn::tcn_up', 'tcn_fwd'),
+ENTRY = (('tc::gcn_tc3_kernel', 'gcn_tc'), ('tc::gcn_tc2_kernel', 'gcn_tc'), ('tc::gcn_tc_kernel', 'gcn_tc'),
+         ('tc::gcn_tc_dw', 'gcn_tc_dw'), ('tc::frame_colsum', 'gcn_tc_dw'), ('tc::gcn_tc_da', 'gcn_tc_dvals'),
+         ('tc::gcn_pair_tc_kernel', 'gcn_pair_grads'), ('tc::pair_reduce_', 'gcn_pair_grads'),
+         ('tcn_bwd', 'tcn_bwd'), ('tcn_down', 'tcn_fwd'), ('tcn_up', 'tcn_fwd'),
          ('tcn2_down_kernel', 'tcn2_down'), ('tcn2_up_kernel', 'tcn2_up'), ('tcn2_bwd_up_kernel', 'tcn2_bwd_up'),
          ('tcn2_bwd_down_kernel', 'tcn2_bwd_down'), ('tcn2_small_conv_kernel<1, 0', 'tcn2_conv'),
          ('tcn2_small_conv_kernel<2, 0', 'tcn2_conv'), ('tcn2_small_conv_kernel<1, 1', 'tcn2_bwd_conv'),
          ('tcn2_small_conv_kernel<2, 1', 'tcn2_bwd_conv'), ('tcn2_small_dw_kernel', 'tcn2_bwd_conv'),
-         ('istgcn::block_tail_fwd', 'block_tail_fwd'), ('istgcn::block_tail_bwd', 'block_tail_bwd'),
-         ('istgcn::bn_back_apply', 'bn_back_apply'), ('istgcn::bn_back_colsum', 'bn_back_colsum'), ('istgcn::gcn_small_fwd', 'gcn_small_fwd'),
-         ('istgcn::gcn_small_bwd', 'gcn_small_bwd'))
+         ('block_tail_fwd', 'block_tail_fwd'), ('block_tail_bwd', 'block_tail_bwd'),
+         ('bn_back_apply', 'bn_back_apply'), ('bn_back_colsum', 'bn_back_colsum'), ('gcn_small_fwd', 'gcn_small_fwd'),
+         ('gcn_small_bwd', 'gcn_small_bwd'))
 
 with open(sys.argv[1], newline='') as f:
     lines = [l for l in f if not l.startswith('==')]
@@ -57,12 +58,12 @@ if len(sys.argv) > 2:
                 e = ent.setdefault(key, [0, 0.0, 0.0])
                 e[0] += n; e[1] += rd + wr; e[2] += t
                 break
-    per_call = {'tcn_bwd': 3, 'tcn_fwd': 2, 'tcn2_bwd_conv': 2}       # kernels per C-ABI call
+    per_call = {'tcn_bwd': 3, 'tcn_fwd': 2, 'tcn2_bwd_conv': 2, 'gcn_pair_grads': 3}       # kernels per C-ABI call
     out = {}
     for key, (n, b, t) in ent.items():
         calls = n / per_call.get(key, 1)
         if key == 'gcn_tc_dw':                    # a frame_colsum launch may ride along: count the dw kernels
-            calls = sum(v[0] for k2, v in rows.items() if k2.startswith('tc::gcn_tc_dw'))
+            calls = sum(v[0] for k2, v in rows.items() if k2.startswith('tc::gcn_tc_dw')) or n
         out[key] = {'dram_bytes_per_launch': b / calls, 'launches': int(calls), 'ms_per_launch': t / calls,
                     'workload': 'ntu', 'clips_per_gpu': 64,
                     'source': 'profiles/%s_launches_dram.md (ncu dram__bytes_read.sum + dram__bytes_write.sum)' % (sys.argv[3] if len(sys.argv) > 3 else 'r1')}
