@@ -271,6 +271,37 @@ int istgcn_tcn2_bwd_down(const float* dh1, const float* z, const float* mean1, c
                          float* dWd, double* sg1, double* sg1x, long long rows_in, int C, int bp,
                          istgcn_stream_t s);
 
+/* ---- the same consumers with the BatchNorm bookkeeping folded in (training mode).  The one-block
+ * istgcn_bn_finalize / istgcn_bn_bwd_coeffs launches in front of them cost ~6 us each with their gaps
+ * (~75 per training step); here every thread block of the consumer derives the per-channel coefficients
+ * it needs from the raw double sums, and the first block also stores them (the arrays named as outputs
+ * below keep their meaning for the backward pass and for later consumers), updates the running
+ * statistics (bn_finalize's formula; may be NULL) and writes dgamma / dbeta (may be NULL).
+ * rstd = 1/sqrt(var + eps) by rsqrtf + one Newton step (float-exact); count = rows behind the sums.  */
+int istgcn_tcn2_down_bn(const float* z, const double* stat_sum, const double* stat_sumsq, double count,
+                        const float* gamma1, const float* beta1, float* running_mean,
+                        float* running_var, float momentum, float eps, float* mean1, float* scale1,
+                        float* rstd1, const float* Wd, const float* bd, float* h1, long long rows_in,
+                        int C, int bp, istgcn_stream_t s);
+int istgcn_tcn2_bwd_up_bn(const float* go, const float* u, const double* sg, const double* sgx,
+                          double count, const float* gamma2, const float* rstd2, float* p2, float* m12,
+                          float* c2, float* dgamma2, float* dbeta2, const float* mean2, const float* h2,
+                          const float* Wu, float* dh2, float* dWu, float* dbu, float* dbeff,
+                          long long rows_out, int C, int bp, float drop_p, uint64_t drop_seed,
+                          const unsigned long long* drop_step, istgcn_stream_t s);
+int istgcn_bn_back_colsum_bn(const float* g, const float* z, const double* sg, const double* sgx,
+                             double count, const float* gamma, const float* rstd, float* p, float* m1,
+                             float* c, float* dgamma, float* dbeta, const float* mean, float* dz,
+                             float* colsum, int frames, int V, int C, istgcn_stream_t s);
+int istgcn_block_tail_fwd_bn(const float* u, const double* sum2, const double* sumsq2, double count,
+                             const float* gamma2, const float* beta2, float* rmean2, float* rvar2,
+                             float momentum2, float eps2, float* mean2, float* scale2, float* rstd2,
+                             const float* res, const double* sum_r, const double* sumsq_r,
+                             const float* gamma_r, const float* beta_r, float* rmean_r, float* rvar_r,
+                             float momentum_r, float eps_r, float* mean_r, float* scale_r, float* rstd_r,
+                             float* out, long long rows, int C, float drop_p, uint64_t drop_seed,
+                             const unsigned long long* drop_step, istgcn_stream_t s);
+
 /* ---- full-width temporal convolution (net/st_gcnold.py:160-174: BN -> ReLU -> Conv2d(C, C,
  * (kt,1), (stride,1), (pad,0)) -> BN -> Dropout; net/st_gcn_mstcn.py: three such convs of 3/9/15
  * taps scaled by mstcn_importance = one 15-tap conv).  The convolution itself is the sum over

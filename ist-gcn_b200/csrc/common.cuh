@@ -239,6 +239,60 @@ __device__ __forceinline__ float bn_back(float g, float x, float p, float m1, fl
     return p * ((g - m1) - c * (x - mean));
 }
 
+// ---- BatchNorm bookkeeping folded into the consumer kernel (the one-block bn_finalize /
+// bn_bwd_coeffs launches cost ~6 us each with their gaps, ~75 of them per training step).
+// Every CTA of the consumer derives the per-channel coefficients it needs from the raw sums; the
+// threads named by `write` also store them (for the backward pass / later consumers) and update the
+// running statistics.  sum == nullptr: the consumer takes ready-made coefficients as before.
+struct BnFold {                 // training forward: y = (x - mean) * scale + beta
+    const double *sum, *sumsq;
+    double inv_count, unbias;   // 1 / count, count / (count - 1)
+    const float* gamma;
+    float *running_mean, *running_var;
+    float momentum, eps;
+    float *mean_out, *scale_out, *rstd_out;
+};
+__device__ __forceinline__ void bn_fold(const BnFold& f, int c, bool write, float& mean, float& scale) {
+    const double mu = f.sum[c] * f.inv_count;
+    double var = fma(-mu, mu, f.sumsq[c] * f.inv_count);
+    if (var < 0) var = 0;
+    const float v = (float)var + f.eps;
+    float rs = rsqrtf(v);
+    rs = rs * (1.5f - 0.5f * v * rs * rs);                    // one Newton step: float-exact
+    mean = (float)mu;
+    scale = f.gamma[c] * rs;
+    if (write) {
+        f.mean_out[c] = mean;
+        f.scale_out[c] = scale;
+        f.rstd_out[c] = rs;
+        if (f.running_mean) {
+            f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+            f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(var * f.unbias);
+        }
+    }
+}
+struct BnBwdFold {              // backward: dx = p * ((g - m1) - c * (x - mean))
+    const double *sg, *sgx;     // sum g, sum g * xhat
+    double inv_count;
+    const float *gamma, *rstd;
+    float *p_out, *m1_out, *c_out, *dgamma, *dbeta;
+};
+__device__ __forceinline__ void bn_bwd_fold(const BnBwdFold& f, int c, bool write, float& p, float& m1,
+                                            float& cc) {
+    const double sg = f.sg[c], sgx = f.sgx[c];
+    const float rs = f.rstd[c];
+    p = f.gamma[c] * rs;
+    m1 = (float)(sg * f.inv_count);
+    cc = (float)((double)rs * (sgx * f.inv_count));
+    if (write) {
+        f.p_out[c] = p;
+        f.m1_out[c] = m1;
+        f.c_out[c] = cc;
+        if (f.dgamma) f.dgamma[c] = (float)sgx;
+        if (f.dbeta) f.dbeta[c] = (float)sg;
+    }
+}
+
 // Dropout seed = host value mixed with an optional device-resident step counter, so that a
 // captured CUDA graph draws a fresh mask on every replay.
 __device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const unsigned long long* step) {

@@ -177,7 +177,8 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
                                       const float* __restrict__ scale_r,
                                       const float* __restrict__ beta_r, float* __restrict__ out,
                                       long long n4, int C, int mode, float drop_p, float keep_scale,
-                                      uint64_t seed0, const unsigned long long* step) {
+                                      uint64_t seed0, const unsigned long long* step, BnFold fold2,
+                                      BnFold foldr) {
     const uint64_t seed = effective_seed(seed0, step);
     const int c4 = C >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -187,9 +188,25 @@ __global__ void block_tail_fwd_kernel(const float* __restrict__ u, const float* 
     // loop (the per-iteration `i % c4` + six coefficient loads made this kernel issue-bound at 0.78 of
     // the HBM peak).
     const int c = (int)(i % c4) * 4;
-    const float4 mu = ld4(mean2 + c), sc = ld4(scale2 + c), be = ld4(beta2 + c);
+    const bool wr = i < c4;              // the first C/4 threads of the grid store folded coefficients
+    float4 mu, sc;
+    if (fold2.sum) {
+        bn_fold(fold2, c, wr, mu.x, sc.x); bn_fold(fold2, c + 1, wr, mu.y, sc.y);
+        bn_fold(fold2, c + 2, wr, mu.z, sc.z); bn_fold(fold2, c + 3, wr, mu.w, sc.w);
+    } else {
+        mu = ld4(mean2 + c); sc = ld4(scale2 + c);
+    }
+    const float4 be = ld4(beta2 + c);
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f), a = m, b = m;
-    if (mode == 2) { m = ld4(mean_r + c); a = ld4(scale_r + c); b = ld4(beta_r + c); }
+    if (mode == 2) {
+        if (foldr.sum) {
+            bn_fold(foldr, c, wr, m.x, a.x); bn_fold(foldr, c + 1, wr, m.y, a.y);
+            bn_fold(foldr, c + 2, wr, m.z, a.z); bn_fold(foldr, c + 3, wr, m.w, a.w);
+        } else {
+            m = ld4(mean_r + c); a = ld4(scale_r + c);
+        }
+        b = ld4(beta_r + c);
+    }
     for (; i < n4; i += stride) {
         const float4 uu = ld4(u + i * 4);
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -445,6 +462,12 @@ ISTGCN_API int istgcn_bn_bwd_coeffs(const double* sg, const double* sgx, double 
     return finish_launch("bn_bwd_coeffs");
 }
 
+static int launch_block_tail_fwd(const float* u, const float* mean2, const float* scale2, const float* beta2,
+                                 const float* res, const float* mean_r, const float* scale_r,
+                                 const float* beta_r, float* out, long long rows, int C, int mode,
+                                 float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                                 const BnFold& fold2, const BnFold& foldr, istgcn_stream_t s);
+
 ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const float* scale2,
                                      const float* beta2, const float* res, const float* mean_r,
                                      const float* scale_r, const float* beta_r, float* out,
@@ -453,9 +476,45 @@ ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const f
     ISTGCN_REQUIRE(u && mean2 && scale2 && beta2 && out, ISTGCN_E_ARG, "block_tail_fwd: null pointer");
     ISTGCN_REQUIRE(scale_r == nullptr || (res && mean_r && beta_r), ISTGCN_E_ARG,
                    "block_tail_fwd: residual BatchNorm needs res, mean_r and beta_r");
+    const int mode = res == nullptr ? 0 : (scale_r == nullptr ? 1 : 2);
+    return launch_block_tail_fwd(u, mean2, scale2, beta2, res, mean_r, scale_r, beta_r, out, rows, C, mode,
+                                 drop_p, drop_seed, drop_step, BnFold{}, BnFold{}, s);
+}
+
+// The same with the BatchNorm bookkeeping folded in (training): mean2 / scale2 / rstd2 -- and, when the
+// residual is a conv + BatchNorm (sum_r != NULL), mean_r / scale_r / rstd_r -- are OUTPUTS derived from
+// the raw sums over `count` rows; running statistics updated in place (may be NULL).
+ISTGCN_API int istgcn_block_tail_fwd_bn(const float* u, const double* sum2, const double* sumsq2, double count,
+                                        const float* gamma2, const float* beta2, float* rmean2, float* rvar2,
+                                        float momentum2, float eps2, float* mean2, float* scale2,
+                                        float* rstd2, const float* res, const double* sum_r,
+                                        const double* sumsq_r, const float* gamma_r, const float* beta_r,
+                                        float* rmean_r, float* rvar_r, float momentum_r, float eps_r,
+                                        float* mean_r, float* scale_r, float* rstd_r, float* out,
+                                        long long rows, int C, float drop_p, uint64_t drop_seed,
+                                        const unsigned long long* drop_step, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(u && sum2 && sumsq2 && gamma2 && beta2 && mean2 && scale2 && rstd2 && out, ISTGCN_E_ARG,
+                   "block_tail_fwd_bn: null pointer");
+    ISTGCN_REQUIRE(count > 0, ISTGCN_E_ARG, "block_tail_fwd_bn: empty batch");
+    ISTGCN_REQUIRE(sum_r == nullptr || (res && sumsq_r && gamma_r && beta_r && mean_r && scale_r && rstd_r),
+                   ISTGCN_E_ARG, "block_tail_fwd_bn: residual BatchNorm needs res, its sums, parameters and outputs");
+    const double unb = count > 1 ? count / (count - 1.0) : 1.0;
+    const BnFold f2{sum2, sumsq2, 1.0 / count, unb, gamma2, rmean2, rvar2, momentum2, eps2, mean2, scale2, rstd2};
+    BnFold fr{};
+    if (sum_r) fr = BnFold{sum_r, sumsq_r, 1.0 / count, unb, gamma_r, rmean_r, rvar_r, momentum_r, eps_r,
+                           mean_r, scale_r, rstd_r};
+    const int mode = res == nullptr ? 0 : (sum_r == nullptr ? 1 : 2);
+    return launch_block_tail_fwd(u, mean2, scale2, beta2, res, mean_r, scale_r, beta_r, out, rows, C, mode,
+                                 drop_p, drop_seed, drop_step, f2, fr, s);
+}
+
+static int launch_block_tail_fwd(const float* u, const float* mean2, const float* scale2, const float* beta2,
+                                 const float* res, const float* mean_r, const float* scale_r,
+                                 const float* beta_r, float* out, long long rows, int C, int mode,
+                                 float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                                 const BnFold& fold2, const BnFold& foldr, istgcn_stream_t s) {
     ISTGCN_REQUIRE(C % 4 == 0, ISTGCN_E_SHAPE, "block_tail_fwd: C=%d not a multiple of 4", C);
     ISTGCN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, ISTGCN_E_ARG, "block_tail_fwd: dropout p=%f", drop_p);
-    const int mode = res == nullptr ? 0 : (scale_r == nullptr ? 1 : 2);
     const long long n4 = rows * C / 4;
     if (n4 == 0) return 0;
     // grid stride = blocks * threads must be a multiple of C/4: a thread then keeps its channel group
@@ -465,7 +524,7 @@ ISTGCN_API int istgcn_block_tail_fwd(const float* u, const float* mean2, const f
     ISTGCN_REQUIRE(threads % c4 == 0, ISTGCN_E_SHAPE, "block_tail_fwd: C=%d has no block size that is a multiple of C/4", C);
     block_tail_fwd_kernel<<<ew_grid(n4, threads), threads, 0, (cudaStream_t)s>>>(
         u, mean2, scale2, beta2, res, mean_r, scale_r, beta_r, out, n4, C, mode, drop_p,
-        1.f / (1.f - drop_p), drop_seed, drop_step);
+        1.f / (1.f - drop_p), drop_seed, drop_step, fold2, foldr);
     return finish_launch("block_tail_fwd");
 }
 

@@ -129,6 +129,7 @@ struct DownP {
     const float *z, *mean, *scale, *beta, *Wd, *bd;
     float* h1;
     long long rows;
+    BnFold fold;                // fold.sum != nullptr: mean / scale come from the raw BN1 sums
 };
 
 template <int C, int NT>
@@ -142,7 +143,9 @@ __global__ void __launch_bounds__(kT2Threads, 2) tcn2_down_kernel(DownP p) {
     float2* s_w = reinterpret_cast<float2*>(smem + 3 * C);          // [CH][2][NT][32]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     for (int i = tid; i < C; i += kT2Threads) {
-        s_mean[i] = p.mean[i]; s_scale[i] = p.scale[i]; s_beta[i] = p.beta[i];
+        if (p.fold.sum) bn_fold(p.fold, i, blockIdx.x == 0, s_mean[i], s_scale[i]);
+        else { s_mean[i] = p.mean[i]; s_scale[i] = p.scale[i]; }
+        s_beta[i] = p.beta[i];
     }
     for (int i = tid; i < CH * 2 * NT * 32; i += kT2Threads) {
         const int l = i & 31, q = i >> 5;
@@ -297,9 +300,12 @@ struct BwdUpP {
     float drop_p, keep_scale;
     uint64_t seed;
     const unsigned long long* step;
+    BnBwdFold fold;             // fold.sg != nullptr: p2 / m12 / c2 come from the raw BN2-backward sums
 };
 
-template <int NT>
+// FOLD: the BN2-backward coefficients come from the raw sums (a separate instantiation: the kernel sits at
+// its register cap and the extra prologue code cost the bp = 8 variant 9 % when it shared one body)
+template <int NT, bool FOLD>
 __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdUpP p) {
     constexpr int BP = NT * 8, W = kT2HeavyWarps, NTHR = W * 32;
     extern __shared__ __align__(16) float smem[];
@@ -313,7 +319,9 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
     float* s_dbe = s_dbu + C;                                       // [BP]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     for (int i = tid; i < C; i += NTHR) {
-        s_p[i] = p.p2[i]; s_p[C + i] = p.m12[i]; s_p[2 * C + i] = p.c2[i]; s_p[3 * C + i] = p.mean2[i];
+        if (FOLD) bn_bwd_fold(p.fold, i, blockIdx.x == 0, s_p[i], s_p[C + i], s_p[2 * C + i]);
+        else { s_p[i] = p.p2[i]; s_p[C + i] = p.m12[i]; s_p[2 * C + i] = p.c2[i]; }
+        s_p[3 * C + i] = p.mean2[i];
     }
     for (int i = tid; i < S * 8 * NT * 32; i += NTHR) {
         const int l = i & 31, q = i >> 5;
@@ -644,13 +652,41 @@ int check2(const char* who, long long rows, int C, int bp) {
 
 using namespace istgcn;
 
+static int launch_tcn2_down(const float* z, const float* mean1, const float* scale1, const float* beta1,
+                            const float* Wd, const float* bd, float* h1, long long rows, int C, int bp,
+                            const BnFold& fold, istgcn_stream_t s);
+
 ISTGCN_API int istgcn_tcn2_down(const float* z, const float* mean1, const float* scale1,
                                 const float* beta1, const float* Wd, const float* bd, float* h1,
                                 long long rows, int C, int bp, istgcn_stream_t s) {
     ISTGCN_REQUIRE(z && mean1 && scale1 && beta1 && Wd && bd && h1, ISTGCN_E_ARG, "tcn2_down: null pointer");
+    return launch_tcn2_down(z, mean1, scale1, beta1, Wd, bd, h1, rows, C, bp, BnFold{}, s);
+}
+
+// The same with BatchNorm-1's bookkeeping folded in (training): mean1 / scale1 / rstd1 are OUTPUTS
+// derived from the raw sums of z (what istgcn_bn_finalize would have written), running statistics
+// updated in place (may be NULL).
+ISTGCN_API int istgcn_tcn2_down_bn(const float* z, const double* stat_sum, const double* stat_sumsq,
+                                   double count, const float* gamma1, const float* beta1,
+                                   float* running_mean, float* running_var, float momentum, float eps,
+                                   float* mean1, float* scale1, float* rstd1, const float* Wd,
+                                   const float* bd, float* h1, long long rows, int C, int bp,
+                                   istgcn_stream_t s) {
+    ISTGCN_REQUIRE(z && stat_sum && stat_sumsq && gamma1 && beta1 && mean1 && scale1 && rstd1 && Wd && bd && h1,
+                   ISTGCN_E_ARG, "tcn2_down_bn: null pointer");
+    ISTGCN_REQUIRE(count > 0 && (running_mean == nullptr) == (running_var == nullptr), ISTGCN_E_ARG,
+                   "tcn2_down_bn: empty batch or one running-statistics pointer");
+    const BnFold fold{stat_sum, stat_sumsq, 1.0 / count, count > 1 ? count / (count - 1.0) : 1.0, gamma1,
+                      running_mean, running_var, momentum, eps, mean1, scale1, rstd1};
+    return launch_tcn2_down(z, mean1, scale1, beta1, Wd, bd, h1, rows, C, bp, fold, s);
+}
+
+static int launch_tcn2_down(const float* z, const float* mean1, const float* scale1, const float* beta1,
+                            const float* Wd, const float* bd, float* h1, long long rows, int C, int bp,
+                            const BnFold& fold, istgcn_stream_t s) {
     if (int e = check2("tcn2_down", rows, C, bp)) return e;
     if (rows == 0) return 0;
-    DownP p{z, mean1, scale1, beta1, Wd, bd, h1, rows};
+    DownP p{z, mean1, scale1, beta1, Wd, bd, h1, rows, fold};
     const int nt = bp / 8;
     const size_t smem = sizeof(float) * (3 * C + (C / 16) * 2 * nt * 64);
     const int grid = grid2((rows + 127) / 128, 2);
@@ -685,6 +721,12 @@ ISTGCN_API int istgcn_tcn2_up(const float* h2, const float* Wu, const float* bu,
     return finish_launch("tcn2_up");
 }
 
+static int launch_tcn2_bwd_up(const float* go, const float* u, const float* p2, const float* m12,
+                              const float* c2, const float* mean2, const float* h2, const float* Wu,
+                              float* dh2, float* dWu, float* dbu, float* dbeff, long long rows, int C,
+                              int bp, float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                              const BnBwdFold& fold, istgcn_stream_t s);
+
 ISTGCN_API int istgcn_tcn2_bwd_up(const float* go, const float* u, const float* p2, const float* m12,
                                   const float* c2, const float* mean2, const float* h2,
                                   const float* Wu, float* dh2, float* dWu, float* dbu, float* dbeff,
@@ -692,23 +734,49 @@ ISTGCN_API int istgcn_tcn2_bwd_up(const float* go, const float* u, const float* 
                                   const unsigned long long* drop_step, istgcn_stream_t s) {
     ISTGCN_REQUIRE(go && u && p2 && m12 && c2 && mean2 && h2 && Wu && dh2 && dWu && dbu && dbeff,
                    ISTGCN_E_ARG, "tcn2_bwd_up: null pointer");
+    return launch_tcn2_bwd_up(go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, rows, C, bp, drop_p,
+                              drop_seed, drop_step, BnBwdFold{}, s);
+}
+
+// The same with istgcn_bn_bwd_coeffs folded in: p2 / m12 / c2 (and dgamma2 / dbeta2, may be NULL) are
+// OUTPUTS derived from the raw sums sg = sum gy, sgx = sum gy * uhat over `count` rows.
+ISTGCN_API int istgcn_tcn2_bwd_up_bn(const float* go, const float* u, const double* sg, const double* sgx,
+                                     double count, const float* gamma2, const float* rstd2, float* p2,
+                                     float* m12, float* c2, float* dgamma2, float* dbeta2,
+                                     const float* mean2, const float* h2, const float* Wu, float* dh2,
+                                     float* dWu, float* dbu, float* dbeff, long long rows, int C, int bp,
+                                     float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                                     istgcn_stream_t s) {
+    ISTGCN_REQUIRE(go && u && sg && sgx && gamma2 && rstd2 && p2 && m12 && c2 && mean2 && h2 && Wu && dh2 &&
+                       dWu && dbu && dbeff,
+                   ISTGCN_E_ARG, "tcn2_bwd_up_bn: null pointer");
+    ISTGCN_REQUIRE(count > 0, ISTGCN_E_ARG, "tcn2_bwd_up_bn: empty batch");
+    const BnBwdFold fold{sg, sgx, 1.0 / count, gamma2, rstd2, p2, m12, c2, dgamma2, dbeta2};
+    return launch_tcn2_bwd_up(go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, rows, C, bp, drop_p,
+                              drop_seed, drop_step, fold, s);
+}
+
+static int launch_tcn2_bwd_up(const float* go, const float* u, const float* p2, const float* m12,
+                              const float* c2, const float* mean2, const float* h2, const float* Wu,
+                              float* dh2, float* dWu, float* dbu, float* dbeff, long long rows, int C,
+                              int bp, float drop_p, uint64_t drop_seed, const unsigned long long* drop_step,
+                              const BnBwdFold& fold, istgcn_stream_t s) {
     ISTGCN_REQUIRE(drop_p >= 0.f && drop_p < 1.f, ISTGCN_E_ARG, "tcn2_bwd_up: dropout p=%f", drop_p);
     if (int e = check2("tcn2_bwd_up", rows, C, bp)) return e;
     if (rows == 0) return 0;
     BwdUpP p{go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, rows, C, drop_p,
-             1.f / (1.f - drop_p), drop_seed, drop_step};
+             1.f / (1.f - drop_p), drop_seed, drop_step, fold};
     const int nt = bp / 8, S = C / 64;
     constexpr int W = kT2HeavyWarps;
     const size_t smem = sizeof(float) * (4 * C + S * 8 * nt * 64 + W * 16 * 64 + 2 * W * 32 * nt * 4 +
                                          bp * C + C + bp);
     const int grid = grid2(((rows + 15) / 16 + W / S - 1) / (W / S), 3);
-    if (nt == 1) {
-        set_smem2(tcn2_bwd_up_kernel<1>, smem);
-        tcn2_bwd_up_kernel<1><<<grid, W * 32, smem, (cudaStream_t)s>>>(p);
-    } else {
-        set_smem2(tcn2_bwd_up_kernel<2>, smem);
-        tcn2_bwd_up_kernel<2><<<grid, W * 32, smem, (cudaStream_t)s>>>(p);
-    }
+#define T2_BWD_UP(NT, FOLD)                                            \
+    set_smem2(tcn2_bwd_up_kernel<NT, FOLD>, smem);                     \
+    tcn2_bwd_up_kernel<NT, FOLD><<<grid, W * 32, smem, (cudaStream_t)s>>>(p)
+    if (nt == 1) { if (fold.sg) { T2_BWD_UP(1, true); } else { T2_BWD_UP(1, false); } }
+    else { if (fold.sg) { T2_BWD_UP(2, true); } else { T2_BWD_UP(2, false); } }
+#undef T2_BWD_UP
     return finish_launch("tcn2_bwd_up");
 }
 

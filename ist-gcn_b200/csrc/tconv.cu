@@ -62,7 +62,7 @@ __global__ void bn_back_colsum_kernel(const float* __restrict__ g, const float* 
                                       const float* __restrict__ p, const float* __restrict__ m1,
                                       const float* __restrict__ cc, const float* __restrict__ mean,
                                       float* __restrict__ dz, float* __restrict__ colsum, int frames,
-                                      int n, int C, int frames_per_cta) {
+                                      int n, int C, int frames_per_cta, BnBwdFold fold) {
     // flat (slab, column) index: no idle lanes when V*C/4 is not a multiple of the block size
     const int n4 = n / 4;
     const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -70,7 +70,17 @@ __global__ void bn_back_colsum_kernel(const float* __restrict__ g, const float* 
     const int f0 = slab * frames_per_cta, f1 = min(frames, f0 + frames_per_cta);
     for (int j4 = (int)(gid - (long long)slab * n4); f0 < f1 && j4 < n4; j4 += n4) {
         const int c = (j4 * 4) % C;
-        const float4 pv = ld4(p + c), mv = ld4(m1 + c), cv = ld4(cc + c), nv = ld4(mean + c);
+        float4 pv, mv, cv;
+        if (fold.sg) {                   // coefficients from the raw sums; the first C/4 threads store them
+            const bool wr = gid < C / 4;
+            bn_bwd_fold(fold, c, wr, pv.x, mv.x, cv.x);
+            bn_bwd_fold(fold, c + 1, wr, pv.y, mv.y, cv.y);
+            bn_bwd_fold(fold, c + 2, wr, pv.z, mv.z, cv.z);
+            bn_bwd_fold(fold, c + 3, wr, pv.w, mv.w, cv.w);
+        } else {
+            pv = ld4(p + c); mv = ld4(m1 + c); cv = ld4(cc + c);
+        }
+        const float4 nv = ld4(mean + c);
         float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
         int f = f0;
         for (; f + 4 <= f1; f += 4) {                 // eight independent loads in flight
@@ -200,11 +210,35 @@ ISTGCN_API int istgcn_bn_back_apply(const float* go, const float* u, const float
 
 // dz[frames*V][C] = p*((g - m1) - c*(z - mean)) and colsum[V][C] += sum over frames of dz
 // (caller-zeroed) in one pass.  C % 4 == 0.
+static int launch_bn_back_colsum(const float* g, const float* z, const float* p, const float* m1,
+                                 const float* c, const float* mean, float* dz, float* colsum, int frames,
+                                 int V, int C, const BnBwdFold& fold, istgcn_stream_t s);
+
 ISTGCN_API int istgcn_bn_back_colsum(const float* g, const float* z, const float* p, const float* m1,
                                      const float* c, const float* mean, float* dz, float* colsum,
                                      int frames, int V, int C, istgcn_stream_t s) {
     ISTGCN_REQUIRE(g && z && p && m1 && c && mean && dz && colsum, ISTGCN_E_ARG,
                    "bn_back_colsum: null pointer");
+    return launch_bn_back_colsum(g, z, p, m1, c, mean, dz, colsum, frames, V, C, BnBwdFold{}, s);
+}
+
+// The same with istgcn_bn_bwd_coeffs folded in: p / m1 / c (and dgamma / dbeta, may be NULL) are OUTPUTS
+// derived from sg = sum g, sgx = sum g * zhat over `count` rows.
+ISTGCN_API int istgcn_bn_back_colsum_bn(const float* g, const float* z, const double* sg, const double* sgx,
+                                        double count, const float* gamma, const float* rstd, float* p,
+                                        float* m1, float* c, float* dgamma, float* dbeta, const float* mean,
+                                        float* dz, float* colsum, int frames, int V, int C,
+                                        istgcn_stream_t s) {
+    ISTGCN_REQUIRE(g && z && sg && sgx && gamma && rstd && p && m1 && c && mean && dz && colsum, ISTGCN_E_ARG,
+                   "bn_back_colsum_bn: null pointer");
+    ISTGCN_REQUIRE(count > 0, ISTGCN_E_ARG, "bn_back_colsum_bn: empty batch");
+    const BnBwdFold fold{sg, sgx, 1.0 / count, gamma, rstd, p, m1, c, dgamma, dbeta};
+    return launch_bn_back_colsum(g, z, p, m1, c, mean, dz, colsum, frames, V, C, fold, s);
+}
+
+static int launch_bn_back_colsum(const float* g, const float* z, const float* p, const float* m1,
+                                 const float* c, const float* mean, float* dz, float* colsum, int frames,
+                                 int V, int C, const BnBwdFold& fold, istgcn_stream_t s) {
     ISTGCN_REQUIRE(C % 4 == 0 && V >= 1, ISTGCN_E_SHAPE, "bn_back_colsum: C=%d V=%d", C, V);
     if (frames == 0) return 0;
     const int n = V * C;
@@ -215,7 +249,7 @@ ISTGCN_API int istgcn_bn_back_colsum(const float* g, const float* z, const float
     const long long items = (long long)(n / 4) * ((frames + fpc - 1) / fpc);
     const int grid = (int)((items + 255) / 256);
     bn_back_colsum_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(g, z, p, m1, c, mean, dz, colsum, frames, n,
-                                                             C, fpc);
+                                                             C, fpc, fold);
     return finish_launch("bn_back_colsum");
 }
 

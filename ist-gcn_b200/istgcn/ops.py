@@ -62,6 +62,12 @@ def _bn_forward_coeffs(training, sum_, sumsq, count, weight, st, C, device):
     return st.running_mean, scale, None
 
 
+def _bn_fold_enabled():
+    """BatchNorm bookkeeping folded into the consumer kernels (istgcn_*_bn entry points) instead of the
+    one-block bn_finalize / bn_bwd_coeffs launches; ISTGCN_BN_FOLD=0 keeps the separate launches."""
+    return os.environ.get('ISTGCN_BN_FOLD', '1') != '0'
+
+
 def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, Cin, Cout, math):
     """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise."""
     if _gcn_small_ok(Cin, Cout):       # first block: 3 input channels, CUDA cores, full fp32
@@ -247,22 +253,33 @@ class STBlock(Function):
         z = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
         _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K,
                      Cin, Cout, math)
-        mean1, scale1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w, cfg.bn1,
-                                                  Cout, dev)
+        tcn2 = _tcn2_ok(Cout, bp)
+        fold = tcn2 and training and _bn_fold_enabled()      # BN bookkeeping inside the consumers
+        if fold:
+            scale1, mean1, rstd1, scale2, mean2, rstd2 = _coeffs(6, Cout, dev)
+        else:
+            mean1, scale1, rstd1 = _bn_forward_coeffs(training, stats[0], stats[1], R_in, bn1_w, cfg.bn1,
+                                                      Cout, dev)
         bn1_b, bn2_b = bn1_b.contiguous(), bn2_b.contiguous()
         h1 = torch.empty(NM, T, V, bp, device=dev, dtype=torch.float32)
         h2 = torch.empty(NM, Tout, V, bp, device=dev, dtype=torch.float32)
         u = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-        tcn2 = _tcn2_ok(Cout, bp)
         if tcn2:
-            call('tcn2_down', z, mean1, scale1, bn1_b, Wd, bd, h1, i64(R_in), Cout, bp)
+            if fold:
+                st1 = cfg.bn1
+                call('tcn2_down_bn', z, stats[0], stats[1], f64(R_in), bn1_w, bn1_b, st1.running_mean,
+                     st1.running_var, float(st1.momentum), float(st1.eps), mean1, scale1, rstd1, Wd, bd, h1,
+                     i64(R_in), Cout, bp)
+            else:
+                call('tcn2_down', z, mean1, scale1, bn1_b, Wd, bd, h1, i64(R_in), Cout, bp)
             call('tcn2_conv', h1, Weff, beff, h2, NM, T, V, bp, s)
             call('tcn2_up', h2, Wu, bu, u, stats[2], stats[3], i64(R_out), Cout, bp)
         else:
             call('tcn_fwd', z, mean1, scale1, bn1_b, Wd, bd, Weff, beff, Wu, bu, h1, h2, u, stats[2],
                  stats[3], NM, T, V, Cout, bp, s, math)
-        mean2, scale2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w, cfg.bn2,
-                                                  Cout, dev)
+        if not fold:
+            mean2, scale2, rstd2 = _bn_forward_coeffs(training, stats[2], stats[3], R_out, bn2_w, cfg.bn2,
+                                                      Cout, dev)
         rres = scale_r = mean_r = rstd_r = None
         res = None
         if cfg.res_mode == 1:
@@ -286,14 +303,28 @@ class STBlock(Function):
             else:
                 call('gcn_fwd', x, Wr, biasterm_r, cfg.ones, idn.dst_ptr, idn.dst_src, idn.dst_id, V,
                      None, rres, stats[4], stats[5], NM * Tout, V, 1, Cin, Cout, T, Tout, s, 0, math)
-            mean_r, scale_r, rstd_r = _bn_forward_coeffs(training, stats[4], stats[5], R_out, bnr_w,
-                                                         cfg.bnr, Cout, dev)
+            if fold:
+                scale_r, mean_r, rstd_r = _coeffs(3, Cout, dev)
+            else:
+                mean_r, scale_r, rstd_r = _bn_forward_coeffs(training, stats[4], stats[5], R_out, bnr_w,
+                                                             cfg.bnr, Cout, dev)
             bnr_b = bnr_b.contiguous()
             res = rres
         out = torch.empty(NM, Tout, V, Cout, device=dev, dtype=torch.float32)
-        call('block_tail_fwd', u, mean2, scale2, bn2_b, res, mean_r, scale_r,
-             bnr_b if cfg.res_mode == 2 else None, out, i64(R_out), Cout, float(drop_p),
-             u64(cfg.seed), step_counter(dev))
+        if fold:
+            st2, str_ = cfg.bn2, cfg.bnr
+            has_r = cfg.res_mode == 2
+            call('block_tail_fwd_bn', u, stats[2], stats[3], f64(R_out), bn2_w, bn2_b, st2.running_mean,
+                 st2.running_var, float(st2.momentum), float(st2.eps), mean2, scale2, rstd2, res,
+                 stats[4] if has_r else None, stats[5] if has_r else None, bnr_w if has_r else None,
+                 bnr_b if has_r else None, str_.running_mean if has_r else None,
+                 str_.running_var if has_r else None, float(str_.momentum) if has_r else 0.0,
+                 float(str_.eps) if has_r else 0.0, mean_r, scale_r, rstd_r, out, i64(R_out), Cout,
+                 float(drop_p), u64(cfg.seed), step_counter(dev))
+        else:
+            call('block_tail_fwd', u, mean2, scale2, bn2_b, res, mean_r, scale_r,
+                 bnr_b if cfg.res_mode == 2 else None, out, i64(R_out), Cout, float(drop_p),
+                 u64(cfg.seed), step_counter(dev))
 
         ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
         ctx.dims = (NM, T, Tout, V, Cin, Cout)
@@ -322,7 +353,9 @@ class STBlock(Function):
              sums[2] if rres is not None else None, sums[3] if rres is not None else None,
              i64(R_out), Cout, float(drop_p), u64(seed), step_counter(dev))
         p2, m12, c2, dg2, db2 = _coeffs(5, Cout, dev)
-        call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2, Cout)
+        fold = ctx.tcn2 and _bn_fold_enabled()          # bn_bwd_coeffs inside the consumer kernels
+        if not fold:
+            call('bn_bwd_coeffs', sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2, Cout)
         # every caller-zeroed fp32 accumulator of this block out of ONE zero-filled buffer (one fill
         # launch instead of twelve); each view starts on a 16-byte boundary
         need_r = cfg.res_mode == 2
@@ -342,8 +375,13 @@ class STBlock(Function):
         dh2 = torch.empty(R_out, bp, device=dev, dtype=torch.float32)
         dh1 = torch.empty(R_in, bp, device=dev, dtype=torch.float32)
         if ctx.tcn2:
-            call('tcn2_bwd_up', go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, i64(R_out), Cout,
-                 bp, float(drop_p), u64(seed), step_counter(dev))
+            if fold:
+                call('tcn2_bwd_up_bn', go, u, sums[0], sums[1], f64(R_out), bn2_w, rstd2, p2, m12, c2, dg2, db2,
+                     mean2, h2, Wu, dh2, dWu, dbu, dbeff, i64(R_out), Cout, bp, float(drop_p), u64(seed),
+                     step_counter(dev))
+            else:
+                call('tcn2_bwd_up', go, u, p2, m12, c2, mean2, h2, Wu, dh2, dWu, dbu, dbeff, i64(R_out), Cout,
+                     bp, float(drop_p), u64(seed), step_counter(dev))
             if getattr(cfg, 'pair_async', False) and _pair_async_enabled() and \
                     os.environ.get('ISTGCN_DW_ASYNC', '1') != '0':
                 # the tap-weight gradient is needed by BlockPrep.backward only: gradient stream
@@ -359,7 +397,10 @@ class STBlock(Function):
                  dh2, dh1, g1, sums[4], sums[5], dWd, dbd, dWeff, dbeff, dWu, dbu, NM, T, V, Cout, bp, s,
                  float(drop_p), u64(seed), step_counter(dev), math)
         p1, m11, c1, dg1, db1 = _coeffs(5, Cout, dev)
-        call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
+        # BN1's coefficients are folded into bn_back_colsum where that kernel is the consumer
+        fold1 = fold and use_tc() and _gcn_tc2_ok(Cout, Cin) and not (_gcn_small_ok(Cin, Cout) and cfg.res_mode == 0)
+        if not fold1:
+            call('bn_bwd_coeffs', sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1, dg1, db1, Cout)
         # identity residual: the block-input gradient starts as `go` and the graph-conv input
         # gradient is accumulated onto it in place (TMA reduce-add on the tcgen05 engine); every
         # other reader of `go` has already run on this stream
@@ -395,7 +436,11 @@ class STBlock(Function):
                 # second-generation engine (csrc/gcn_tc2.cu): its input arrives by TMA, so dz
                 # (BatchNorm backward of g1) is materialised by the element-wise kernel first
                 # (the same pass sums dz over frames: the bias-term gradient dbt)
-                call('bn_back_colsum', g1, z, p1, m11, c1, mean1, dz, dbt, NM * T, V, Cout)
+                if fold1:
+                    call('bn_back_colsum_bn', g1, z, sums[4], sums[5], f64(R_in), bn1_w, rstd1, p1, m11, c1,
+                         dg1, db1, mean1, dz, dbt, NM * T, V, Cout)
+                else:
+                    call('bn_back_colsum', g1, z, p1, m11, c1, mean1, dz, dbt, NM * T, V, Cout)
                 dbt_done = True
                 call('gcn_tc', dz, None, None, None, None, None, Wc, vals, pat.t_ptr, pat.t_src,
                      pat.t_id, pat.nnz, None, None, add_in, gin, None, None, None, NM * T, V, K, Cout,
