@@ -504,3 +504,49 @@ def test_data_parallel_two_ranks_nccl(tmp_path):
         assert rel_l2(pg, pe) < 1e-3, mode
         # (five steps at lr 0.05 amplify the atomics-order noise between the runs)
         assert max(abs(a - b) / abs(a) for a, b in zip(res[False]['losses'], res[mode]['losses'])) < 5e-3, mode
+
+
+# ----------------------------------------------------------------------------- A/B switches
+@pytest.mark.parametrize('switch', ['ISTGCN_PAIR_ASYNC=0', 'ISTGCN_DW_ASYNC=0', 'ISTGCN_BN_FOLD=0',
+                                    'ISTGCN_PAIR_NB_MAX=128', 'ISTGCN_PAIR_BLOCKS=0', 'ISTGCN_PAIR_BLOCKS=1'])
+def test_ab_switches_give_the_same_step(env, monkeypatch, switch):
+    """The environment switches documented in DESIGN.md section 6 select alternative schedules of the
+    SAME arithmetic (gradient stream on / off, BatchNorm bookkeeping folded into its consumers or not,
+    item shapes of the pair-moment gradient): loss, every parameter gradient and the BatchNorm running
+    statistics of one fast-mode training iteration must agree with the default path to rounding
+    (bound: 10x the run-to-run noise of the default path, see below)."""
+    mg, g_args, num_class, shape, state, x, label = _case('ist_gcn')
+    env.set_math('tf32')
+    x, label = x.cuda(), label.cuda()
+
+    def run():
+        torch.manual_seed(0)
+        model = _model('ist_gcn', shape, num_class, g_args, state)
+        model.train()
+        # item plans are cached per pattern object: a fresh model re-plans under the current switches
+        loss = F.cross_entropy(model(x), label)
+        loss.backward()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
+        stats = {n: b.detach().clone() for n, b in model.named_buffers() if 'running' in n}
+        return loss.item(), grads, stats
+
+    loss0, g0, s0 = run()
+    loss0b, g0b, s0b = run()
+    key, val = switch.split('=')
+    monkeypatch.setenv(key, val)
+    loss1, g1, s1 = run()
+    monkeypatch.delenv(key)
+    # two runs of the DEFAULT path already differ in the last bits (atomic accumulation order of the
+    # BatchNorm sums and weight gradients, amplified through ten blocks): the bound is 10x that noise,
+    # with a floor (1e-2 on gradients) far below what a wrong schedule (a missed join, a stale
+    # coefficient: errors of order one) would produce
+    noise_l = abs(loss0b - loss0)
+    assert abs(loss1 - loss0) <= max(10 * noise_l, 1e-3 * max(1.0, abs(loss0)))
+    assert g0.keys() == g1.keys()
+    for n in g0:
+        noise = rel_l2(g0b[n], g0[n], floor=1e-12)
+        assert rel_l2(g1[n], g0[n], floor=1e-12) < max(10 * noise, 1e-2), n
+    for n in s0:
+        noise = rel_l2(s0b[n], s0[n], floor=1e-12)
+        assert rel_l2(s1[n], s0[n], floor=1e-12) < max(10 * noise, 2e-3), n
