@@ -178,8 +178,22 @@ int istgcn_gcn_pair_grads(const float* dz, const float* x, const float* vals, co
  *                  (k, source v) with tsrc = destination w.  Cout = 64.                        */
 int istgcn_gcn_small_fwd(const float* x, const float* Wc, const float* biasterm, const float* vals,
                          const int* lptr, const int* lsrc, const int* lid, int nnz, float* out,
-                         double* stat_sum, double* stat_sumsq, int frames, int V, int K, int Cin,
-                         int Cout, istgcn_stream_t s);
+                         double* stat_sum, double* stat_sumsq, float* xagg_out, float* zsum_out,
+                         int frames, int V, int K, int Cin, int Cout, istgcn_stream_t s);
+/* The same backward with its heavy part on the tensor core (fast mode).  The forward optionally stores
+ * xagg_out [frames*V][16] = the aggregated input X'[(f,w)][k*4 + c] (TF32-rounded) and zsum_out [V][Cout]
+ * += sum_f out[(f,w)][n] (Cout = 64).  Backward = istgcn_tcn2_bwd_up(go = g1, u = z, BN1-backward
+ * coefficients, h2 = X', Wu = Wc padded to [16][64] rows k*4 + c, C = 64, bp = 16): its dh2 is
+ * G[(f,w)][k*4+c] = sum_n dz[(f,w)][n] Wc[k*Cin+c][n], its dWu the weight gradient; then
+ * istgcn_joint_colsum(g1) and istgcn_gcn_small_bwd_post: dx (written), dvals += ..., and
+ * dbt[w][n] += p[n]((sg1[w][n] - F m1[n]) - c[n](sz[w][n] - F mu[n])) -- dz is affine in (g1, z).   */
+int istgcn_joint_colsum(const float* a, float* sums, int frames, int V, int C, istgcn_stream_t s);
+int istgcn_gcn_small_bwd_post(const float* G, const float* x, const float* vals, const int* lptr,
+                              const int* lsrc, const int* lid, const int* tptr, const int* tsrc,
+                              const int* tid, int nnz, float* dx, float* dvals, const float* sg1,
+                              const float* sz, const float* bn_p, const float* bn_m1, const float* bn_c,
+                              const float* bn_mu, float* dbt, int frames, int V, int K, int Cin, int Cout,
+                              istgcn_stream_t s);
 int istgcn_gcn_small_bwd(const float* g1, const float* z, const float* bn_p, const float* bn_m1,
                          const float* bn_c, const float* bn_mu, const float* x, const float* Wc,
                          const float* vals, const int* lptr, const int* lsrc, const int* lid,

@@ -58,7 +58,8 @@ template <int COUT>
 __global__ void __launch_bounds__(512, 1)
 gcn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wc,
                      const float* __restrict__ biasterm, SmallLists L, float* __restrict__ out,
-                     double* stat_sum, double* stat_sumsq, long long frames, int V, int K, int Cin) {
+                     double* stat_sum, double* stat_sumsq, float* __restrict__ xagg_out,
+                     float* __restrict__ zsum_out, long long frames, int V, int K, int Cin) {
     constexpr int CG = COUT / 4;                 // channel groups per row
     constexpr int WPB = 512 / CG;                // joints handled per pass
     __shared__ __align__(16) float xs[kSmallFT * 32 * 4];
@@ -82,6 +83,11 @@ gcn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wc,
         const int nf = (int)min((long long)kSmallFT, frames - f0);
         __syncthreads();
         small_stage(x, xs, xa, L, f0, nf, V, K, Cin, tid, 512);
+        if (xagg_out)       // the aggregated input X'[(f,w)][k*4 + c], TF32-rounded: the backward's operand
+            for (int i = tid; i < nf * V * kSmallKC; i += 512)
+                xagg_out[(size_t)f0 * V * kSmallKC + i] =
+                    (i & (kSmallKC - 1)) < 4 * K ? __uint_as_float((__float_as_uint(xa[i]) + 0x1000u) & 0xFFFFE000u)
+                                                 : 0.f;
         float s4[4] = {0, 0, 0, 0}, q4[4] = {0, 0, 0, 0};
         for (int w = wslot; w < V; w += WPB) {
             const float4 bt = ld4(biasterm + (size_t)w * COUT + 4 * cg);
@@ -107,6 +113,10 @@ gcn_small_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wc,
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) { ds[c] += (double)s4[c]; dq[c] += (double)q4[c]; }
+    }
+    if (zsum_out && wslot < V && WPB >= V) {      // per-joint sums of the output over the frames
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(&zsum_out[(size_t)wslot * COUT + 4 * cg + c], (float)ds[c]);
     }
     if (stat_sum) {
 #pragma unroll
@@ -280,6 +290,120 @@ gcn_small_bwd_kernel(const float* __restrict__ g1, const float* __restrict__ z,
     }
 }
 
+// ----------------------------------------------------------------------------- backward, second form
+// The heavy part of the first block's backward has the shape of the temporal chain's up-projection
+// backward: with X' (aggregated input, 16 columns = K x 4) in the role of h2 and Wc (padded to 16 rows)
+// in the role of Wu, istgcn_tcn2_bwd_up computes dz = BN1-backward(g1, z) on the fly and from it
+//     G[(f,w)][kc] = sum_n dz[(f,w)][n] Wc16[kc][n]         (its dh2)
+//     dWc16[kc][n] += sum_rows X'[row][kc] dz[row][n]       (its dWu)
+// on the tensor core in ONE pass over (g1, z) at 0.6 of the HBM rate (the CUDA-core kernel above: 0.15).
+// What is left is cheap: the per-joint sums of g1 (below; together with the per-joint sums of z from the
+// forward they give dbt, because dz is affine in (g1, z)), and dx / dvals from the 16-wide G.
+
+// sums[w][c] += sum_f a[(f,w)][c]: thread = one float4 column of the [V*C] frame vector
+__global__ void joint_colsum_kernel(const float* __restrict__ a, float* __restrict__ sums, int frames, int n,
+                                    int frames_per_cta) {
+    const int n4 = n / 4;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int slab = (int)(gid / n4);
+    const int j4 = (int)(gid - (long long)slab * n4);
+    const int f0 = slab * frames_per_cta, f1 = min(frames, f0 + frames_per_cta);
+    if (f0 >= f1) return;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    int f = f0;
+    for (; f + 8 <= f1; f += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ld4(a + (size_t)(f + u) * n + j4 * 4);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { s.x += v[u].x; s.y += v[u].y; s.z += v[u].z; s.w += v[u].w; }
+    }
+    for (; f < f1; ++f) {
+        const float4 v = ld4(a + (size_t)f * n + j4 * 4);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    atomicAdd(sums + j4 * 4 + 0, s.x);
+    atomicAdd(sums + j4 * 4 + 1, s.y);
+    atomicAdd(sums + j4 * 4 + 2, s.z);
+    atomicAdd(sums + j4 * 4 + 3, s.w);
+}
+
+// dx[(f,v)][c] = sum_k sum_{j in t(k,v)} vals_j G[(f,w_j)][k*4+c]  (written),
+// dvals[j] += sum_{f,c} x[(f,v_j)][c] G[(f,w_j)][k_j*4+c], and the bias-term gradient
+// dbt[w][n] += p[n] * ((sg1[w][n] - F m1[n]) - c[n] * (sz[w][n] - F mu[n]))   (block 0 only)
+__global__ void __launch_bounds__(256)
+gcn_small_post_kernel(const float* __restrict__ Gg, const float* __restrict__ x, SmallLists L,
+                      float* __restrict__ dx, float* dvals, const float* __restrict__ sg1,
+                      const float* __restrict__ sz, const float* __restrict__ bn_p,
+                      const float* __restrict__ bn_m1, const float* __restrict__ bn_c,
+                      const float* __restrict__ bn_mu, float* dbt, long long frames, int V, int K, int Cin,
+                      int Cout) {
+    constexpr int FT = 16;                                   // frames per tile
+    __shared__ __align__(16) float xs[FT * 32 * 4];
+    __shared__ __align__(16) float G[FT * 32 * kSmallKC];
+    const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && dbt)
+        for (int i = tid; i < V * Cout; i += 256) {
+            const int n = i % Cout;
+            const float F = (float)frames;
+            dbt[i] += bn_p[n] * ((sg1[i] - F * bn_m1[n]) - bn_c[n] * (sz[i] - F * bn_mu[n]));
+        }
+    float dv[4] = {0.f, 0.f, 0.f, 0.f};                      // entries tid, tid + 256, ... of the (k, w) lists
+    int ent_kw[4] = {-1, -1, -1, -1}, ent_v[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+        const int e = tid + 256 * h;
+        if (e < L.nnz) {                                     // largest kw with lptr[kw] <= e
+            int lo = 0, hi = K * V;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (L.lptr[mid] <= e) lo = mid; else hi = mid;
+            }
+            ent_kw[h] = lo;
+            ent_v[h] = L.lsrc[e];
+        }
+    }
+    const long long tiles = (frames + FT - 1) / FT;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const long long f0 = tile * FT;
+        const int nf = (int)min((long long)FT, frames - f0);
+        __syncthreads();
+        for (int i = tid; i < nf * V * 4; i += 256) {
+            const int c = i & 3, r = i >> 2;
+            xs[i] = c < Cin ? x[(f0 * V + r) * Cin + c] : 0.f;
+        }
+        for (int i = tid; i < nf * V * (kSmallKC / 4); i += 256)
+            reinterpret_cast<float4*>(G)[i] = ld4(Gg + (size_t)f0 * V * kSmallKC + 4 * (size_t)i);
+        __syncthreads();
+        for (int i = tid; i < nf * V * Cin; i += 256) {
+            const int c = i % Cin, r = i / Cin;
+            const int f = r / V, v = r - f * V;
+            float acc = 0.f;
+            for (int k = 0; k < K; ++k)
+                for (int j = L.tptr[k * V + v]; j < L.tptr[k * V + v + 1]; ++j)
+                    acc = fmaf(L.vals[L.tid[j]], G[(f * V + L.tsrc[j]) * kSmallKC + k * 4 + c], acc);
+            dx[((f0 + f) * V + v) * Cin + c] = acc;
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (ent_kw[h] < 0) continue;
+            const int k = ent_kw[h] / V, wd = ent_kw[h] - k * V, v = ent_v[h];
+            float acc = 0.f;
+            for (int f = 0; f < nf; ++f) {
+                const float4 xv = *reinterpret_cast<const float4*>(xs + (f * V + v) * 4);
+                const float4 gq = *reinterpret_cast<const float4*>(G + (f * V + wd) * kSmallKC + k * 4);
+                acc += xv.x * gq.x + xv.y * gq.y + xv.z * gq.z + xv.w * gq.w;
+            }
+            dv[h] += acc;
+        }
+    }
+    if (dvals) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h)
+            if (tid + 256 * h < L.nnz) atomicAdd(&dvals[L.lid[tid + 256 * h]], dv[h]);
+    }
+}
+
 }  // namespace istgcn
 
 using namespace istgcn;
@@ -289,7 +413,8 @@ using namespace istgcn;
 ISTGCN_API int istgcn_gcn_small_fwd(const float* x, const float* Wc, const float* biasterm,
                                     const float* vals, const int* lptr, const int* lsrc, const int* lid,
                                     int nnz, float* out, double* stat_sum, double* stat_sumsq,
-                                    int frames, int V, int K, int Cin, int Cout, istgcn_stream_t s) {
+                                    float* xagg_out, float* zsum_out, int frames, int V, int K, int Cin,
+                                    int Cout, istgcn_stream_t s) {
     ISTGCN_REQUIRE(x && Wc && biasterm && vals && lptr && lsrc && lid && out, ISTGCN_E_ARG,
                    "gcn_small_fwd: null pointer");
     ISTGCN_REQUIRE((stat_sum == nullptr) == (stat_sumsq == nullptr), ISTGCN_E_ARG,
@@ -309,10 +434,10 @@ ISTGCN_API int istgcn_gcn_small_fwd(const float* x, const float* Wc, const float
     cudaStream_t st = (cudaStream_t)s;
     if (Cout == 64)
         gcn_small_fwd_kernel<64><<<grid, 512, 0, st>>>(x, Wc, biasterm, L, out, stat_sum, stat_sumsq,
-                                                       frames, V, K, Cin);
+                                                       xagg_out, zsum_out, frames, V, K, Cin);
     else
         gcn_small_fwd_kernel<128><<<grid, 512, 0, st>>>(x, Wc, biasterm, L, out, stat_sum, stat_sumsq,
-                                                        frames, V, K, Cin);
+                                                        xagg_out, nullptr, frames, V, K, Cin);
     return finish_launch("gcn_small_fwd");
 }
 
@@ -348,4 +473,46 @@ ISTGCN_API int istgcn_gcn_small_bwd(const float* g1, const float* z, const float
         gcn_small_bwd_kernel<4><<<grid, 512, 0, (cudaStream_t)s>>>(g1, z, bn_p, bn_m1, bn_c, bn_mu, x, Wc, L,
                                                                   dx, dvals, dWc, dbt, frames, V, K, Cin);
     return finish_launch("gcn_small_bwd");
+}
+
+// sums[V][C] += sum over frames of a[(f,v)][c] (caller-zeroed; C % 4 == 0)
+ISTGCN_API int istgcn_joint_colsum(const float* a, float* sums, int frames, int V, int C, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(a && sums, ISTGCN_E_ARG, "joint_colsum: null pointer");
+    ISTGCN_REQUIRE(C % 4 == 0 && V >= 1, ISTGCN_E_SHAPE, "joint_colsum: C=%d V=%d", C, V);
+    if (frames == 0) return 0;
+    const int n = V * C;
+    int slabs = (num_sms() * 8 * 256) / (n / 4);
+    if (slabs < 1) slabs = 1;
+    if (slabs > frames) slabs = frames;
+    const int fpc = (frames + slabs - 1) / slabs;
+    const long long items = (long long)(n / 4) * ((frames + fpc - 1) / fpc);
+    joint_colsum_kernel<<<(int)((items + 255) / 256), 256, 0, (cudaStream_t)s>>>(a, sums, frames, n, fpc);
+    return finish_launch("joint_colsum");
+}
+
+// Tail of the first block's backward behind the tensor-core pass (see above): G [frames*V][16] is the
+// dh2 of istgcn_tcn2_bwd_up run on (g1, z, X', Wc16).  dx [frames*V][Cin] written; dvals, dbt [V][Cout]
+// accumulated (may be NULL); sg1 / sz [V][Cout] = per-joint sums over the frames of g1 / z.
+ISTGCN_API int istgcn_gcn_small_bwd_post(const float* G, const float* x, const float* vals, const int* lptr,
+                                         const int* lsrc, const int* lid, const int* tptr, const int* tsrc,
+                                         const int* tid, int nnz, float* dx, float* dvals, const float* sg1,
+                                         const float* sz, const float* bn_p, const float* bn_m1,
+                                         const float* bn_c, const float* bn_mu, float* dbt, int frames,
+                                         int V, int K, int Cin, int Cout, istgcn_stream_t s) {
+    ISTGCN_REQUIRE(G && x && vals && lptr && lsrc && lid && tptr && tsrc && tid && dx, ISTGCN_E_ARG,
+                   "gcn_small_bwd_post: null pointer");
+    ISTGCN_REQUIRE(dbt == nullptr || (sg1 && sz && bn_p && bn_m1 && bn_c && bn_mu), ISTGCN_E_ARG,
+                   "gcn_small_bwd_post: dbt needs the per-joint sums and the BatchNorm coefficients");
+    ISTGCN_REQUIRE(V >= 1 && V <= 32 && K >= 1 && K <= 4 && Cin >= 1 && Cin <= 4, ISTGCN_E_SHAPE,
+                   "gcn_small_bwd_post: V=%d K=%d Cin=%d unsupported", V, K, Cin);
+    ISTGCN_REQUIRE(nnz >= 0 && nnz <= 1024, ISTGCN_E_SHAPE, "gcn_small_bwd_post: nnz=%d", nnz);
+    ISTGCN_REQUIRE((reinterpret_cast<uintptr_t>(G) & 15) == 0, ISTGCN_E_ARG, "gcn_small_bwd_post: G alignment");
+    if (frames == 0) return 0;
+    SmallLists L{vals, lptr, lsrc, lid, tptr, tsrc, tid, nnz};
+    const long long tiles = ((long long)frames + 15) / 16;
+    int grid = num_sms() * 4;
+    if (grid > tiles) grid = (int)tiles;
+    gcn_small_post_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(G, x, L, dx, dvals, sg1, sz, bn_p, bn_m1, bn_c, bn_mu,
+                                                             dbt, frames, V, K, Cin, Cout);
+    return finish_launch("gcn_small_bwd_post");
 }

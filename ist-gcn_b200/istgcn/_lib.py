@@ -17,7 +17,7 @@ SYMBOLS = (
     'istgcn_data_bn_stats', 'istgcn_data_bn_apply', 'istgcn_data_bn_bwd',
     'istgcn_bn_finalize', 'istgcn_bn_eval_coeffs', 'istgcn_bn_bwd_coeffs',
     'istgcn_gcn_fwd', 'istgcn_gcn_bwd_x', 'istgcn_gcn_bwd_w', 'istgcn_gcn_tc', 'istgcn_gcn_tc_dvals', 'istgcn_gcn_tc_dw', 'istgcn_gcn_pair_grads', 'istgcn_tcn2_down_bn', 'istgcn_tcn2_bwd_up_bn', 'istgcn_bn_back_colsum_bn',
-    'istgcn_block_tail_fwd_bn',
+    'istgcn_block_tail_fwd_bn', 'istgcn_joint_colsum', 'istgcn_gcn_small_bwd_post',
     'istgcn_gcn_small_fwd', 'istgcn_gcn_small_bwd',
     'istgcn_tcn_fwd', 'istgcn_tcn_bwd',
     'istgcn_tcn2_down', 'istgcn_tcn2_conv', 'istgcn_tcn2_up', 'istgcn_tcn2_bwd_up', 'istgcn_tcn2_bwd_conv',

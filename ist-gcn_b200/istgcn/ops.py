@@ -68,11 +68,23 @@ def _bn_fold_enabled():
     return os.environ.get('ISTGCN_BN_FOLD', '1') != '0'
 
 
-def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, Cin, Cout, math):
-    """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise."""
+def _small_bwd_tc_enabled():
+    """First block's backward with its heavy part on the tensor core (istgcn_tcn2_bwd_up on the
+    aggregated input, csrc/gcn_small.cu); ISTGCN_SMALL_BWD_TC=0 keeps the one-kernel CUDA-core form."""
+    return os.environ.get('ISTGCN_SMALL_BWD_TC', '1') != '0'
+
+
+def _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, s_sum, s_sq, frames, V, K, Cin, Cout, math, keep=None):
+    """The fused graph convolution: tcgen05 engine when enabled, mma.sync engine otherwise.
+    ``keep``: dict that receives what the first block's tensor-core backward needs (X', per-joint sums)."""
     if _gcn_small_ok(Cin, Cout):       # first block: 3 input channels, CUDA cores, full fp32
+        xagg = zsum = None
+        if keep is not None:
+            xagg = torch.empty(frames * V, 16, device=x.device, dtype=torch.float32)
+            zsum = torch.zeros(V, Cout, device=x.device, dtype=torch.float32)
+            keep['xagg'], keep['zsum'] = xagg, zsum
         call('gcn_small_fwd', x, Wc, biasterm, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.nnz, z,
-             s_sum, s_sq, frames, V, K, Cin, Cout)
+             s_sum, s_sq, xagg, zsum, frames, V, K, Cin, Cout)
     elif use_tc():
         W2, bias_k, colsum = W2        # graph_conv_operands: weight rows + the bias-term factors
         W2 = W2.contiguous()
@@ -251,9 +263,13 @@ class STBlock(Function):
         stats = torch.zeros(6, Cout, device=dev, dtype=torch.float64) if training else [None] * 6
 
         z = torch.empty(NM, T, V, Cout, device=dev, dtype=torch.float32)
-        _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K,
-                     Cin, Cout, math)
         tcn2 = _tcn2_ok(Cout, bp)
+        # first block, training, fast mode: the backward runs on the tensor core and wants X' and the
+        # per-joint sums of z from this pass
+        keep = {} if (training and tcn2 and _gcn_small_ok(Cin, Cout) and cfg.res_mode == 0 and Cin <= 3
+                      and pat.K <= 4 and _small_bwd_tc_enabled()) else None
+        _gcn_forward(x, Wc, W2, biasterm, vals, pat, z, stats[0], stats[1], NM * T, V, K,
+                     Cin, Cout, math, keep)
         fold = tcn2 and training and _bn_fold_enabled()      # BN bookkeeping inside the consumers
         if fold:
             scale1, mean1, rstd1, scale2, mean2, rstd2 = _coeffs(6, Cout, dev)
@@ -329,6 +345,7 @@ class STBlock(Function):
         ctx.cfg, ctx.training, ctx.math, ctx.drop_p, ctx.seed = cfg, training, math, drop_p, cfg.seed
         ctx.dims = (NM, T, Tout, V, Cin, Cout)
         ctx.tcn2 = tcn2
+        ctx.small_keep = keep
         if training:
             ctx.save_for_backward(x, vals, Wc, z, h1, h2, u, out, rres, scale1, bn1_b, mean1, rstd1,
                                   mean2, rstd2, mean_r, rstd_r, Wd, Weff, Wu, Wr, bn1_w, bn2_w, bnr_w)
@@ -423,7 +440,26 @@ class STBlock(Function):
             add_in = gin
         small = _gcn_small_ok(Cin, Cout) and cfg.res_mode == 0
         dbt_done = pair = False
-        if small:
+        if small and ctx.small_keep is not None:
+            # first block, tensor-core form (csrc/gcn_small.cu, second form): the up-projection backward
+            # of the temporal chain on (g1, z, X', Wc16) gives G = dz Wc^T and the weight gradient in one
+            # pass over (g1, z); per-joint sums of g1; dx / dvals / dbt from the 16-wide G
+            keep = ctx.small_keep
+            Wc16 = torch.zeros(4, 4, Cout, device=dev, dtype=torch.float32)
+            Wc16[:K, :Cin] = Wc.view(K, Cin, Cout)
+            G = torch.empty(R_in, 16, device=dev, dtype=torch.float32)
+            scratch = torch.zeros(16 * Cout + Cout + 16 + V * Cout, device=dev, dtype=torch.float32)
+            dW16 = scratch[:16 * Cout].view(16, Cout)
+            sg1 = scratch[16 * Cout + Cout + 16:].view(V, Cout)
+            call('tcn2_bwd_up', g1, z, p1, m11, c1, mean1, keep['xagg'], Wc16.view(16, Cout), G, dW16,
+                 scratch[16 * Cout:16 * Cout + Cout], scratch[16 * Cout + Cout:16 * Cout + Cout + 16],
+                 i64(R_in), Cout, 16, 0.0, u64(0), None)
+            call('joint_colsum', g1, sg1, NM * T, V, Cout)
+            call('gcn_small_bwd_post', G, x, vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.t_ptr, pat.t_src,
+                 pat.t_id, pat.nnz, gin, dvals, sg1, keep['zsum'], p1, m11, c1, mean1, dbt, NM * T, V, K, Cin,
+                 Cout)
+            dWc += dW16.view(4, 4, Cout)[:K, :Cin].reshape(K * Cin, Cout)
+        elif small:
             # first block: dz, dx, dvals, dWc and dbt in one CUDA-core kernel
             call('gcn_small_bwd', g1, z, p1, m11, c1, mean1, x, Wc, vals, pat.dst_ptr, pat.dst_src,
                  pat.dst_id, pat.t_ptr, pat.t_src, pat.t_id, pat.nnz, gin, dvals, dWc, dbt, NM * T, V,

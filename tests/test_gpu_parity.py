@@ -198,10 +198,17 @@ def test_first_block_kernels_vs_fp64(env, layout, strategy, cin, nm, t):
     ref = torch.einsum('fvc,kvw,kcn->fwn', x64, A64, W64.view(K, cin, cout)) + bt.double()
     out = torch.full((frames, V, cout), float('nan'), device=dev)
     st = torch.zeros(2, cout, device=dev, dtype=torch.float64)
+    xagg = torch.full((frames * V, 16), float('nan'), device=dev)
+    zsum = torch.zeros(V, cout, device=dev)
     call('gcn_small_fwd', x.to(dev), Wc.to(dev), bt.to(dev), vals, pat.dst_ptr, pat.dst_src, pat.dst_id,
-         pat.nnz, out, st[0], st[1], frames, V, K, cin, cout)
+         pat.nnz, out, st[0], st[1], xagg, zsum, frames, V, K, cin, cout)
     assert rel(out, ref) < 1e-5
     assert rel(st[0], ref.sum((0, 1))) < 1e-5 and rel(st[1], (ref * ref).sum((0, 1))) < 1e-5
+    # by-products for the tensor-core backward: X'[(f,w)][k*4+c] (TF32-rounded) and per-joint sums
+    xa_ref = torch.zeros(frames, V, 4, 4, dtype=torch.float64)
+    xa_ref[:, :, :K, :cin] = torch.einsum('fvc,kvw->fwkc', x.double(), A)
+    assert rel(xagg, xa_ref.reshape(frames * V, 16)) < 1e-3
+    assert rel(zsum, ref.detach().sum(0)) < 1e-5
     g1 = torch.randn(frames, V, cout, generator=gen)
     z = torch.randn(frames, V, cout, generator=gen)
     p, m1, c, mu = (torch.randn(cout, generator=gen) * s + o for s, o in ((0.2, 1.0), (0.1, 0), (0.1, 0), (0.5, 0)))
@@ -216,6 +223,33 @@ def test_first_block_kernels_vs_fp64(env, layout, strategy, cin, nm, t):
     assert rel(dWc, W64.grad) < 1e-5
     assert rel(dbt, dz.sum(0)) < 1e-5
     assert rel(dvals, A64.grad.reshape(-1)[pat.flat_idx.cpu()]) < 1e-5
+    # the same gradients with the heavy part on the tensor core (single-pass TF32: the fast mode's
+    # per-operator bar, 5e-3): tcn2_bwd_up on (g1, z, X', Wc16), joint_colsum, gcn_small_bwd_post
+    from istgcn._lib import i64, u64
+    R = frames * V
+    Wc16 = torch.zeros(K, 4, cout, device=dev)
+    Wc16[:, :cin] = Wc.to(dev).view(K, cin, cout)
+    Wc16 = torch.cat([Wc16, torch.zeros(4 - K, 4, cout, device=dev)]).view(16, cout) if K < 4 else Wc16.view(16, cout)
+    G = torch.full((R, 16), float('nan'), device=dev)
+    dW16, dbu, dbe = torch.zeros(16, cout, device=dev), torch.zeros(cout, device=dev), torch.zeros(16, device=dev)
+    g1d, zd = g1.to(dev).contiguous(), z.to(dev).contiguous()
+    zsum_z = torch.zeros(V, cout, device=dev)
+    call('joint_colsum', zd, zsum_z, frames, V, cout)
+    assert rel(zsum_z, z.double().sum(0)) < 1e-5
+    call('tcn2_bwd_up', g1d, zd, p.to(dev), m1.to(dev), c.to(dev), mu.to(dev), xagg, Wc16, G, dW16, dbu, dbe,
+         i64(R), cout, 16, 0.0, u64(0), None)
+    sg1 = torch.zeros(V, cout, device=dev)
+    call('joint_colsum', g1d, sg1, frames, V, cout)
+    dx2 = torch.full((frames, V, cin), float('nan'), device=dev)
+    dvals2, dbt2 = torch.zeros_like(vals), torch.zeros(V, cout, device=dev)
+    call('gcn_small_bwd_post', G, x.to(dev), vals, pat.dst_ptr, pat.dst_src, pat.dst_id, pat.t_ptr, pat.t_src,
+         pat.t_id, pat.nnz, dx2, dvals2, sg1, zsum_z, p.to(dev), m1.to(dev), c.to(dev), mu.to(dev), dbt2,
+         frames, V, K, cin, cout)
+    dWc2 = dW16.view(4, 4, cout)[:K, :cin].reshape(K * cin, cout)
+    assert rel(dx2, x64.grad) < 5e-3
+    assert rel(dWc2, W64.grad) < 5e-3
+    assert rel(dbt2, dz.sum(0), floor=1e-2) < 1e-4
+    assert rel(dvals2, A64.grad.reshape(-1)[pat.flat_idx.cpu()]) < 5e-3
 
 
 # ----------------------------------------------------------------------------- tcgen05, 2nd generation
