@@ -166,6 +166,14 @@ def algorithmic_bytes(kernel, batch, shape):
         elif kernel == 'tcn2_bwd_up':    # reads go, u, h2, writes dh2
             bp = 8 if int(cout ** 0.5) <= 8 else 16
             per_launch.append(4 * r_out * (2 * cout + 2 * bp))
+            if cin < 32:                 # block 0's graph-conv backward runs on the same kernel:
+                per_launch.append(4 * r_in * (2 * cout + 2 * 16))      # reads g1, z, X', writes G
+        elif kernel == 'joint_colsum':   # block 0: per-joint sums of g1
+            if cin < 32:
+                per_launch.append(4 * r_in * cout)
+        elif kernel == 'gcn_small_bwd_post':   # block 0: reads G (16 wide), x, writes dx
+            if cin < 32:
+                per_launch.append(4 * r_in * (16 + 2 * cin))
         elif kernel == 'tcn2_bwd_conv':  # reads dh2, h1 (twice: data + weight kernel), writes dh1
             bp = 8 if int(cout ** 0.5) <= 8 else 16
             per_launch.append(4 * (2 * r_in + 2 * r_out) * bp)
