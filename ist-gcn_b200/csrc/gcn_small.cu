@@ -341,7 +341,14 @@ gcn_small_post_kernel(const float* __restrict__ Gg, const float* __restrict__ x,
     constexpr int FT = 16;                                   // frames per tile
     __shared__ __align__(16) float xs[FT * 32 * 4];
     __shared__ __align__(16) float G[FT * 32 * kSmallKC];
+    __shared__ int s_tptr[4 * 32 + 1];                       // the transposed lists, once per CTA
+    __shared__ int s_tsrc[1024];
+    __shared__ float s_tval[1024];
     const int tid = threadIdx.x;
+    __shared__ int s_lptr[4 * 32 + 1];
+    for (int i = tid; i <= K * V; i += 256) { s_tptr[i] = L.tptr[i]; s_lptr[i] = L.lptr[i]; }
+    for (int i = tid; i < L.nnz; i += 256) { s_tsrc[i] = L.tsrc[i]; s_tval[i] = L.vals[L.tid[i]]; }
+    __syncthreads();
     if (blockIdx.x == 0 && dbt)
         for (int i = tid; i < V * Cout; i += 256) {
             const int n = i % Cout;
@@ -357,7 +364,7 @@ gcn_small_post_kernel(const float* __restrict__ Gg, const float* __restrict__ x,
             int lo = 0, hi = K * V;
             while (hi - lo > 1) {
                 const int mid = (lo + hi) >> 1;
-                if (L.lptr[mid] <= e) lo = mid; else hi = mid;
+                if (s_lptr[mid] <= e) lo = mid; else hi = mid;
             }
             ent_kw[h] = lo;
             ent_v[h] = L.lsrc[e];
@@ -380,8 +387,8 @@ gcn_small_post_kernel(const float* __restrict__ Gg, const float* __restrict__ x,
             const int f = r / V, v = r - f * V;
             float acc = 0.f;
             for (int k = 0; k < K; ++k)
-                for (int j = L.tptr[k * V + v]; j < L.tptr[k * V + v + 1]; ++j)
-                    acc = fmaf(L.vals[L.tid[j]], G[(f * V + L.tsrc[j]) * kSmallKC + k * 4 + c], acc);
+                for (int j = s_tptr[k * V + v]; j < s_tptr[k * V + v + 1]; ++j)
+                    acc = fmaf(s_tval[j], G[(f * V + s_tsrc[j]) * kSmallKC + k * 4 + c], acc);
             dx[((f0 + f) * V + v) * Cin + c] = acc;
         }
 #pragma unroll
@@ -481,7 +488,7 @@ ISTGCN_API int istgcn_joint_colsum(const float* a, float* sums, int frames, int 
     ISTGCN_REQUIRE(C % 4 == 0 && V >= 1, ISTGCN_E_SHAPE, "joint_colsum: C=%d V=%d", C, V);
     if (frames == 0) return 0;
     const int n = V * C;
-    int slabs = (num_sms() * 8 * 256) / (n / 4);
+    int slabs = (num_sms() * 4 * 256) / (n / 4);      // long slabs: one atomic per thread and column at the end
     if (slabs < 1) slabs = 1;
     if (slabs > frames) slabs = frames;
     const int fpc = (frames + slabs - 1) / slabs;
@@ -510,7 +517,7 @@ ISTGCN_API int istgcn_gcn_small_bwd_post(const float* G, const float* x, const f
     if (frames == 0) return 0;
     SmallLists L{vals, lptr, lsrc, lid, tptr, tsrc, tid, nnz};
     const long long tiles = ((long long)frames + 15) / 16;
-    int grid = num_sms() * 4;
+    int grid = num_sms() * 2;
     if (grid > tiles) grid = (int)tiles;
     gcn_small_post_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(G, x, L, dx, dvals, sg1, sz, bn_p, bn_m1, bn_c, bn_mu,
                                                              dbt, frames, V, K, Cin, Cout);
