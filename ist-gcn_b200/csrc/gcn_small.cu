@@ -342,12 +342,12 @@ gcn_small_post_kernel(const float* __restrict__ Gg, const float* __restrict__ x,
     __shared__ __align__(16) float xs[FT * 32 * 4];
     __shared__ __align__(16) float G[FT * 32 * kSmallKC];
     __shared__ int s_tptr[4 * 32 + 1];                       // the transposed lists, once per CTA
-    __shared__ int s_tsrc[1024];
+    __shared__ unsigned char s_tsrc[1024];                   // joints < 32; 48 KB of static shared memory in all
     __shared__ float s_tval[1024];
     const int tid = threadIdx.x;
     __shared__ int s_lptr[4 * 32 + 1];
     for (int i = tid; i <= K * V; i += 256) { s_tptr[i] = L.tptr[i]; s_lptr[i] = L.lptr[i]; }
-    for (int i = tid; i < L.nnz; i += 256) { s_tsrc[i] = L.tsrc[i]; s_tval[i] = L.vals[L.tid[i]]; }
+    for (int i = tid; i < L.nnz; i += 256) { s_tsrc[i] = (unsigned char)L.tsrc[i]; s_tval[i] = L.vals[L.tid[i]]; }
     __syncthreads();
     if (blockIdx.x == 0 && dbt)
         for (int i = tid; i < V * Cout; i += 256) {
@@ -517,7 +517,7 @@ ISTGCN_API int istgcn_gcn_small_bwd_post(const float* G, const float* x, const f
     if (frames == 0) return 0;
     SmallLists L{vals, lptr, lsrc, lid, tptr, tsrc, tid, nnz};
     const long long tiles = ((long long)frames + 15) / 16;
-    int grid = num_sms() * 2;
+    int grid = num_sms() * 4;
     if (grid > tiles) grid = (int)tiles;
     gcn_small_post_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(G, x, L, dx, dvals, sg1, sz, bn_p, bn_m1, bn_c, bn_mu,
                                                              dbt, frames, V, K, Cin, Cout);
