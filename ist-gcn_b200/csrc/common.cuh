@@ -299,6 +299,12 @@ __device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const unsigned
     return step ? seed + static_cast<uint64_t>(*step) * 0xD1B54A32D192ED03ull : seed;
 }
 
+// one 16-byte reduction into global memory (four scalar atomicAdds cost four L2 transactions)
+__device__ __forceinline__ void red_add4(float* p, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
 __device__ __forceinline__ float4 ld4(const float* p) {
     return *reinterpret_cast<const float4*>(p);
 }

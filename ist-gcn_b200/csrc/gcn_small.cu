@@ -322,10 +322,7 @@ __global__ void joint_colsum_kernel(const float* __restrict__ a, float* __restri
         const float4 v = ld4(a + (size_t)f * n + j4 * 4);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    atomicAdd(sums + j4 * 4 + 0, s.x);
-    atomicAdd(sums + j4 * 4 + 1, s.y);
-    atomicAdd(sums + j4 * 4 + 2, s.z);
-    atomicAdd(sums + j4 * 4 + 3, s.w);
+    red_add4(sums + j4 * 4, s);
 }
 
 // dx[(f,v)][c] = sum_k sum_{j in t(k,v)} vals_j G[(f,w_j)][k*4+c]  (written),
@@ -486,6 +483,8 @@ ISTGCN_API int istgcn_gcn_small_bwd(const float* g1, const float* z, const float
 ISTGCN_API int istgcn_joint_colsum(const float* a, float* sums, int frames, int V, int C, istgcn_stream_t s) {
     ISTGCN_REQUIRE(a && sums, ISTGCN_E_ARG, "joint_colsum: null pointer");
     ISTGCN_REQUIRE(C % 4 == 0 && V >= 1, ISTGCN_E_SHAPE, "joint_colsum: C=%d V=%d", C, V);
+    ISTGCN_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(sums)) & 15) == 0, ISTGCN_E_ARG,
+                   "joint_colsum: pointers must be 16-byte aligned");
     if (frames == 0) return 0;
     const int n = V * C;
     int slabs = (num_sms() * 4 * 256) / (n / 4);      // long slabs: one atomic per thread and column at the end

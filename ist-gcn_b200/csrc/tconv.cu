@@ -111,10 +111,7 @@ __global__ void bn_back_colsum_kernel(const float* __restrict__ g, const float* 
             st4(dz + off, d);
             a.x += d.x; a.y += d.y; a.z += d.z; a.w += d.w;
         }
-        atomicAdd(colsum + j4 * 4 + 0, a.x);
-        atomicAdd(colsum + j4 * 4 + 1, a.y);
-        atomicAdd(colsum + j4 * 4 + 2, a.z);
-        atomicAdd(colsum + j4 * 4 + 3, a.w);
+        red_add4(colsum + j4 * 4, a);
     }
 }
 
@@ -240,6 +237,8 @@ static int launch_bn_back_colsum(const float* g, const float* z, const float* p,
                                  const float* c, const float* mean, float* dz, float* colsum, int frames,
                                  int V, int C, const BnBwdFold& fold, istgcn_stream_t s) {
     ISTGCN_REQUIRE(C % 4 == 0 && V >= 1, ISTGCN_E_SHAPE, "bn_back_colsum: C=%d V=%d", C, V);
+    ISTGCN_REQUIRE((reinterpret_cast<uintptr_t>(colsum) & 15) == 0, ISTGCN_E_ARG,
+                   "bn_back_colsum: colsum must be 16-byte aligned");
     if (frames == 0) return 0;
     const int n = V * C;
     int slabs = (num_sms() * 8 * 256) / (n / 4);
