@@ -491,7 +491,11 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_up_kernel(BwdU
             if (g == 0 && slice == 0) atomicAdd(&s_dbe[nt * 8 + 2 * t + e], v);
         }
     __syncthreads();
-    for (int i = tid; i < BP * C; i += NTHR) atomicAdd(&p.dWu[i], s_dW[i]);
+    if ((reinterpret_cast<uintptr_t>(p.dWu) & 15) == 0) {          // 16-byte reductions: a quarter of the L2 traffic
+        for (int i = tid; i < BP * C / 4; i += NTHR) red_add4(p.dWu + 4 * i, *reinterpret_cast<const float4*>(s_dW + 4 * i));
+    } else {
+        for (int i = tid; i < BP * C; i += NTHR) atomicAdd(&p.dWu[i], s_dW[i]);
+    }
     for (int i = tid; i < C; i += NTHR) atomicAdd(&p.dbu[i], s_dbu[i]);
     for (int i = tid; i < BP; i += NTHR) atomicAdd(&p.dbeff[i], s_dbe[i]);
 }
@@ -619,9 +623,17 @@ __global__ void __launch_bounds__(kT2HeavyWarps * 32, 3) tcn2_bwd_down_kernel(Bw
             }
         }
     __syncthreads();
-    for (int i = tid; i < BP * C; i += NTHR) {
-        const int j = i / C, c = i - j * C;
-        atomicAdd(&p.dWd[c * BP + j], s_dW[i]);
+    if ((reinterpret_cast<uintptr_t>(p.dWd) & 15) == 0) {          // dWd[c][j .. j+3] in one 16-byte reduction
+        for (int i = tid; i < C * BP / 4; i += NTHR) {
+            const int c = i / (BP / 4), j = (i - c * (BP / 4)) * 4;
+            red_add4(p.dWd + c * BP + j, make_float4(s_dW[j * C + c], s_dW[(j + 1) * C + c], s_dW[(j + 2) * C + c],
+                                                     s_dW[(j + 3) * C + c]));
+        }
+    } else {
+        for (int i = tid; i < BP * C; i += NTHR) {
+            const int j = i / C, c = i - j * C;
+            atomicAdd(&p.dWd[c * BP + j], s_dW[i]);
+        }
     }
     for (int c = tid; c < C; c += NTHR) {
         atomicAdd(&p.sg[c], (double)s_sg[c]);

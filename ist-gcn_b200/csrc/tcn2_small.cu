@@ -304,7 +304,12 @@ __global__ void __launch_bounds__(kThr, 2) tcn2_small_dw_kernel(SmallP p) {
             }
     }
     __syncthreads();
-    for (int i = tid; i < kTaps * BP * BP; i += kThr) atomicAdd(&p.out[i], s_dW[i]);
+    if ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+        for (int i = tid; i < kTaps * BP * BP / 4; i += kThr)
+            red_add4(p.out + 4 * i, make_float4(s_dW[4 * i], s_dW[4 * i + 1], s_dW[4 * i + 2], s_dW[4 * i + 3]));
+    } else {
+        for (int i = tid; i < kTaps * BP * BP; i += kThr) atomicAdd(&p.out[i], s_dW[i]);
+    }
 }
 
 template <typename K>
