@@ -157,8 +157,14 @@ tconv_dw_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_consta
                     tmem_ld32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + mb * nb + c0, v);
                     if (R < rows_total) {
                         float* dst = p.dW + (size_t)R * p.Cout + col0 + c0;
+                        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {     // 16-byte reductions
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+                            for (int j = 0; j < 32; j += 4)
+                                red_add4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, v[j]);
+                        }
                     }
                 }
             }
